@@ -1,0 +1,147 @@
+// The whole loss step behind one C-ABI call (upstream call site: criterion(model_out, t) followed by
+// loss.backward(), model.py:235-237), plus the small ABI utilities.
+#include "pgasr_common.cuh"
+
+namespace pgasr {
+
+thread_local int g_last_cuda_error = 0;
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct StepWorkspace {
+    uint8_t* samples; uint8_t* hyps;
+    int32_t* hyp_len; int32_t* dist;
+    float* logp; float* rewards; float* adv; float* loss_terms; float* nll; float* probs;
+    void* ctc; size_t ctc_bytes; size_t total;
+};
+
+static StepWorkspace carve(void* base, int B, int T, int V, int K, int Lmax) {
+    StepWorkspace w;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align256(bytes); return r; };
+    const size_t BK = (size_t)B * K;
+    w.samples = reinterpret_cast<uint8_t*>(take(BK * T));
+    w.hyps = reinterpret_cast<uint8_t*>(take(BK * T));
+    w.hyp_len = reinterpret_cast<int32_t*>(take(BK * 4));
+    w.dist = reinterpret_cast<int32_t*>(take(BK * 4));
+    w.logp = reinterpret_cast<float*>(take(BK * 4));
+    w.rewards = reinterpret_cast<float*>(take(BK * 4));
+    w.adv = reinterpret_cast<float*>(take(BK * 4));
+    w.loss_terms = reinterpret_cast<float*>(take((size_t)B * 4));
+    w.nll = reinterpret_cast<float*>(take((size_t)B * 4));
+    w.probs = reinterpret_cast<float*>(take((size_t)B * T * V * 4));
+    w.ctc_bytes = pgasr_ctc_workspace_bytes(B, T, V, Lmax);
+    w.ctc = take(w.ctc_bytes);
+    w.total = off;
+    return w;
+}
+
+// loss = w_pg / (B K) * sum_b loss_terms[b] + w_ctc / B * sum_b nll[b]; one warp, fixed order.
+__global__ void finalize_loss_kernel(const float* __restrict__ loss_terms, const float* __restrict__ nll,
+                                     int B, int K, float w_pg, float w_ctc, float* __restrict__ loss) {
+    float a = 0.0f, c = 0.0f;
+    for (int b = threadIdx.x; b < B; b += 32) {
+        if (loss_terms) a += loss_terms[b];
+        if (nll) c += nll[b];
+    }
+    a = warp_sum(a);
+    c = warp_sum(c);
+    if (threadIdx.x == 0) {
+        float l = 0.0f;
+        if (loss_terms) l += w_pg * a / ((float)B * (float)K);
+        if (nll) l += w_ctc * c / (float)B;
+        loss[0] = l;
+    }
+}
+
+__global__ void copy_bytes_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+}  // namespace pgasr
+
+extern "C" int pgasr_abi_version(void) { return PGASR_ABI_VERSION; }
+
+extern "C" const char* pgasr_status_string(int status) {
+    switch (status) {
+        case PGASR_OK: return "ok";
+        case PGASR_ERR_INVALID_ARG: return "invalid argument";
+        case PGASR_ERR_UNSUPPORTED: return "unsupported size for this build";
+        case PGASR_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        case PGASR_ERR_WORKSPACE: return "workspace too small";
+        case PGASR_ERR_CUDA: return "CUDA error (see pgasr_last_cuda_error)";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int pgasr_last_cuda_error(void) { return pgasr::g_last_cuda_error; }
+
+extern "C" int pgasr_device_check(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PGASR_ERR_NO_DEVICE;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+        return PGASR_ERR_NO_DEVICE;
+    return major == 10 ? PGASR_OK : PGASR_ERR_NO_DEVICE;
+}
+
+extern "C" size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax) {
+    if (B < 0 || T <= 0 || V <= 0 || K <= 0 || Lmax <= 0) return 0;
+    return pgasr::carve(nullptr, B, T, V, K, Lmax).total;
+}
+
+extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, const int32_t* in_len,
+                                 const int32_t* tgt_len, const float* uniforms, uint64_t seed, int B, int T,
+                                 int V, int K, int Lmax, int blank, int reward_mode, int baseline_mode,
+                                 float baseline_value, float w_pg, float w_ctc, float* loss, float* dlogits,
+                                 float* rewards, float* logp, int32_t* hyp_len, int32_t* dist, float* nll,
+                                 uint8_t* samples, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace pgasr;
+    if (!logits || !targets || !loss || !dlogits || !workspace || B <= 0 || T <= 0 || V <= 0 || K <= 0 ||
+        Lmax <= 0 || blank < 0 || blank >= V)
+        return PGASR_ERR_INVALID_ARG;
+    StepWorkspace w = carve(workspace, B, T, V, K, Lmax);
+    if (w.ctc_bytes == 0) return PGASR_ERR_UNSUPPORTED;
+    if (workspace_bytes < w.total) return PGASR_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    uint8_t* smp = samples ? samples : w.samples;
+    float* lp = logp ? logp : w.logp;
+    int32_t* hl = hyp_len ? hyp_len : w.hyp_len;
+    int32_t* ds = dist ? dist : w.dist;
+    float* rw = rewards ? rewards : w.rewards;
+    float* nl = nll ? nll : w.nll;
+    const bool do_pg = w_pg != 0.0f, do_ctc = w_ctc != 0.0f;
+    const bool dense = baseline_mode != PGASR_BASELINE_MEAN;   // sum_k A_k == 0 under the per-utterance mean
+    int rc;
+    if (do_pg || do_ctc) {
+        // the sampler also produces the softmax the CTC lattice and the dense PG term read
+        rc = pgasr_softmax_sample(logits, in_len, uniforms, seed, B, T, V, K, smp, lp, w.probs, stream);
+        if (rc) return rc;
+    }
+    if (do_pg) {
+        rc = pgasr_collapse_u8(smp, in_len, K, B * K, T, blank, w.hyps, hl, stream);
+        if (rc) return rc;
+        rc = pgasr_edit_distance_u8(w.hyps, hl, B * K, T, targets, tgt_len, K, Lmax, V, ds, nullptr, stream);
+        if (rc) return rc;
+        rc = pgasr_pg_advantages(ds, tgt_len, lp, B, K, Lmax, reward_mode, baseline_mode, baseline_value, rw,
+                                 w.adv, w.loss_terms, stream);
+        if (rc) return rc;
+    }
+    if (do_ctc) {
+        rc = pgasr_ctc_loss_grad(logits, w.probs, targets, in_len, tgt_len, B, T, V, Lmax, blank,
+                                 w_ctc / (float)B, 0, nl, dlogits, w.ctc, w.ctc_bytes, stream);
+        if (rc) return rc;
+    }
+    if (do_pg) {
+        rc = pgasr_pg_grad(smp, w.adv, dense ? w.probs : nullptr, in_len, B, T, V, K,
+                           w_pg / ((float)B * (float)K), do_ctc ? 1 : 0, dlogits, stream);
+        if (rc) return rc;
+    }
+    if (!do_pg && !do_ctc) PGASR_CUDA_TRY(cudaMemsetAsync(dlogits, 0, (size_t)B * T * V * sizeof(float), st));
+    finalize_loss_kernel<<<1, 32, 0, st>>>(do_pg ? w.loss_terms : nullptr, do_ctc ? nl : nullptr, B, K, w_pg,
+                                           w_ctc, loss);
+    PGASR_LAUNCH_CHECK();
+    return PGASR_OK;
+}

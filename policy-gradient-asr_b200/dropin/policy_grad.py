@@ -1,0 +1,5 @@
+"""Top-level stand-in for upstream policy_grad.py: put <repo> and <repo>/policy-gradient-asr_b200/dropin on
+sys.path ahead of the upstream checkout and `import policy_grad` resolves here."""
+from pgasr_b200.policy_grad import *            # noqa: F401,F403
+from pgasr_b200 import policy_grad as _impl
+globals().update({k: getattr(_impl, k) for k in dir(_impl) if not k.startswith("__")})

@@ -1,0 +1,261 @@
+"""Batched tensor-level operators of the PG-loss + CTC hot path.
+
+Each function takes CUDA tensors, launches the sm_100a kernels of libpgasr_b200.so on torch's current
+stream through the C ABI (include/pgasr.h) and returns CUDA tensors.  torch is used for device memory
+and streams only.  There is no CPU path: a CPU tensor is a TypeError, a missing library a RuntimeError.
+"""
+import torch
+
+from . import _native
+
+REWARD_MODES = {"ed": 0, "cer": 1}
+BASELINE_MODES = {"none": 0, "mean": 1, "loo": 2, "value": 3}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (pgasr_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _opt_i32(t, name, n, device):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    t = t.to(device=device, dtype=torch.int32).contiguous()
+    if t.numel() != n:
+        raise ValueError(f"{name} must have {n} entries, got {t.numel()}")
+    return t
+
+
+def as_targets(targets, device):
+    """[B,Lmax] label ids, padded with 0 (upstream data.py:99) -> int32 on `device`."""
+    if not isinstance(targets, torch.Tensor):
+        targets = torch.as_tensor(targets)
+    if targets.dim() != 2:
+        raise ValueError("targets must be [B, Lmax]")
+    return targets.to(device=device, dtype=torch.int32).contiguous()
+
+
+def softmax_sample(logits, input_lengths=None, K=16, uniforms=None, seed=0, return_probs=False):
+    """Row a6.  logits [B,T,V] fp32 -> samples [B,K,T] uint8, logp [B,K] fp32 (and probs [B,T,V])."""
+    logits = _need(logits, torch.float32, "logits", 3)
+    B, T, V = logits.shape
+    if uniforms is not None:
+        uniforms = _need(uniforms, torch.float32, "uniforms", 3)
+        if uniforms.shape[0] != B or uniforms.shape[2] != T:
+            raise ValueError("uniforms must be [B,K,T]")
+        K = uniforms.shape[1]
+    in_len = _opt_i32(input_lengths, "input_lengths", B, logits.device)
+    samples = torch.empty((B, K, T), dtype=torch.uint8, device=logits.device)
+    logp = torch.empty((B, K), dtype=torch.float32, device=logits.device)
+    probs = torch.empty_like(logits) if return_probs else None
+    _native.call("pgasr_softmax_sample", _ptr(logits), _ptr(in_len), _ptr(uniforms), int(seed) & (2**64 - 1),
+                 B, T, V, K, _ptr(samples), _ptr(logp), _ptr(probs), _stream())
+    return (samples, logp, probs) if return_probs else (samples, logp)
+
+
+def collapse(seqs, lengths=None, rows_per_len=1, blank=0):
+    """Row a3.  seqs [N,T] (or [B,K,T]) uint8 -> (collapsed rows, lengths).  blank=None: merge repeats only
+    (exactly upstream collapse_fn, CTCdecoder.py:119-131); blank=0: then drop blanks."""
+    seqs = _need(seqs, torch.uint8, "seqs")
+    shape = seqs.shape
+    T = shape[-1]
+    flat = seqs.reshape(-1, T)
+    N = flat.shape[0]
+    if seqs.dim() == 3 and lengths is not None and rows_per_len == 1:
+        rows_per_len = shape[1]
+    n_len = (N + rows_per_len - 1) // rows_per_len
+    lengths = _opt_i32(lengths, "lengths", n_len, seqs.device)
+    out = torch.empty_like(flat)
+    out_len = torch.empty((N,), dtype=torch.int32, device=seqs.device)
+    _native.call("pgasr_collapse_u8", _ptr(flat), _ptr(lengths), rows_per_len, N, T,
+                 -1 if blank is None else int(blank), _ptr(out), _ptr(out_len), _stream())
+    return out.reshape(shape), out_len.reshape(shape[:-1])
+
+
+def edit_distance(hyps, hyp_len, refs, ref_len=None, rows_per_ref=None, vocab=256, last_col=False):
+    """Rows a1/a4.  hyps [N,Th] (or [B,K,Th]) uint8, hyp_len [N], refs [G,Lr] int32 with N = G*rows_per_ref
+    -> dist [N] int32 (and last_col [N,Th+1]: ED(ref, hyp[:i])).  Bit-parallel kernel; len(ref) <= 512."""
+    hyps = _need(hyps, torch.uint8, "hyps")
+    shape = hyps.shape
+    Th = shape[-1]
+    flat = hyps.reshape(-1, Th)
+    N = flat.shape[0]
+    refs = _need(refs, torch.int32, "refs", 2)
+    G, Lr = refs.shape
+    if rows_per_ref is None:
+        rows_per_ref = N // max(G, 1)
+    if G * rows_per_ref != N:
+        raise ValueError("hyps rows must be refs rows * rows_per_ref")
+    hyp_len = _opt_i32(hyp_len, "hyp_len", N, hyps.device)
+    ref_len = _opt_i32(ref_len, "ref_len", G, hyps.device)
+    dist = torch.empty((N,), dtype=torch.int32, device=hyps.device)
+    col = torch.zeros((N, Th + 1), dtype=torch.int32, device=hyps.device) if last_col else None
+    _native.call("pgasr_edit_distance_u8", _ptr(flat), _ptr(hyp_len), N, Th, _ptr(refs), _ptr(ref_len),
+                 rows_per_ref, Lr, int(vocab), _ptr(dist), _ptr(col), _stream())
+    dist = dist.reshape(shape[:-1])
+    return (dist, col.reshape(*shape[:-1], Th + 1)) if last_col else dist
+
+
+def edit_distance_tokens(hyps, hyp_len, refs, ref_len=None, rows_per_ref=1):
+    """Row a1 for arbitrary int32 tokens (word ids, code points): anti-diagonal wavefront kernel."""
+    hyps = _need(hyps, torch.int32, "hyps", 2)
+    refs = _need(refs, torch.int32, "refs", 2)
+    N, Th = hyps.shape
+    G, Lr = refs.shape
+    if G * rows_per_ref != N:
+        raise ValueError("hyps rows must be refs rows * rows_per_ref")
+    hyp_len = _opt_i32(hyp_len, "hyp_len", N, hyps.device)
+    ref_len = _opt_i32(ref_len, "ref_len", G, hyps.device)
+    dist = torch.empty((N,), dtype=torch.int32, device=hyps.device)
+    _native.call("pgasr_edit_distance_i32", _ptr(hyps), _ptr(hyp_len), N, Th, _ptr(refs), _ptr(ref_len),
+                 rows_per_ref, Lr, _ptr(dist), _stream())
+    return dist
+
+
+def pg_advantages(dist, target_lengths, logp, reward="ed", baseline="mean", baseline_value=0.0, Lmax=0):
+    """Row a7 (first half).  -> rewards [B,K], adv [B,K], loss_terms [B] (= -sum_k adv*logp)."""
+    dist = _need(dist, torch.int32, "dist", 2)
+    logp = _need(logp, torch.float32, "logp", 2)
+    B, K = dist.shape
+    tl = _opt_i32(target_lengths, "target_lengths", B, dist.device)
+    rewards = torch.empty((B, K), dtype=torch.float32, device=dist.device)
+    adv = torch.empty_like(rewards)
+    terms = torch.empty((B,), dtype=torch.float32, device=dist.device)
+    _native.call("pgasr_pg_advantages", _ptr(dist), _ptr(tl), _ptr(logp), B, K, int(Lmax), REWARD_MODES[reward],
+                 BASELINE_MODES[baseline], float(baseline_value), _ptr(rewards), _ptr(adv), _ptr(terms), _stream())
+    return rewards, adv, terms
+
+
+def pg_grad(samples, adv, input_lengths=None, probs=None, V=None, scale=1.0, out=None):
+    """Row a7 (second half).  dlogits = scale * (probs * sum_k adv - scatter_k adv) -> [B,T,V].  With `out`
+    the result is accumulated into it."""
+    samples = _need(samples, torch.uint8, "samples", 3)
+    adv = _need(adv, torch.float32, "adv", 2)
+    B, K, T = samples.shape
+    if probs is not None:
+        probs = _need(probs, torch.float32, "probs", 3)
+        V = probs.shape[2]
+    if V is None:
+        raise ValueError("V is required when probs is None")
+    in_len = _opt_i32(input_lengths, "input_lengths", B, samples.device)
+    acc = out is not None
+    if out is None:
+        out = torch.empty((B, T, V), dtype=torch.float32, device=samples.device)
+    else:
+        out = _need(out, torch.float32, "out", 3)
+    _native.call("pgasr_pg_grad", _ptr(samples), _ptr(adv), _ptr(probs), _ptr(in_len), B, T, V, K, float(scale),
+                 1 if acc else 0, _ptr(out), _stream())
+    return out
+
+
+def ctc_loss_grad(logits, targets, input_lengths=None, target_lengths=None, blank=0, grad_scale=1.0,
+                  probs=None, out=None):
+    """Row a8.  -> nll [B] fp32, dlogits [B,T,V] = grad_scale * d nll_b / d logits_b.  With `out` the
+    gradient is accumulated into it."""
+    logits = _need(logits, torch.float32, "logits", 3)
+    B, T, V = logits.shape
+    targets = as_targets(targets, logits.device)
+    Lmax = targets.shape[1]
+    in_len = _opt_i32(input_lengths, "input_lengths", B, logits.device)
+    tg_len = _opt_i32(target_lengths, "target_lengths", B, logits.device)
+    if probs is not None:
+        probs = _need(probs, torch.float32, "probs", 3)
+    nll = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    acc = out is not None
+    dlogits = _need(out, torch.float32, "out", 3) if acc else torch.empty_like(logits)
+    nbytes = _native.lib().pgasr_ctc_workspace_bytes(B, T, V, Lmax)
+    if nbytes == 0:
+        raise _native.PgasrError("pgasr_ctc_workspace_bytes", -2, "unsupported size (Lmax <= 511)")
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=logits.device)
+    _native.call("pgasr_ctc_loss_grad", _ptr(logits), _ptr(probs), _ptr(targets), _ptr(in_len), _ptr(tg_len),
+                 B, T, V, Lmax, int(blank), float(grad_scale), 1 if acc else 0, _ptr(nll), _ptr(dlogits),
+                 _ptr(ws), nbytes, _stream())
+    return nll, dlogits
+
+
+def nll_sum_forward(inp, target, ignore_index=-1):
+    """Row a5 (upstream loss.py:13-17).  inp [L,B,V] fp32 log-probs, target [B,L] int64 -> 0-d loss."""
+    inp = _need(inp, torch.float32, "inp", 3)
+    target = _need(target, torch.int64, "target", 2)
+    L, B, V = inp.shape
+    if target.shape[0] != B or target.shape[1] < L:
+        raise IndexError("target must be [B, >=L]")
+    if target.shape[1] != L:
+        target = target[:, :L].contiguous()
+    loss = torch.empty((1,), dtype=torch.float32, device=inp.device)
+    _native.call("pgasr_nll_sum_forward", _ptr(inp), _ptr(target), L, B, V, int(ignore_index), _ptr(loss), _stream())
+    return loss[0]
+
+
+def nll_sum_backward(target, grad_out, L, B, V, ignore_index=-1):
+    target = _need(target, torch.int64, "target", 2)
+    if target.shape[1] != L:
+        target = target[:, :L].contiguous()
+    grad_out = _need(grad_out.reshape(1), torch.float32, "grad_out")
+    g = torch.empty((L, B, V), dtype=torch.float32, device=target.device)
+    _native.call("pgasr_nll_sum_backward", _ptr(target), _ptr(grad_out), L, B, V, int(ignore_index), _ptr(g), _stream())
+    return g
+
+
+class StepWorkspace:
+    """Device scratch of pgasr_pg_ctc_step, sized once per (B,T,V,K,Lmax) and reused across steps."""
+
+    def __init__(self, B, T, V, K, Lmax, device):
+        self.key = (B, T, V, K, Lmax)
+        self.nbytes = _native.lib().pgasr_pg_ctc_step_workspace_bytes(B, T, V, K, Lmax)
+        if self.nbytes == 0:
+            raise _native.PgasrError("pgasr_pg_ctc_step_workspace_bytes", -2, "unsupported size")
+        self.buf = torch.empty((self.nbytes,), dtype=torch.uint8, device=device)
+
+
+def pg_ctc_step(logits, targets, input_lengths=None, target_lengths=None, K=16, blank=0, reward="ed",
+                baseline="mean", baseline_value=0.0, pg_weight=1.0, ctc_weight=1.0, uniforms=None, seed=0,
+                workspace=None, want=("rewards", "nll")):
+    """The whole loss step (rows a1-a8 chained) in one C-ABI call.
+    Returns a dict: loss (0-d), dlogits [B,T,V], plus the optional outputs named in `want` out of
+    rewards, logp, hyp_len, dist, nll, samples."""
+    logits = _need(logits, torch.float32, "logits", 3)
+    B, T, V = logits.shape
+    dev = logits.device
+    targets = as_targets(targets, dev)
+    Lmax = targets.shape[1]
+    if uniforms is not None:
+        uniforms = _need(uniforms, torch.float32, "uniforms", 3)
+        K = uniforms.shape[1]
+    in_len = _opt_i32(input_lengths, "input_lengths", B, dev)
+    tg_len = _opt_i32(target_lengths, "target_lengths", B, dev)
+    if workspace is None or workspace.key != (B, T, V, K, Lmax):
+        workspace = StepWorkspace(B, T, V, K, Lmax, dev)
+    out = {"loss": torch.empty((1,), dtype=torch.float32, device=dev), "dlogits": torch.empty_like(logits)}
+    shapes = {"rewards": ((B, K), torch.float32), "logp": ((B, K), torch.float32),
+              "hyp_len": ((B, K), torch.int32), "dist": ((B, K), torch.int32),
+              "nll": ((B,), torch.float32), "samples": ((B, K, T), torch.uint8)}
+    for name in want:
+        shp, dt = shapes[name]
+        out[name] = torch.empty(shp, dtype=dt, device=dev)
+    _native.call("pgasr_pg_ctc_step", _ptr(logits), _ptr(targets), _ptr(in_len), _ptr(tg_len), _ptr(uniforms),
+                 int(seed) & (2**64 - 1), B, T, V, K, Lmax, int(blank), REWARD_MODES[reward],
+                 BASELINE_MODES[baseline], float(baseline_value), float(pg_weight), float(ctc_weight),
+                 _ptr(out["loss"]), _ptr(out["dlogits"]), _ptr(out.get("rewards")), _ptr(out.get("logp")),
+                 _ptr(out.get("hyp_len")), _ptr(out.get("dist")), _ptr(out.get("nll")), _ptr(out.get("samples")),
+                 _ptr(workspace.buf), workspace.nbytes, _stream())
+    out["loss"] = out["loss"][0]
+    out["workspace"] = workspace
+    return out
