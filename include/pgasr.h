@@ -62,6 +62,7 @@ enum { PGASR_BASELINE_NONE = 0, PGASR_BASELINE_MEAN = 1, PGASR_BASELINE_LOO = 2,
 PGASR_API int         pgasr_abi_version(void);
 PGASR_API const char* pgasr_status_string(int status);
 PGASR_API int         pgasr_last_cuda_error(void);          /* cudaError_t of the last failing CUDA call (thread local) */
+PGASR_API uint64_t    pgasr_launch_count(void);             /* kernels launched so far by the calling thread */
 PGASR_API int         pgasr_device_check(void);             /* PGASR_OK iff the current device is sm_10x */
 
 /* ---- a6: fused softmax + inverse-CDF categorical sampler ------------------------------------

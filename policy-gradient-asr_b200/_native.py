@@ -15,6 +15,7 @@ SIGNATURES = {
     "pgasr_abi_version": (_i, []),
     "pgasr_status_string": (C.c_char_p, [_i]),
     "pgasr_last_cuda_error": (_i, []),
+    "pgasr_launch_count": (_u64, []),
     "pgasr_device_check": (_i, []),
     "pgasr_softmax_sample": (_i, [_vp, _vp, _vp, _u64, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pgasr_collapse_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

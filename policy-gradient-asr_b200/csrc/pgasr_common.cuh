@@ -8,6 +8,7 @@
 namespace pgasr {
 
 extern thread_local int g_last_cuda_error;
+extern thread_local unsigned long long g_launches;   // kernels launched by this thread (bench.py's gpu_launches)
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
@@ -20,7 +21,11 @@ inline int cuda_fail(cudaError_t e) {
         if (_e != cudaSuccess) return ::pgasr::cuda_fail(_e);  \
     } while (0)
 
-#define PGASR_LAUNCH_CHECK() PGASR_CUDA_TRY(cudaGetLastError())
+#define PGASR_LAUNCH_CHECK()                \
+    do {                                    \
+        ++::pgasr::g_launches;              \
+        PGASR_CUDA_TRY(cudaGetLastError()); \
+    } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

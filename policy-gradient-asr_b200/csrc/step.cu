@@ -5,6 +5,7 @@
 namespace pgasr {
 
 thread_local int g_last_cuda_error = 0;
+thread_local unsigned long long g_launches = 0;
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -77,6 +78,8 @@ extern "C" const char* pgasr_status_string(int status) {
 }
 
 extern "C" int pgasr_last_cuda_error(void) { return pgasr::g_last_cuda_error; }
+
+extern "C" uint64_t pgasr_launch_count(void) { return pgasr::g_launches; }
 
 extern "C" int pgasr_device_check(void) {
     int dev = 0;

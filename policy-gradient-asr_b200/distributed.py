@@ -19,9 +19,13 @@ def shard_range(n, rank, world):
 
 
 def balanced_assignment(lengths, world):
-    """Length-sorted round-robin: utterance indices per rank so ragged T balances across GPUs."""
-    order = sorted(range(len(lengths)), key=lambda i: -int(lengths[i]))
-    return [order[r::world] for r in range(world)]
+    """Longest-first greedy assignment: utterance indices per rank so ragged T balances across GPUs."""
+    parts, loads = [[] for _ in range(world)], [0] * world
+    for i in sorted(range(len(lengths)), key=lambda i: -int(lengths[i])):
+        r = loads.index(min(loads))
+        parts[r].append(i)
+        loads[r] += int(lengths[i])
+    return parts
 
 
 def reward_stats(rewards):

@@ -1,0 +1,383 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the upstream golden vectors.
+
+Bars: samples / collapsed hypotheses / edit distances / rewards bit-exact; CTC loss, CTC gradient, sequence
+log-probabilities and the policy gradient within 1e-4 relative (gradients: max abs error over the tensor
+relative to its max abs value), fp32, as BASELINE.json's north_star states.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport
+from tests.synth import make_batch
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def dev_t(a, device, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(device=device, dtype=dtype) if dtype else t.to(device)
+
+
+def rel_err(got, want):
+    want = np.asarray(want, np.float64)
+    got = np.asarray(got, np.float64)
+    scale = max(np.abs(want).max(), 1e-30)
+    return np.abs(got - want).max() / scale
+
+
+def enc(s):
+    return [ord(c) for c in s]
+
+
+# ---------------------------------------------------------------- a6 sampler
+@pytest.mark.parametrize("B,T,V,K,ragged", [(3, 37, 30, 4, True), (2, 300, 5, 16, False), (64, 500, 30, 16, False),
+                                            (2, 700, 32, 7, True), (1, 1, 2, 1, False)])
+def test_sampler_bit_exact_injected_uniforms(cuda, B, T, V, K, ragged):
+    from pgasr_b200 import functional as F
+    logits, _, in_len, _, uni = make_batch(B, T, V, K, max(T // 5, 1), seed=B + T, ragged=ragged)
+    s_ref, lp_ref = cport.softmax_sample(logits, in_len, uni)
+    s, lp, probs = F.softmax_sample(dev_t(logits, cuda), dev_t(in_len, cuda), uniforms=dev_t(uni, cuda), return_probs=True)
+    assert np.array_equal(s.cpu().numpy(), s_ref)
+    assert rel_err(lp.cpu().numpy(), lp_ref) < RTOL
+    p_ref = torch.softmax(torch.tensor(logits, dtype=torch.float64), -1).numpy()
+    for b in range(B):
+        p_ref[b, in_len[b]:] = 0
+    assert np.abs(probs.cpu().numpy() - p_ref).max() < 1e-6
+
+
+def test_sampler_bit_exact_philox(cuda):
+    from pgasr_b200 import functional as F
+    logits, _, in_len, _, _ = make_batch(5, 211, 30, 16, 10, seed=9, ragged=True)
+    for seed, K in [(0x5EED, 16), (2**63 + 12345, 6)]:
+        s_ref, lp_ref = cport.softmax_sample(logits, in_len, None, seed=seed, K=K)
+        s, lp = F.softmax_sample(dev_t(logits, cuda), dev_t(in_len, cuda), K=K, seed=seed)
+        assert np.array_equal(s.cpu().numpy(), s_ref)
+        assert rel_err(lp.cpu().numpy(), lp_ref) < RTOL
+
+
+def test_sampler_extreme_logits(cuda):
+    from pgasr_b200 import functional as F
+    rng = np.random.default_rng(0)
+    logits = (rng.standard_normal((2, 64, 30)) * 40).astype(np.float32)      # exp underflow below -87
+    logits[0, 0, :] = 0.0
+    logits[0, 1, :] = -1e4
+    logits[0, 1, 7] = 50.0
+    uni = np.minimum(rng.random((2, 8, 64), dtype=np.float32), np.float32(1 - 2**-24))
+    uni[0, 0, :] = 0.0
+    uni[0, 1, :] = np.float32(1 - 2**-24)
+    s_ref, _ = cport.softmax_sample(logits, None, uni)
+    s, _ = F.softmax_sample(dev_t(logits, cuda), uniforms=dev_t(uni, cuda))
+    assert np.array_equal(s.cpu().numpy(), s_ref)
+    assert (s_ref[0, :, 1] == 7).all()
+
+
+# ---------------------------------------------------------------- a3 collapse
+def test_collapse_golden_and_random(cuda, golden):
+    from pgasr_b200 import functional as F
+    for e in golden["collapse_paths"]:
+        x = dev_t(np.array([e["path"]], np.uint8), cuda)
+        out, n = F.collapse(x, blank=None)
+        assert out[0, :int(n[0])].cpu().tolist() == e["collapsed"]
+        out, n = F.collapse(x, blank=0)
+        assert out[0, :int(n[0])].cpu().tolist() == e["collapsed_no_blank"]
+    rng = np.random.default_rng(3)
+    B, K, T = 7, 5, 333
+    s = rng.integers(0, 4, (B, K, T)).astype(np.uint8)
+    in_len = rng.integers(0, T + 1, B).astype(np.int32)
+    in_len[0], in_len[1] = 0, T
+    out, n = F.collapse(dev_t(s, cuda), dev_t(in_len, cuda), blank=0)
+    out, n = out.cpu().numpy(), n.cpu().numpy()
+    for b in range(B):
+        for k in range(K):
+            want = cport.collapse(s[b, k, :in_len[b]].astype(np.int32), blank=0)
+            assert n[b, k] == len(want)
+            assert np.array_equal(out[b, k, :len(want)], want.astype(np.uint8))
+            assert (out[b, k, len(want):] == 0).all()
+
+
+def test_dropin_collapse_fn(cuda, golden):
+    import pgasr_b200
+    for e in golden["collapse_fn"]:
+        assert pgasr_b200.CTCdecoder.collapse_fn(e["in"]) == e["out"]
+    with pytest.raises(TypeError):
+        pgasr_b200.CTCdecoder.collapse_fn(["a", "a"])
+
+
+# ---------------------------------------------------------------- a1 / a2 / a4 edit distance
+def test_dropin_edit_dist_golden(cuda, golden):
+    import pgasr_b200
+    for e in golden["edit_dist"]:
+        a, b = e["ref"], e["hyp"]
+        if e["kind"] == "words":
+            a, b = a.split(" "), b.split(" ")
+        assert list(pgasr_b200.metrics.edit_dist(a, b)) == e["out"], e
+    for e in golden["evaluate"]:
+        assert list(pgasr_b200.metrics.evaluate(e["ref"], e["hyp"])) == e["out"]
+    with pytest.raises(ZeroDivisionError):
+        pgasr_b200.metrics.evaluate("", "abc")
+    assert pgasr_b200.metrics.edit_dist("", "") == (0, 0)
+
+
+def test_dropin_reward_golden(cuda, golden):
+    import pgasr_b200
+    for e in golden["reward_positions"]:
+        y, h = e["true_y"], e["hyp"]
+        got = [pgasr_b200.policy_grad.reward_from_hyp(y, h, t) for t in range(1, len(h) + 3)]
+        assert got == e["r"]
+    y, h = "hello world", "helo wurld!"
+    r = pgasr_b200.policy_grad.reward_all(y, h)
+    assert r[:10] == [2, 1, 1, 1, 1, 0, 1, 1, 1, -1] and sum(r) == 8
+    with pytest.raises(UnboundLocalError):
+        pgasr_b200.policy_grad.reward_from_hyp(y, h, 0)
+
+    class FakeDecoder:                      # reward() through the upstream call shape
+        def decode(self, probs, beam_size=100, blank=0):
+            assert beam_size == 5
+            return tuple(enc("heello")), 0.0
+    ind2char = {i: chr(i) for i in range(128)}
+    got = pgasr_b200.policy_grad.reward("hello", np.zeros((3, 3)), 2, ind2char, FakeDecoder())
+    assert got == -(cport.edit_distance(enc("hello"), enc("hel")) - cport.edit_distance(enc("hello"), enc("he")))
+
+
+@pytest.mark.parametrize("Lr,Th,V,rows", [(1, 50, 30, 3), (31, 40, 3, 4), (32, 33, 2, 16), (33, 64, 5, 1), (100, 500, 30, 16),
+                                          (128, 200, 4, 2), (129, 130, 30, 5), (256, 300, 8, 2), (400, 450, 30, 3), (512, 64, 6, 2)])
+def test_edit_distance_bit_exact_random(cuda, Lr, Th, V, rows):
+    from pgasr_b200 import functional as F
+    rng = np.random.default_rng(Lr * 1000 + Th)
+    G = 6
+    refs = rng.integers(1, V, (G, Lr)).astype(np.int32)
+    ref_len = rng.integers(0, Lr + 1, G).astype(np.int32)
+    ref_len[0], ref_len[1] = Lr, 0
+    hyps = rng.integers(1, V, (G * rows, Th)).astype(np.uint8)
+    hyp_len = rng.integers(0, Th + 1, G * rows).astype(np.int32)
+    hyp_len[0], hyp_len[1] = Th, 0
+    d, col = F.edit_distance(dev_t(hyps, cuda), dev_t(hyp_len, cuda), dev_t(refs, cuda), dev_t(ref_len, cuda),
+                             rows_per_ref=rows, vocab=V, last_col=True)
+    d2 = F.edit_distance(dev_t(hyps, cuda), dev_t(hyp_len, cuda), dev_t(refs, cuda), dev_t(ref_len, cuda),
+                         rows_per_ref=rows, vocab=V)
+    dw = F.edit_distance_tokens(dev_t(hyps.astype(np.int32), cuda), dev_t(hyp_len, cuda), dev_t(refs, cuda),
+                                dev_t(ref_len, cuda), rows_per_ref=rows)
+    d, col, d2, dw = d.cpu().numpy(), col.cpu().numpy(), d2.cpu().numpy(), dw.cpu().numpy()
+    for r in range(G * rows):
+        g = r // rows
+        want, wcol = cport.edit_distance(refs[g, :ref_len[g]], hyps[r, :hyp_len[r]].astype(np.int32), last_col=True)
+        assert d[r] == want and d2[r] == want and dw[r] == want, (r, d[r], d2[r], dw[r], want)
+        assert np.array_equal(col[r, :hyp_len[r] + 1], wcol)
+
+
+def test_wavefront_large_tokens(cuda):
+    from pgasr_b200 import functional as F
+    rng = np.random.default_rng(5)
+    refs = rng.integers(-2**31, 2**31 - 1, (3, 700), dtype=np.int64).astype(np.int32)
+    hyps = refs.copy()[:, :650]
+    hyps[:, ::7] += 1                                                    # substitutions
+    d = F.edit_distance_tokens(dev_t(hyps, cuda), None, dev_t(refs, cuda), None).cpu().numpy()
+    for i in range(3):
+        assert d[i] == cport.edit_distance(refs[i], hyps[i])
+
+
+# ---------------------------------------------------------------- a7 policy gradient
+@pytest.mark.parametrize("reward,baseline", [("ed", "mean"), ("cer", "loo"), ("cer", "none"), ("ed", "value")])
+def test_pg_advantages_and_grad(cuda, reward, baseline):
+    from pgasr_b200 import functional as F
+    B, T, V, K, L = 5, 61, 30, 16, 12
+    logits, targets, in_len, tgt_len, uni = make_batch(B, T, V, K, L, seed=11, ragged=True)
+    samples, logp = cport.softmax_sample(logits, in_len, uni)
+    _, _, dist = cport.collapse_score(samples, targets, in_len, tgt_len)
+    rm, bm = F.REWARD_MODES[reward], F.BASELINE_MODES[baseline]
+    loss, R, A, grad = cport.pg_loss_grad(logits, samples, logp, dist, in_len, tgt_len, L, rm, bm, -3.5)
+    R_g, A_g, terms = F.pg_advantages(dev_t(dist, cuda), dev_t(tgt_len, cuda), dev_t(logp.astype(np.float32), cuda),
+                                      reward=reward, baseline=baseline, baseline_value=-3.5, Lmax=L)
+    assert np.array_equal(R_g.cpu().numpy(), R)                           # one fp32 division: bit-exact
+    assert rel_err(A_g.cpu().numpy(), A) < RTOL
+    assert abs(float(terms.sum()) / (B * K) - loss) <= RTOL * abs(loss) + 1e-6
+    probs = torch.softmax(dev_t(logits, cuda), -1)
+    g = F.pg_grad(dev_t(samples, cuda), A_g, dev_t(in_len, cuda), probs=probs if baseline != "mean" else None,
+                  V=V, scale=1.0 / (B * K))
+    assert rel_err(g.cpu().numpy(), grad) < RTOL
+
+
+# ---------------------------------------------------------------- a8 CTC
+def ctc_case(cuda, B, T, V, L, seed, ragged, regime="random", repeat=False):
+    from pgasr_b200 import functional as F
+    logits, targets, in_len, tgt_len, _ = make_batch(B, T, V, 1, L, seed=seed, ragged=ragged, regime=regime)
+    if repeat:
+        targets[0, :min(4, L)] = targets[0, 0]
+    nll_ref, g_ref = cport.ctc_loss_grad(logits, targets, in_len, tgt_len)
+    nll, g = F.ctc_loss_grad(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda))
+    nll, g = nll.cpu().numpy(), g.cpu().numpy()
+    fin = np.isfinite(nll_ref)
+    assert np.array_equal(np.isfinite(nll), fin)
+    assert np.abs(nll[fin] - nll_ref[fin]).max() <= RTOL * np.abs(nll_ref[fin]).max()
+    assert np.abs(nll[fin] / nll_ref[fin] - 1).max() < RTOL
+    assert rel_err(g, g_ref) < RTOL
+    for b in range(B):
+        assert (g[b, in_len[b]:] == 0).all()
+    return nll, g
+
+
+@pytest.mark.parametrize("B,T,V,L,ragged,regime", [(4, 40, 7, 9, False, "random"), (6, 123, 30, 20, True, "random"),
+                                                   (64, 500, 30, 100, False, "random"), (8, 500, 30, 100, True, "peaky"),
+                                                   (3, 64, 5, 63, True, "random"), (2, 300, 30, 127, False, "random"),
+                                                   (2, 600, 30, 128, False, "random"), (2, 900, 12, 255, True, "peaky"),
+                                                   (2, 1100, 30, 400, False, "random"), (3, 9, 4, 1, False, "random")])
+def test_ctc_matches_oracle(cuda, B, T, V, L, ragged, regime):
+    ctc_case(cuda, B, T, V, L, seed=T + L, ragged=ragged, regime=regime, repeat=True)
+
+
+def test_ctc_config3_full_size(cuda):
+    """BASELINE.json configs[2]: B=128, T=1000, V=30, label length 200."""
+    ctc_case(cuda, 128, 1000, 30, 200, seed=1, ragged=False)
+
+
+def test_ctc_against_torch_cpu_double(cuda):
+    """Independent external check: torch.nn.functional.ctc_loss on the CPU in fp64."""
+    from pgasr_b200 import functional as F
+    B, T, V, L = 5, 150, 30, 25
+    logits, targets, in_len, tgt_len, _ = make_batch(B, T, V, 1, L, seed=77, ragged=True)
+    x = torch.tensor(logits, dtype=torch.float64, requires_grad=True)
+    want = torch.nn.functional.ctc_loss(torch.log_softmax(x, -1).transpose(0, 1), torch.tensor(targets, dtype=torch.long),
+                                        torch.tensor(in_len, dtype=torch.long), torch.tensor(tgt_len, dtype=torch.long),
+                                        blank=0, reduction="none")
+    want.sum().backward()
+    nll, g = F.ctc_loss_grad(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda))
+    assert np.abs(nll.cpu().numpy() / want.detach().numpy() - 1).max() < RTOL
+    assert rel_err(g.cpu().numpy(), x.grad.numpy()) < RTOL
+
+
+def test_ctc_edge_cases(cuda):
+    from pgasr_b200 import functional as F
+    logits, targets, in_len, tgt_len, _ = make_batch(4, 12, 6, 1, 5, seed=3)
+    targets[0] = [1, 1, 1, 1, 1]; in_len[0] = 6                           # infeasible: needs 9 frames
+    targets[1] = [1, 2, 3, 4, 1]; in_len[1] = 5                           # exactly feasible, single path family
+    tgt_len[2] = 0                                                        # empty transcript: all-blank path
+    in_len[3] = 1; tgt_len[3] = 1
+    nll_ref, g_ref = cport.ctc_loss_grad(logits, targets, in_len, tgt_len)
+    nll, g = F.ctc_loss_grad(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda))
+    nll, g = nll.cpu().numpy(), g.cpu().numpy()
+    assert math.isinf(nll[0]) and math.isinf(nll_ref[0]) and (g[0] == 0).all()
+    assert np.abs(nll[1:] / nll_ref[1:] - 1).max() < RTOL
+    assert rel_err(g, g_ref) < RTOL
+    # accumulate into an existing gradient and scale
+    base = torch.full((4, 12, 6), 0.25, device=cuda)
+    _, g2 = F.ctc_loss_grad(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda),
+                            grad_scale=0.5, out=base)
+    assert np.abs(g2.cpu().numpy() - (0.25 + 0.5 * g)).max() < 1e-6
+
+
+# ---------------------------------------------------------------- a5 customNLLLoss
+def test_custom_nll_loss(cuda, golden):
+    import pgasr_b200
+    g = golden["nll"]
+    inp = torch.tensor(g["inp"], dtype=torch.float32, device=cuda, requires_grad=True)
+    tgt = torch.tensor(g["target"], dtype=torch.long, device=cuda)
+    for c in g["cases"]:
+        inp.grad = None
+        crit = pgasr_b200.loss.customNLLLoss(ignore_index=c["ignore_index"])
+        loss = crit(inp, tgt)
+        assert abs(float(loss) - c["out"]) < 1e-5
+        (2.0 * loss).backward()
+        ign = c["ignore_index"] if c["ignore_index"] else -1
+        _, gref = cport.nll_sum(np.array(g["inp"], np.float32), np.array(g["target"]), ign, want_grad=True)
+        assert np.abs(inp.grad.cpu().numpy() - 2.0 * gref).max() < 1e-6
+
+
+# ---------------------------------------------------------------- whole step
+def step_case(cuda, B, T, V, K, L, seed, ragged, regime, reward="ed", baseline="mean", w_pg=1.0, w_ctc=1.0, philox=False):
+    from pgasr_b200 import functional as F
+    logits, targets, in_len, tgt_len, uni = make_batch(B, T, V, K, L, seed=seed, ragged=ragged, regime=regime)
+    kw = dict(reward_mode=F.REWARD_MODES[reward], baseline_mode=F.BASELINE_MODES[baseline], baseline_value=-2.0,
+              w_pg=w_pg, w_ctc=w_ctc)
+    loss_ref, R_ref, nll_ref, dl_ref = cport.pg_ctc_step(logits, targets, in_len, tgt_len, None if philox else uni,
+                                                         seed=99, K=K, **kw)
+    s_ref, _ = cport.softmax_sample(logits, in_len, None if philox else uni, seed=99, K=K)
+    h_ref, hl_ref, d_ref = cport.collapse_score(s_ref, targets, in_len, tgt_len)
+    out = F.pg_ctc_step(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda), K=K,
+                        reward=reward, baseline=baseline, baseline_value=-2.0, pg_weight=w_pg, ctc_weight=w_ctc,
+                        uniforms=None if philox else dev_t(uni, cuda), seed=99,
+                        want=("rewards", "nll", "logp", "dist", "hyp_len", "samples"))
+    assert np.array_equal(out["samples"].cpu().numpy(), s_ref)            # bit-exact
+    assert np.array_equal(out["hyp_len"].cpu().numpy(), hl_ref)
+    assert np.array_equal(out["dist"].cpu().numpy(), d_ref)
+    assert np.array_equal(out["rewards"].cpu().numpy(), R_ref)
+    if w_ctc:
+        assert np.abs(out["nll"].cpu().numpy() / nll_ref - 1).max() < RTOL
+    assert abs(float(out["loss"]) - loss_ref) <= RTOL * abs(loss_ref) + 1e-5
+    assert rel_err(out["dlogits"].cpu().numpy(), dl_ref) < RTOL
+    return out
+
+
+@pytest.mark.parametrize("B,T,V,K,L,ragged,regime", [(3, 50, 30, 4, 8, True, "random"), (64, 500, 30, 16, 100, False, "random"),
+                                                     (16, 500, 30, 16, 100, True, "peaky"), (2, 250, 30, 64, 40, False, "random"),
+                                                     (2, 1000, 30, 4, 200, True, "peaky")])
+def test_step_matches_oracle(cuda, B, T, V, K, L, ragged, regime):
+    step_case(cuda, B, T, V, K, L, seed=B * 7 + K, ragged=ragged, regime=regime)
+
+
+def test_step_modes(cuda):
+    step_case(cuda, 4, 80, 30, 8, 12, 1, True, "random", reward="cer", baseline="loo", w_pg=0.3, w_ctc=0.7)
+    step_case(cuda, 4, 80, 30, 8, 12, 2, True, "peaky", reward="cer", baseline="value", w_pg=1.0, w_ctc=0.0)
+    step_case(cuda, 4, 80, 30, 8, 12, 3, False, "random", reward="ed", baseline="none", w_pg=0.0, w_ctc=1.0)
+    step_case(cuda, 4, 80, 30, 16, 12, 4, True, "random", philox=True)
+
+
+def test_step_all_blank_hypotheses(cuda):
+    """Every sample collapses to the empty string: reward = -len(ref), advantage 0."""
+    from pgasr_b200 import functional as F
+    B, T, V, K, L = 2, 40, 30, 4, 6
+    logits, targets, in_len, tgt_len, uni = make_batch(B, T, V, K, L, seed=1)
+    logits[:, :, 0] += 80.0
+    out = F.pg_ctc_step(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda),
+                        uniforms=dev_t(uni, cuda), want=("rewards", "hyp_len", "dist"))
+    assert (out["hyp_len"].cpu().numpy() == 0).all()
+    assert (out["dist"].cpu().numpy() == L).all()
+    assert (out["rewards"].cpu().numpy() == -float(L)).all()
+
+
+def test_module_autograd_slot(cuda):
+    """PolicyGradCTCLoss in the upstream criterion slot: loss = criterion(model_out, t); loss.backward()."""
+    import pgasr_b200
+    B, T, V, K, L = 4, 60, 30, 8, 10
+    logits, targets, in_len, tgt_len, uni = make_batch(B, T, V, K, L, seed=8, ragged=True)
+    feats = torch.randn(B, T, 16, device=cuda)
+    head = torch.nn.Linear(16, V).to(cuda)
+    model_out = head(feats)
+    crit = pgasr_b200.PolicyGradCTCLoss(K=K, reward="cer", pg_weight=0.5, ctc_weight=1.0)
+    loss = crit(model_out, dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda), uniforms=dev_t(uni, cuda))
+    loss.backward()
+    loss_ref, _, _, dl_ref = cport.pg_ctc_step(model_out.detach().cpu().numpy(), targets, in_len, tgt_len, uni,
+                                               reward_mode=1, w_pg=0.5, w_ctc=1.0)
+    assert abs(float(loss) - loss_ref) <= RTOL * abs(loss_ref)
+    want_w = torch.einsum("btv,btf->vf", torch.tensor(dl_ref), feats.cpu())
+    assert rel_err(head.weight.grad.cpu().numpy(), want_w.numpy()) < 5e-4
+    assert crit.last["rewards"].shape == (B, K)
+    with pytest.raises(ZeroDivisionError):
+        crit(model_out, dev_t(targets, cuda), dev_t(in_len, cuda), torch.zeros(B, dtype=torch.int32))
+
+
+def test_size_independent_properties_full_size(cuda):
+    """BASELINE.json configs[1] size: properties that hold without the oracle."""
+    from pgasr_b200 import functional as F
+    B, T, V, K, L = 64, 500, 30, 16, 100
+    logits, targets, in_len, tgt_len, uni = make_batch(B, T, V, K, L, seed=0)
+    out = F.pg_ctc_step(dev_t(logits, cuda), dev_t(targets, cuda), None, None, uniforms=dev_t(uni, cuda),
+                        want=("rewards", "hyp_len", "dist", "samples", "nll"))
+    d, hl = out["dist"].cpu().numpy(), out["hyp_len"].cpu().numpy()
+    assert (d >= np.abs(hl - L)).all() and (d <= np.maximum(hl, L)).all()      # Levenshtein bounds
+    g = out["dlogits"].cpu().numpy().astype(np.float64)
+    assert np.abs(g.sum(-1)).max() < 1e-5            # both gradients are differences of distributions: rows sum to 0
+    # collapse is idempotent; distance to itself is zero
+    s = out["samples"]
+    c1, n1 = F.collapse(s, blank=0)
+    c2, n2 = F.collapse(c1, n1.reshape(-1), rows_per_len=1, blank=0)
+    assert torch.equal(n1, n2) and torch.equal(c1, c2)
+    same = F.edit_distance(c1[:, 0, :].contiguous(), n1[:, 0].contiguous(), c1[:, 0, :].to(torch.int32).contiguous(),
+                           n1[:, 0].contiguous(), rows_per_ref=1, vocab=V)
+    assert (same.cpu().numpy() == 0).all()
+    # determinism: the same call twice is bit-identical
+    out2 = F.pg_ctc_step(dev_t(logits, cuda), dev_t(targets, cuda), None, None, uniforms=dev_t(uni, cuda), want=("nll",))
+    assert torch.equal(out["dlogits"], out2["dlogits"]) and torch.equal(out["nll"], out2["nll"])
