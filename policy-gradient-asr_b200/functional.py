@@ -70,16 +70,20 @@ def softmax_sample(logits, input_lengths=None, K=16, uniforms=None, seed=0, retu
     return (samples, logp, probs) if return_probs else (samples, logp)
 
 
-def collapse(seqs, lengths=None, rows_per_len=1, blank=0):
-    """Row a3.  seqs [N,T] (or [B,K,T]) uint8 -> (collapsed rows, lengths).  blank=None: merge repeats only
+def collapse(seqs, lengths=None, rows_per_len=None, blank=0):
+    """Row a3.  seqs [N,T] (or [B,K,T]) uint8 -> (collapsed rows, lengths); `lengths` has one entry per row or
+    one per group of rows_per_len consecutive rows (e.g. [B] for [B,K,T]).  blank=None: merge repeats only
     (exactly upstream collapse_fn, CTCdecoder.py:119-131); blank=0: then drop blanks."""
     seqs = _need(seqs, torch.uint8, "seqs")
     shape = seqs.shape
     T = shape[-1]
     flat = seqs.reshape(-1, T)
     N = flat.shape[0]
-    if seqs.dim() == 3 and lengths is not None and rows_per_len == 1:
-        rows_per_len = shape[1]
+    if rows_per_len is None:          # infer: one length per row, or one per group of K rows ([B,K,T] with [B] lengths)
+        n_given = N if lengths is None else int(torch.as_tensor(lengths).numel())
+        if n_given == 0 or N % n_given:
+            raise ValueError("lengths must have one entry per row or per equal group of rows")
+        rows_per_len = N // n_given
     n_len = (N + rows_per_len - 1) // rows_per_len
     lengths = _opt_i32(lengths, "lengths", n_len, seqs.device)
     out = torch.empty_like(flat)

@@ -194,7 +194,8 @@ def test_pg_advantages_and_grad(cuda, reward, baseline):
                                       reward=reward, baseline=baseline, baseline_value=-3.5, Lmax=L)
     assert np.array_equal(R_g.cpu().numpy(), R)                           # one fp32 division: bit-exact
     assert rel_err(A_g.cpu().numpy(), A) < RTOL
-    assert abs(float(terms.sum()) / (B * K) - loss) <= RTOL * abs(loss) + 1e-6
+    scale = np.abs(A * logp).sum() / (B * K)                            # the terms cancel; judge against their size
+    assert abs(float(terms.double().sum()) / (B * K) - loss) <= RTOL * scale
     probs = torch.softmax(dev_t(logits, cuda), -1)
     g = F.pg_grad(dev_t(samples, cuda), A_g, dev_t(in_len, cuda), probs=probs if baseline != "mean" else None,
                   V=V, scale=1.0 / (B * K))
@@ -301,9 +302,10 @@ def step_case(cuda, B, T, V, K, L, seed, ragged, regime, reward="ed", baseline="
                         uniforms=None if philox else dev_t(uni, cuda), seed=99,
                         want=("rewards", "nll", "logp", "dist", "hyp_len", "samples"))
     assert np.array_equal(out["samples"].cpu().numpy(), s_ref)            # bit-exact
-    assert np.array_equal(out["hyp_len"].cpu().numpy(), hl_ref)
-    assert np.array_equal(out["dist"].cpu().numpy(), d_ref)
-    assert np.array_equal(out["rewards"].cpu().numpy(), R_ref)
+    if w_pg:
+        assert np.array_equal(out["hyp_len"].cpu().numpy(), hl_ref)
+        assert np.array_equal(out["dist"].cpu().numpy(), d_ref)
+        assert np.array_equal(out["rewards"].cpu().numpy(), R_ref)
     if w_ctc:
         assert np.abs(out["nll"].cpu().numpy() / nll_ref - 1).max() < RTOL
     assert abs(float(out["loss"]) - loss_ref) <= RTOL * abs(loss_ref) + 1e-5
@@ -373,7 +375,7 @@ def test_size_independent_properties_full_size(cuda):
     # collapse is idempotent; distance to itself is zero
     s = out["samples"]
     c1, n1 = F.collapse(s, blank=0)
-    c2, n2 = F.collapse(c1, n1.reshape(-1), rows_per_len=1, blank=0)
+    c2, n2 = F.collapse(c1, n1.reshape(-1), blank=0)
     assert torch.equal(n1, n2) and torch.equal(c1, c2)
     same = F.edit_distance(c1[:, 0, :].contiguous(), n1[:, 0].contiguous(), c1[:, 0, :].to(torch.int32).contiguous(),
                            n1[:, 0].contiguous(), rows_per_ref=1, vocab=V)
