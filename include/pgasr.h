@@ -130,8 +130,11 @@ PGASR_API int pgasr_nll_sum_backward(const int64_t* target, const float* grad_ou
  *   loss[0]  = w_pg * L_pg + w_ctc * mean_b nll[b]
  *   dlogits  = w_pg * g_pg + (w_ctc / B) * g_ctc                     (written once, not accumulated)
  * Optional outputs (NULL to skip): rewards, logp, hyp_len, dist, nll, samples.
- * workspace: pgasr_pg_ctc_step_workspace_bytes(B,T,V,K,Lmax) bytes, 256-byte aligned.            */
+ * workspace: pgasr_pg_ctc_step_workspace_bytes(B,T,V,K,Lmax) bytes, 256-byte aligned, armed ONCE with
+ * pgasr_pg_ctc_step_workspace_init before its first use (and again after a step that returned an error);
+ * one workspace serves one stream at a time.  V <= 32, K <= 64.                                   */
 PGASR_API size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax);
+PGASR_API int pgasr_pg_ctc_step_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 PGASR_API int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, const int32_t* in_len,
                       const int32_t* tgt_len, const float* uniforms, uint64_t seed,
                       int B, int T, int V, int K, int Lmax, int blank,

@@ -28,6 +28,7 @@ SIGNATURES = {
     "pgasr_nll_sum_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pgasr_nll_sum_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pgasr_pg_ctc_step_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "pgasr_pg_ctc_step_workspace_init": (_i, [_vp, _sz, _vp]),
     "pgasr_pg_ctc_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -1,0 +1,569 @@
+// CTC alpha-beta lattice walker shared by the standalone CTC kernel (ctc.cu) and the fused step kernel
+// (fused.cu).  See ctc.cu for the design notes; spec = DESIGN.md "CTC spec" (SURVEY.md 8a row a8).
+#pragma once
+#include "pgasr_common.cuh"
+
+namespace pgasr {
+
+constexpr int kCtcChunk = 32;     // frames staged per cp.async batch (staged mode); must be even
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__host__ __device__ inline int ctc_row_stride(int V) { return (V + 2) & ~1; }   // doubles per probability row
+
+constexpr double kCtcMagic = 6755399441055744.0;       // 2^52 + 2^51: low word of (x + magic) = round(x)
+constexpr double kCtcFix = 1073741824.0;               // occupancies and probabilities in 2^-30 fixed point
+constexpr float kCtcUnfix = 9.31322574615478515625e-10f;
+
+// softmax of one frame into an fp64 row of RS slots; slots V..RS-1 are zero (slot V is what label states
+// beyond the transcript read).
+__device__ __forceinline__ void softmax_row_f64(const float* __restrict__ z, const float* __restrict__ p_in,
+                                                double* __restrict__ o, int V, int RS) {
+    if (p_in) {
+        for (int v = 0; v < V; ++v) o[v] = (double)p_in[v];
+    } else {
+        float m = -INFINITY;
+        for (int v = 0; v < V; ++v) m = fmaxf(m, z[v]);
+        float s = 0.0f;
+        for (int v = 0; v < V; ++v) s += __expf(z[v] - m);
+        const float inv = 1.0f / s;
+        for (int v = 0; v < V; ++v) o[v] = (double)(__expf(z[v] - m) * inv);
+    }
+    for (int v = V; v < RS; ++v) o[v] = 0.0;
+}
+
+template <int SPL>
+struct CtcLane {
+    double a[SPL];            // alpha-hat / beta-hat of states lane*SPL + j (after the emission)
+    double skipm[SPL / 2];    // odd state 2i+1: 1.0 if its two-state transition is legal, else 0.0
+    int loff[SPL / 2];        // odd state 2i+1: slot of its class in a probability row (V = the zero slot)
+    int E;                    // true value = hat value * 2^E
+};
+
+struct GradNorm {
+    double invZ0;             // 2^30 / Z0, Z0 = sum_s alpha beta' at the first gradient frame
+    int E0;                   // exponent sum (own + other) at that frame
+    bool have;                // Z0 measured
+    bool dead;                // Z0 == 0: no valid alignment
+};
+
+__device__ __forceinline__ double pow2i(int e) {       // 2^e, e clamped to the normal range
+    e = max(-1022, min(1023, e));
+    return __hiloint2double((1023 + e) << 20, 0);
+}
+
+template <int SPL, bool kAlpha>
+__device__ __forceinline__ void ctc_lane_init(CtcLane<SPL>& st, const int32_t* __restrict__ lab_u, int L, int V) {
+    const int lane = threadIdx.x & 31;
+    st.E = 0;
+#pragma unroll
+    for (int i = 0; i < SPL / 2; ++i) {
+        const int li = (lane * SPL) / 2 + i;              // label index of odd state lane*SPL + 2i + 1
+        const int c = li < L ? lab_u[li] : -1;
+        st.loff[i] = c >= 0 ? c : V;
+        bool legal;
+        if (kAlpha) legal = c >= 0 && li >= 1 && lab_u[li - 1] != c;
+        else legal = c >= 0 && li + 1 < L && lab_u[li + 1] != c;
+        st.skipm[i] = legal ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) st.a[j] = 0.0;
+}
+
+// One frame.  `row`: the fp64 probability row of frame t (shared memory).  kGrad: second half -- `o` holds the
+// other direction's pre-emission sums of this frame (exponent eo); the values of the next frame are prefetched
+// into `on` / `eon`.  !kGrad: first half -- this direction's pre-emission sums are stored for the other one.
+template <int SPL, bool kAlpha, bool kGrad, bool kAccum>
+__device__ __forceinline__ void ctc_step(CtcLane<SPL>& st, GradNorm& gn, int step, int t, bool more, int S, int V,
+                                         int blank, const double* row, double* __restrict__ lat_u,
+                                         int* __restrict__ exp_u, float grad_scale, float* __restrict__ dlog_u,
+                                         int* racc, const double (&o)[SPL], int eo, double (&on)[SPL], int& eon) {
+    const int lane = threadIdx.x & 31;
+    const bool edge = kAlpha ? lane == 0 : lane == 31;
+
+    if (kGrad && more) {                                  // prefetch the next frame's values (used one step later)
+        const int tn = kAlpha ? t + 1 : t - 1;
+        const double* lp = lat_u + (size_t)tn * (SPL * 32) + lane;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) on[j] = lp[j * 32];
+        eon = exp_u[tn];
+    }
+
+    // ---- pre-emission sums, in place -----------------------------------------------------------
+    if (step == 0) {
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int s = lane * SPL + j;
+            const bool on_ = kAlpha ? (s <= 1 && s < S) : (s < S && s >= S - 2);
+            st.a[j] = on_ ? 1.0 : 0.0;
+        }
+    } else if (kAlpha) {
+        double h = __shfl_up_sync(kFull, st.a[SPL - 1], 1);
+        h = edge ? 0.0 : h;
+#pragma unroll
+        for (int j = SPL - 1; j >= 2; --j) {
+            if (j & 1) st.a[j] = fma(st.skipm[j >> 1], st.a[j - 2], st.a[j] + st.a[j - 1]);
+            else st.a[j] = st.a[j] + st.a[j - 1];
+        }
+        st.a[1] = fma(st.skipm[0], h, st.a[1] + st.a[0]);
+        st.a[0] = st.a[0] + h;
+    } else {
+        double h0 = __shfl_down_sync(kFull, st.a[0], 1);
+        double h1 = __shfl_down_sync(kFull, st.a[1], 1);
+        h0 = edge ? 0.0 : h0;
+        h1 = edge ? 0.0 : h1;
+#pragma unroll
+        for (int j = 0; j < SPL - 2; ++j) {
+            if (j & 1) st.a[j] = fma(st.skipm[j >> 1], st.a[j + 2], st.a[j] + st.a[j + 1]);
+            else st.a[j] = st.a[j] + st.a[j + 1];
+        }
+        st.a[SPL - 2] = st.a[SPL - 2] + st.a[SPL - 1];
+        st.a[SPL - 1] = fma(st.skipm[SPL / 2 - 1], h1, st.a[SPL - 1] + h0);
+    }
+
+    if (!kGrad) {
+        double* lp = lat_u + (size_t)t * (SPL * 32) + lane;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) lp[j * 32] = st.a[j];
+        if (lane == 0) exp_u[t] = st.E;
+    }
+
+    // ---- emission ------------------------------------------------------------------------------
+    const double pb = row[blank];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) st.a[j] *= (j & 1) ? row[st.loff[j >> 1]] : pb;
+
+    // ---- gradient row of frame t ---------------------------------------------------------------
+    if (kGrad) {
+        double w[SPL];
+        double zb = 0.0;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            w[j] = st.a[j] * o[j];
+            if (!(j & 1)) zb += w[j];
+        }
+        if (!gn.have) {                                   // first gradient frame: measure Z0 once
+            double zl = 0.0;
+#pragma unroll
+            for (int j = 1; j < SPL; j += 2) zl += w[j];
+            const double Z0 = warp_sum(zb + zl);
+            gn.have = true;
+            gn.dead = !(Z0 > 0.0);
+            gn.invZ0 = gn.dead ? 0.0 : kCtcFix / Z0;
+            gn.E0 = st.E + eo;
+        }
+        const double c = gn.invZ0 * pow2i(st.E + eo - gn.E0);
+        const int gb = __reduce_add_sync(kFull, __double2loint(fma(zb, c, kCtcMagic)));
+#pragma unroll
+        for (int j = 1; j < SPL; j += 2)
+            atomicAdd(&racc[st.loff[j >> 1]], __double2loint(fma(w[j], c, kCtcMagic)));
+        __syncwarp();
+        float* out = dlog_u + (size_t)t * V;
+        for (int v = lane; v < V; v += 32) {
+            const int occ = v == blank ? gb : racc[v];
+            racc[v] = 0;
+            const int pfix = __double2loint(fma(row[v], kCtcFix, kCtcMagic));
+            float g = grad_scale * ((float)(pfix - occ) * kCtcUnfix);
+            g = gn.dead ? 0.0f : g;
+            out[v] = kAccum ? out[v] + g : g;
+        }
+        __syncwarp();
+    }
+
+    // ---- exact power-of-two rescale every 4 steps ------------------------------------------------
+    if ((step & 3) == 3) {
+        int mx = 0;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) mx = max(mx, __double2hiint(st.a[j]));
+        mx = __reduce_max_sync(kFull, mx);
+        if (mx >= 0x00100000) {
+            const int e = (mx >> 20) - 1023;
+            const double sc = __hiloint2double((1023 - e) << 20, 0);
+            st.E += e;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) st.a[j] *= sc;
+        }
+    }
+}
+
+// Steps [step_lo, step_hi) of one direction.  kTile: `probs` is a shared-memory tile [Tb][RS] of the whole
+// utterance; else it is the global fp64 workspace and rows are staged through `stage` with cp.async.
+template <int SPL, bool kAlpha, bool kGrad, bool kAccum, bool kTile>
+__device__ __forceinline__ void ctc_frames(CtcLane<SPL>& st, GradNorm& gn, int step_lo, int step_hi, int Tb, int S,
+                                           int V, int RS, int blank, const double* probs,
+                                           double* __restrict__ lat_u, int* __restrict__ exp_u, float grad_scale,
+                                           float* __restrict__ dlog_u, double* stage, int* racc) {
+    const int lane = threadIdx.x & 31;
+    if (step_lo >= step_hi) return;
+    double oa[SPL], ob[SPL];
+    int ea = 0, eb = 0;
+    if (kGrad) {
+        const int t = kAlpha ? step_lo : Tb - 1 - step_lo;
+        const double* lp = lat_u + (size_t)t * (SPL * 32) + lane;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) oa[j] = lp[j * 32];
+        ea = exp_u[t];
+    }
+    if (kTile) {
+        int step = step_lo;
+        for (; step + 1 < step_hi; step += 2) {
+            const int t = kAlpha ? step : Tb - 1 - step;
+            const int t2 = kAlpha ? t + 1 : t - 1;
+            ctc_step<SPL, kAlpha, kGrad, kAccum>(st, gn, step, t, true, S, V, blank, probs + (size_t)t * RS, lat_u,
+                                                 exp_u, grad_scale, dlog_u, racc, oa, ea, ob, eb);
+            ctc_step<SPL, kAlpha, kGrad, kAccum>(st, gn, step + 1, t2, step + 2 < step_hi, S, V, blank,
+                                                 probs + (size_t)t2 * RS, lat_u, exp_u, grad_scale, dlog_u, racc, ob,
+                                                 eb, oa, ea);
+        }
+        if (step < step_hi) {
+            const int t = kAlpha ? step : Tb - 1 - step;
+            ctc_step<SPL, kAlpha, kGrad, kAccum>(st, gn, step, t, false, S, V, blank, probs + (size_t)t * RS, lat_u,
+                                                 exp_u, grad_scale, dlog_u, racc, oa, ea, ob, eb);
+        }
+        return;
+    }
+
+    auto issue_chunk = [&](int lo, int buf) {             // steps [lo, hi) -> contiguous frames
+        const int hi = min(lo + kCtcChunk, step_hi);
+        const int f0 = kAlpha ? lo : Tb - hi;
+        const char* src = reinterpret_cast<const char*>(probs + (size_t)f0 * RS);
+        char* dst = reinterpret_cast<char*>(stage + (size_t)buf * kCtcChunk * RS);
+        const int n16 = (hi - lo) * RS / 2;
+        for (int i = lane; i < n16; i += 32) cp_async16(dst + (size_t)i * 16, src + (size_t)i * 16);
+        cp_async_commit();
+    };
+    int buf = 0;
+    issue_chunk(step_lo, 0);
+    for (int lo = step_lo; lo < step_hi; lo += kCtcChunk, buf ^= 1) {
+        const int hi = min(lo + kCtcChunk, step_hi);
+        if (hi < step_hi) {
+            issue_chunk(hi, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const double* chunk = stage + (size_t)buf * kCtcChunk * RS;
+        int step = lo;
+        for (; step + 1 < hi; step += 2) {                // chunks hold an even number of frames except the last
+            const int t = kAlpha ? step : Tb - 1 - step;
+            const int t2 = kAlpha ? t + 1 : t - 1;
+            const double* row = chunk + (size_t)(kAlpha ? step - lo : hi - 1 - step) * RS;
+            const double* row2 = kAlpha ? row + RS : row - RS;
+            ctc_step<SPL, kAlpha, kGrad, kAccum>(st, gn, step, t, true, S, V, blank, row, lat_u, exp_u, grad_scale,
+                                                 dlog_u, racc, oa, ea, ob, eb);
+            ctc_step<SPL, kAlpha, kGrad, kAccum>(st, gn, step + 1, t2, step + 2 < step_hi, S, V, blank, row2, lat_u,
+                                                 exp_u, grad_scale, dlog_u, racc, ob, eb, oa, ea);
+        }
+        if (step < hi) {
+            const int t = kAlpha ? step : Tb - 1 - step;
+            const double* row = chunk + (size_t)(kAlpha ? step - lo : hi - 1 - step) * RS;
+            ctc_step<SPL, kAlpha, kGrad, kAccum>(st, gn, step, t, false, S, V, blank, row, lat_u, exp_u, grad_scale,
+                                                 dlog_u, racc, oa, ea, ob, eb);
+        }
+        __syncwarp();
+    }
+}
+
+// One whole direction: first half (store), mid-point barrier, second half (gradient rows), and for alpha the
+// negative log-likelihood.  `mid_barrier()` must synchronise the alpha and the beta warp (and make their global
+// stores visible to each other).
+template <int SPL, bool kAlpha, bool kAccum, bool kTile, typename Barrier>
+__device__ __forceinline__ void ctc_direction(const double* probs, const int32_t* __restrict__ lab_u, int Tb, int L,
+                                              int V, int RS, int blank, float grad_scale,
+                                              float* __restrict__ nll_out, float* __restrict__ dlog_u,
+                                              double* __restrict__ lat_u, int* __restrict__ exp_u, double* stage,
+                                              int* racc, Barrier mid_barrier) {
+    const int lane = threadIdx.x & 31;
+    const int S = 2 * L + 1;
+    const int tm = Tb / 2;
+    CtcLane<SPL> st;
+    ctc_lane_init<SPL, kAlpha>(st, lab_u, L, V);
+    for (int v = lane; v <= V; v += 32) racc[v] = 0;
+    __syncwarp();
+    GradNorm gn;
+    gn.have = false; gn.dead = false; gn.invZ0 = 0.0; gn.E0 = 0;
+    // steps 0..Tb-1 visit frames 0..Tb-1 (alpha) or Tb-1..0 (beta)
+    const int n_first = kAlpha ? tm : Tb - tm;
+    ctc_frames<SPL, kAlpha, false, kAccum, kTile>(st, gn, 0, n_first, Tb, S, V, RS, blank, probs, lat_u, exp_u,
+                                                  grad_scale, dlog_u, stage, racc);
+    mid_barrier();
+    ctc_frames<SPL, kAlpha, true, kAccum, kTile>(st, gn, n_first, Tb, Tb, S, V, RS, blank, probs, lat_u, exp_u,
+                                                 grad_scale, dlog_u, stage, racc);
+    if (kAlpha) {
+        double fin = 0.0;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int s = lane * SPL + j;
+            if (s < S && s >= S - 2) fin += st.a[j];
+        }
+        fin = warp_sum(fin);
+        if (lane == 0)
+            *nll_out = fin > 0.0 ? (float)(-(log(fin) + (double)st.E * 0.69314718055994530942)) : INFINITY;
+    }
+}
+
+inline int ctc_spl(int Lmax) {
+    const int S = 2 * Lmax + 1;
+    if (S <= 4 * 32) return 4;
+    if (S <= 8 * 32) return 8;
+    if (S <= 16 * 32) return 16;
+    if (S <= 32 * 32) return 32;
+    return 0;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace pgasr
+
+// =====================================================================================================
+// Split walker (fused kernel, probability tile in shared memory): the two recurrence warps carry ONLY the
+// recurrence; in their second half they hand each frame's post-emission values to gradient worker warps through
+// a double-buffered shared-memory ring, in batches of kBatch frames guarded by named barriers (bar.arrive /
+// bar.sync: waiting warps sleep in hardware, and the only memory fence is the barrier itself, once per batch --
+// a per-frame release store costs a MEMBAR that drains the 8 pending STS, ~300 cycles, measured).  The workers
+// turn the values into gradient rows; frames are independent there, so G workers per direction work on G frames
+// at once.  A warp issues in order, so taking the gradient's latencies (lattice loads, redux, shared atomics,
+// row stores) out of the recurrence warp is what shortens the frame time.
+// =====================================================================================================
+namespace pgasr {
+
+constexpr int kBatch = 8;         // frames per hand-off batch; two batches in flight per direction
+
+template <int SPL>
+struct GradRing {
+    double* slots;                // [2 * kBatch][SPL*32]
+    int* eslot;                   // [2 * kBatch] exponent of the published values
+    int bar_full;                 // named barrier ids: bar_full + k, bar_empty + k for buffer k in {0, 1}
+    int bar_empty;
+};
+
+template <int SPL>
+__host__ __device__ inline size_t grad_ring_bytes() {
+    return (size_t)2 * kBatch * SPL * 32 * 8 + 2 * kBatch * 4;
+}
+
+template <int SPL>
+__device__ __forceinline__ GradRing<SPL> grad_ring_carve(unsigned char* p, int bar_base) {   // p 16-byte aligned
+    GradRing<SPL> r;
+    r.slots = reinterpret_cast<double*>(p);
+    r.eslot = reinterpret_cast<int*>(p + (size_t)2 * kBatch * SPL * 32 * 8);
+    r.bar_full = bar_base;
+    r.bar_empty = bar_base + 2;
+    return r;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+
+// pre-emission sums in place; h0 (and h1 for beta) are the halo values fetched from the neighbour lane
+template <int SPL, bool kAlpha>
+__device__ __forceinline__ void ctc_presum(CtcLane<SPL>& st, double h0, double h1) {
+    if (kAlpha) {
+#pragma unroll
+        for (int j = SPL - 1; j >= 2; --j) {
+            if (j & 1) st.a[j] = fma(st.skipm[j >> 1], st.a[j - 2], st.a[j] + st.a[j - 1]);
+            else st.a[j] = st.a[j] + st.a[j - 1];
+        }
+        st.a[1] = fma(st.skipm[0], h0, st.a[1] + st.a[0]);
+        st.a[0] = st.a[0] + h0;
+    } else {
+#pragma unroll
+        for (int j = 0; j < SPL - 2; ++j) {
+            if (j & 1) st.a[j] = fma(st.skipm[j >> 1], st.a[j + 2], st.a[j] + st.a[j + 1]);
+            else st.a[j] = st.a[j] + st.a[j + 1];
+        }
+        st.a[SPL - 2] = st.a[SPL - 2] + st.a[SPL - 1];
+        st.a[SPL - 1] = fma(st.skipm[SPL / 2 - 1], h1, st.a[SPL - 1] + h0);
+    }
+}
+
+// Recurrence warp of one direction over the whole utterance (tile mode).  G: workers of this direction.
+template <int SPL, int G, bool kAlpha, typename Barrier>
+__device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t* __restrict__ lab_u, int Tb, int L,
+                                              int V, int RS, int blank, float* __restrict__ nll_out,
+                                              double* __restrict__ lat_u, int* __restrict__ exp_u,
+                                              GradRing<SPL> ring, Barrier mid_barrier) {
+    constexpr int kGroup = 32 * (1 + G);                  // this warp + its workers
+    const int lane = threadIdx.x & 31;
+    const bool edge = kAlpha ? lane == 0 : lane == 31;
+    const int S = 2 * L + 1;
+    const int tm = Tb / 2;
+    const int n_first = kAlpha ? tm : Tb - tm;
+    CtcLane<SPL> st;
+    ctc_lane_init<SPL, kAlpha>(st, lab_u, L, V);
+
+    for (int step = 0; step < Tb; ++step) {
+        if (step == n_first) mid_barrier();
+        const int t = kAlpha ? step : Tb - 1 - step;
+        const double* row = tile + (size_t)t * RS;
+        // probabilities of this frame (independent of the recurrence: issued first)
+        double p[SPL / 2];
+        const double pb = row[blank];
+#pragma unroll
+        for (int i = 0; i < SPL / 2; ++i) p[i] = row[st.loff[i]];
+
+        if (step == 0) {
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                const int s = lane * SPL + j;
+                const bool on_ = kAlpha ? (s <= 1 && s < S) : (s < S && s >= S - 2);
+                st.a[j] = on_ ? 1.0 : 0.0;
+            }
+        } else {
+            double h0, h1 = 0.0;
+            if (kAlpha) {
+                h0 = __shfl_up_sync(kFull, st.a[SPL - 1], 1);
+            } else {
+                h0 = __shfl_down_sync(kFull, st.a[0], 1);
+                h1 = __shfl_down_sync(kFull, st.a[1], 1);
+            }
+            h0 = edge ? 0.0 : h0;
+            h1 = edge ? 0.0 : h1;
+            ctc_presum<SPL, kAlpha>(st, h0, h1);
+        }
+
+        if (step < n_first) {                             // first half: pre-emission sums for the other direction
+            double* lp = lat_u + (size_t)t * (SPL * 32) + lane;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) lp[j * 32] = st.a[j];
+            if (lane == 0) exp_u[t] = st.E;
+        }
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) st.a[j] *= (j & 1) ? p[j >> 1] : pb;
+
+        if (step >= n_first) {                            // second half: hand the post-emission values over
+            const int q = step - n_first;
+            const int buf = (q / kBatch) & 1;
+            if ((q % kBatch) == 0 && q >= 2 * kBatch) named_bar_sync(ring.bar_empty + buf, kGroup);
+            const int slot = q % (2 * kBatch);
+            double* sp = ring.slots + (size_t)slot * (SPL * 32) + lane;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) sp[j * 32] = st.a[j];
+            if (lane == 0) ring.eslot[slot] = st.E;
+            if ((q % kBatch) == kBatch - 1 || step == Tb - 1) named_bar_arrive(ring.bar_full + buf, kGroup);
+        }
+
+        if ((step & 3) == 3) {                            // exact power-of-two rescale
+            int mx = 0;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) mx = max(mx, __double2hiint(st.a[j]));
+            mx = __reduce_max_sync(kFull, mx);
+            if (mx >= 0x00100000) {
+                const int e = (mx >> 20) - 1023;
+                const double sc = __hiloint2double((1023 - e) << 20, 0);
+                st.E += e;
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) st.a[j] *= sc;
+            }
+        }
+    }
+    if (Tb == n_first) mid_barrier();                     // (keeps the barrier counts equal when the half is empty)
+
+    if (kAlpha) {
+        double fin = 0.0;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int s = lane * SPL + j;
+            if (s < S && s >= S - 2) fin += st.a[j];
+        }
+        fin = warp_sum(fin);
+        if (lane == 0)
+            *nll_out = fin > 0.0 ? (float)(-(log(fin) + (double)st.E * 0.69314718055994530942)) : INFINITY;
+    }
+}
+
+// Gradient worker g of one direction: frames q with q % G == g of that direction's second half.
+template <int SPL, int G, bool kAlpha, typename Barrier>
+__device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const int32_t* __restrict__ lab_u, int Tb,
+                                                int L, int V, int RS, int blank, float grad_scale,
+                                                float* __restrict__ dlog_u, const double* __restrict__ lat_u,
+                                                const int* __restrict__ exp_u, GradRing<SPL> ring, int* racc,
+                                                Barrier mid_barrier) {
+    static_assert(kBatch % G == 0, "workers must divide the batch");
+    constexpr int kGroup = 32 * (1 + G);
+    const int lane = threadIdx.x & 31;
+    const int tm = Tb / 2;
+    const int n_first = kAlpha ? tm : Tb - tm;
+    const int n2 = Tb - n_first;
+    int loff[SPL / 2];
+#pragma unroll
+    for (int i = 0; i < SPL / 2; ++i) {
+        const int li = (lane * SPL) / 2 + i;
+        const int c = li < L ? lab_u[li] : -1;
+        loff[i] = c >= 0 ? c : V;
+    }
+    for (int v = lane; v <= V; v += 32) racc[v] = 0;
+    __syncwarp();
+    mid_barrier();                                        // the other direction's half-lattice is complete
+    double invZ0 = 0.0;
+    int E0 = 0;
+    bool dead = false, have = false;
+    const int nbatch = (n2 + kBatch - 1) / kBatch;
+    for (int nb = 0; nb < nbatch; ++nb) {
+        const int buf = nb & 1;
+        // this worker's frames of the batch: their lattice rows can be fetched before the batch is ready
+        named_bar_sync(ring.bar_full + buf, kGroup);
+        for (int q = nb * kBatch + g; q < min(n2, (nb + 1) * kBatch); q += G) {
+            const int step = n_first + q;
+            const int t = kAlpha ? step : Tb - 1 - step;
+            const double* lp = lat_u + (size_t)t * (SPL * 32) + lane;
+            double o[SPL];
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) o[j] = __ldcg(lp + j * 32);
+            const int eo = __ldcg(exp_u + t);
+            const int slot = q % (2 * kBatch);
+            const double* sp = ring.slots + (size_t)slot * (SPL * 32) + lane;
+            double w[SPL];
+            double zb = 0.0;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                w[j] = sp[j * 32] * o[j];
+                if (!(j & 1)) zb += w[j];
+            }
+            const int E = ring.eslot[slot];
+            if (!have) {                                  // this worker's first frame: measure Z0 = P / 2^(E+eo)
+                double zl = 0.0;
+#pragma unroll
+                for (int j = 1; j < SPL; j += 2) zl += w[j];
+                const double Z0 = warp_sum(zb + zl);
+                dead = !(Z0 > 0.0);
+                invZ0 = dead ? 0.0 : kCtcFix / Z0;
+                E0 = E + eo;
+                have = true;
+            }
+            const double c = invZ0 * pow2i(E + eo - E0);
+            const int gb = __reduce_add_sync(kFull, __double2loint(fma(zb, c, kCtcMagic)));
+#pragma unroll
+            for (int j = 1; j < SPL; j += 2) atomicAdd(&racc[loff[j >> 1]], __double2loint(fma(w[j], c, kCtcMagic)));
+            __syncwarp();
+            const double* row = tile + (size_t)t * RS;
+            float* out = dlog_u + (size_t)t * V;
+            for (int v = lane; v < V; v += 32) {
+                const int occ = v == blank ? gb : racc[v];
+                racc[v] = 0;
+                const int pfix = __double2loint(fma(row[v], kCtcFix, kCtcMagic));
+                const float gr = grad_scale * ((float)(pfix - occ) * kCtcUnfix);
+                out[v] = dead ? 0.0f : gr;
+            }
+            __syncwarp();
+        }
+        if (nb + 2 < nbatch) named_bar_arrive(ring.bar_empty + buf, kGroup);   // buffer may be overwritten
+    }
+}
+
+}  // namespace pgasr

@@ -1,0 +1,411 @@
+// The whole PG + CTC loss step as ONE kernel launch (upstream call site: criterion(model_out, t) followed by
+// loss.backward(), model.py:235-237; SURVEY.md rows a1-a8 chained).
+//
+// Grid = 2B CTAs that pick their role from an atomic ticket (tickets < B: CTC role of utterance `ticket`;
+// the rest: PG role of utterance `ticket - B`), so the long-pole CTC CTAs are always resident before any PG CTA
+// waits on them.  Both roles of an utterance run at the same time on different SMs:
+//   CTC role: softmax of the utterance into an fp64 shared-memory tile, then warp 0 / warp 1 walk alpha / beta
+//             (ctc_core.cuh) and write the CTC gradient rows; finally a release flag.
+//   PG role:  logits tile -> shared memory (cp.async), one thread per frame: softmax CDF + K inverse-CDF draws
+//             (Philox or injected uniforms), one warp per sample: ballot/popc collapse, one thread per sample:
+//             bit-parallel Levenshtein against the transcript, warp 0: rewards / baseline / advantages, then the
+//             REINFORCE gradient tile is built in place of the logits tile, the CTA acquires the CTC role's flag
+//             and adds its tile onto the CTC rows with coalesced float4 read-modify-writes.
+// The last CTA to finish (second ticket) reduces the loss in a fixed order and re-arms the control block.
+// dlogits is written once by the CTC role and updated once by the PG role; every sum is order independent or
+// fixed-order, so the step is bit-reproducible run to run.
+#include "ctc_core.cuh"
+#include "myers_core.cuh"
+
+namespace pgasr {
+
+struct FusedArgs {
+    const float* logits; const int32_t* targets; const int32_t* in_len; const int32_t* tgt_len;
+    const float* uniforms; unsigned long long seed;
+    int B, T, V, K, Lmax, blank, reward_mode, baseline_mode;
+    float baseline_value, w_pg, w_ctc;
+    int do_pg, do_ctc;
+    float* loss; float* dlogits;
+    float* rewards; float* logp; int32_t* hyp_len; int32_t* dist; float* nll; uint8_t* samples;   // optional
+    unsigned* ctrl;          // [0] role ticket, [1] done ticket, [4 + b] CTC-done flag of utterance b
+    double* lattice; int* lat_exp; float* loss_terms; float* nll_ws;
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int kFusedMaxK = 64;
+
+// ------------------------------------------------------------------------------------------------ CTC role
+// warp 0: alpha recurrence, warp 1: beta recurrence; warps with (warp & 3) == 2: alpha-side gradient workers,
+// (warp & 3) == 3: beta-side workers (they sit on the two schedulers the recurrence warps do not use).
+template <int SPL, int kThreads>
+__device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw) {
+    constexpr int G = kThreads / 128;                      // gradient workers per direction
+    constexpr int kMidThreads = 32 * (2 + 2 * G);
+    const int warp = threadIdx.x >> 5;
+    const int T = a.T, V = a.V;
+    const int RS = ctc_row_stride(V);
+    int Tb = a.in_len ? a.in_len[b] : T;
+    Tb = min(max(Tb, 0), T);
+    int L = a.tgt_len ? a.tgt_len[b] : a.Lmax;
+    L = min(max(L, 0), a.Lmax);
+    float* dlog_u = a.dlogits + (size_t)b * T * V;
+    float* nll_u = (a.nll ? a.nll : a.nll_ws) + b;
+    for (int i = Tb * V + threadIdx.x; i < T * V; i += kThreads) dlog_u[i] = 0.0f;
+    if (Tb == 0) {
+        if (threadIdx.x == 0) *nll_u = L == 0 ? 0.0f : INFINITY;
+    } else {
+        double* tile = reinterpret_cast<double*>(smem_raw);                 // [T][RS]
+        unsigned char* p = smem_raw + (size_t)T * RS * 8;
+        GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
+        GradRing<SPL> ring_b = grad_ring_carve<SPL>(p, 6);                  p += grad_ring_bytes<SPL>();
+        int* racc_all = reinterpret_cast<int*>(p);                          // [2G][V + 2]
+        const float* lg = a.logits + (size_t)b * T * V;
+        for (int t = threadIdx.x; t < Tb; t += kThreads)
+            softmax_row_f64(lg + (size_t)t * V, nullptr, tile + (size_t)t * RS, V, RS);
+        __syncthreads();
+        double* lat_u = a.lattice + (size_t)b * T * (SPL * 32);
+        int* exp_u = a.lat_exp + (size_t)b * T;
+        const int32_t* lab_u = a.targets + (size_t)b * a.Lmax;
+        const float gs = a.w_ctc / (float)a.B;
+        auto mid = [] {
+            __threadfence_block();
+            asm volatile("bar.sync 1, %0;\n" ::"n"(kMidThreads) : "memory");
+        };
+        const int role = warp & 3, g = warp >> 2;
+        if (warp == 0)
+            ctc_walk_tile<SPL, G, true>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid);
+        else if (warp == 1)
+            ctc_walk_tile<SPL, G, false>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_b, mid);
+        else if (role == 2)
+            ctc_grad_worker<SPL, G, true>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_a,
+                                          racc_all + g * (V + 2), mid);
+        else if (role == 3)
+            ctc_grad_worker<SPL, G, false>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_b,
+                                           racc_all + (G + g) * (V + 2), mid);
+    }
+    __threadfence();                                       // rows and nll visible device-wide before the flag
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(a.ctrl + 4 + b, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------ PG role
+template <int W, int kThreads>
+__device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw) {
+    constexpr int kWarps = kThreads / 32;
+    constexpr int VP = 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int T = a.T, V = a.V, K = a.K;
+    const int Tp = (T + 15) & ~15;
+    int Tb = a.in_len ? a.in_len[b] : T;
+    Tb = min(max(Tb, 0), T);
+    int m = a.tgt_len ? a.tgt_len[b] : a.Lmax;
+    m = min(max(m, 0), a.Lmax);
+
+    // shared-memory carve-up
+    float* ztile = reinterpret_cast<float*>(smem_raw);                                // [T][V]
+    size_t off = ((size_t)T * V * 4 + 15) & ~(size_t)15;
+    uint8_t* samples_s = smem_raw + off;            off += (size_t)K * Tp;            // [K][Tp]
+    uint8_t* hyp_s = smem_raw + off;                off += (size_t)K * Tp;            // [K][Tp]
+    uint32_t* peq = reinterpret_cast<uint32_t*>(smem_raw + off); off += (size_t)(V + 1) * W * 4;
+    off = (off + 15) & ~(size_t)15;
+    float* warp_acc = reinterpret_cast<float*>(smem_raw + off);  off += (size_t)kWarps * kFusedMaxK * 4;
+    float* adv_s = reinterpret_cast<float*>(smem_raw + off);     off += kFusedMaxK * 4;
+    int* hlen_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
+    int* dist_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
+    float* misc_s = reinterpret_cast<float*>(smem_raw + off);    // [0] sum of advantages
+
+    // ---- P0: logits tile -> shared memory ------------------------------------------------------
+    const float* lg = a.logits + (size_t)b * T * V;
+    if ((((size_t)T * V * 4) & 15) == 0) {
+        const int n16 = T * V / 4;
+        for (int i = threadIdx.x; i < n16; i += kThreads) cp_async16(reinterpret_cast<char*>(ztile) + (size_t)i * 16,
+                                                                     reinterpret_cast<const char*>(lg) + (size_t)i * 16);
+    } else {
+        for (int i = threadIdx.x; i < T * V; i += kThreads) cp_async4(ztile + i, lg + i);
+    }
+    cp_async_commit();
+    for (int i = threadIdx.x; i < kWarps * kFusedMaxK; i += kThreads) warp_acc[i] = 0.0f;
+    for (int i = threadIdx.x; i < (V + 1) * W; i += kThreads) peq[i] = 0u;
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- P1: softmax CDF + K draws, one thread per frame (DESIGN.md "sampler spec") ------------
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    for (int t0 = 0; t0 < T; t0 += kThreads) {
+        const int t = t0 + threadIdx.x;
+        const bool live = t < Tb;
+        const float* z = ztile + (size_t)(live ? t : 0) * V;
+        float cdf[VP];
+        float mx = -INFINITY, S = 0.0f, logS = 0.0f;
+        if (live) {
+#pragma unroll
+            for (int v = 0; v < VP; ++v) cdf[v] = v < V ? z[v] : -INFINITY;
+#pragma unroll
+            for (int v = 0; v < VP; ++v) mx = fmaxf(mx, cdf[v]);
+            float c = 0.0f;
+#pragma unroll
+            for (int v = 0; v < VP; ++v) {
+                if (v < V) c = __fadd_rn(c, exp_spec(__fsub_rn(cdf[v], mx)));
+                cdf[v] = c;
+            }
+            S = c;
+            logS = logf(S);
+        }
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < K; ++k) {
+            float term = 0.0f;
+            int pi = 0;
+            if (live) {
+                float u;
+                if (a.uniforms) {
+                    u = __ldg(a.uniforms + ((size_t)b * K + k) * T + t);
+                } else {
+                    if ((k & 3) == 0)
+                        rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k >> 2), 0x50474153u), key);
+                    const uint32_t x = (k & 3) == 0 ? rnd.x : (k & 3) == 1 ? rnd.y : (k & 3) == 2 ? rnd.z : rnd.w;
+                    u = u32_to_uniform(x);
+                }
+                const float tau = __fmul_rn(u, S);
+                int cnt = 0;
+#pragma unroll
+                for (int v = 0; v < VP; ++v) cnt += (v < V && cdf[v] <= tau) ? 1 : 0;
+                pi = min(cnt, V - 1);
+                term = (z[pi] - mx) - logS;
+            }
+            if (t < T) {
+                samples_s[(size_t)k * Tp + t] = (uint8_t)pi;
+                if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi;
+            }
+            term = warp_sum(term);
+            if (lane == 0) warp_acc[warp * kFusedMaxK + k] += term;
+        }
+    }
+    __syncthreads();
+
+    // ---- P2: collapse (one warp per sample) and the match table of the transcript ---------------
+    const int32_t* ref = a.targets + (size_t)b * a.Lmax;
+    for (int j = threadIdx.x; j < m; j += kThreads) {
+        const uint32_t c = (uint32_t)ref[j];
+        if (c < (uint32_t)V) atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+    }
+    for (int k = warp; k < K; k += kWarps) {
+        const uint8_t* in = samples_s + (size_t)k * Tp;
+        uint8_t* o = hyp_s + (size_t)k * Tp;
+        int base = 0, carry = -1;
+        for (int t0 = 0; t0 < Tb; t0 += 32) {
+            const int t = t0 + lane;
+            const int x = t < Tb ? (int)in[t] : -2;
+            int p = __shfl_up_sync(kFull, x, 1);
+            if (lane == 0) p = carry;
+            const bool keep = t < Tb && x != p && x != a.blank;
+            const unsigned mask = __ballot_sync(kFull, keep);
+            if (keep) o[base + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)x;
+            base += __popc(mask);
+            carry = __shfl_sync(kFull, x, 31);
+        }
+        if (lane == 0) hlen_s[k] = base;
+    }
+    __syncthreads();
+
+    // ---- P3: edit distance, one thread per sample ------------------------------------------------
+    if ((int)threadIdx.x < K) {
+        const int k = threadIdx.x;
+        dist_s[k] = myers_row<W, false>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, nullptr);
+    }
+    __syncthreads();
+
+    // ---- P4: rewards, baseline, advantages, loss term (warp 0) -----------------------------------
+    if (warp == 0) {
+        float sumR = 0.0f;
+        for (int k = lane; k < K; k += 32) {
+            float R = -(float)dist_s[k];
+            if (a.reward_mode == PGASR_REWARD_NEG_CER) R = __fdiv_rn(R, (float)m);
+            adv_s[k] = R;
+            sumR += R;
+        }
+        sumR = warp_sum(sumR);
+        float term = 0.0f, sumA = 0.0f;
+        for (int k = lane; k < K; k += 32) {
+            const float R = adv_s[k];
+            float base = 0.0f;
+            if (a.baseline_mode == PGASR_BASELINE_MEAN) base = sumR / (float)K;
+            else if (a.baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumR - R) / (float)(K - 1) : 0.0f;
+            else if (a.baseline_mode == PGASR_BASELINE_VALUE) base = a.baseline_value;
+            const float A = R - base;
+            float lp = 0.0f;
+            for (int w = 0; w < kWarps; ++w) lp += warp_acc[w * kFusedMaxK + k];
+            term += -A * lp;
+            sumA += A;
+            adv_s[k] = A;
+            const size_t o = (size_t)b * K + k;
+            if (a.rewards) a.rewards[o] = R;
+            if (a.logp) a.logp[o] = lp;
+            if (a.hyp_len) a.hyp_len[o] = hlen_s[k];
+            if (a.dist) a.dist[o] = dist_s[k];
+        }
+        term = warp_sum(term);
+        sumA = warp_sum(sumA);
+        if (lane == 0) {
+            a.loss_terms[b] = term;
+            misc_s[0] = sumA;
+        }
+    }
+    __syncthreads();
+
+    // ---- P5: REINFORCE gradient tile, in place of the logits tile ---------------------------------
+    const float coef = a.w_pg / ((float)a.B * (float)K);
+    const bool dense = a.baseline_mode != PGASR_BASELINE_MEAN;   // sum_k A_k == 0 under the per-utterance mean
+    const float dense_c = coef * misc_s[0];
+    for (int t = threadIdx.x; t < T; t += kThreads) {
+        float* row = ztile + (size_t)t * V;
+        if (t < Tb) {
+            if (dense) {
+                float mx = -INFINITY, s = 0.0f;
+                for (int v = 0; v < V; ++v) mx = fmaxf(mx, row[v]);
+                for (int v = 0; v < V; ++v) s += __expf(row[v] - mx);
+                const float sc = dense_c / s;
+                for (int v = 0; v < V; ++v) row[v] = __expf(row[v] - mx) * sc;
+            } else {
+                for (int v = 0; v < V; ++v) row[v] = 0.0f;
+            }
+            for (int k = 0; k < K; ++k) row[samples_s[(size_t)k * Tp + t]] -= coef * adv_s[k];
+        } else {
+            for (int v = 0; v < V; ++v) row[v] = 0.0f;
+        }
+    }
+    __syncthreads();
+
+    // ---- P6: add the tile onto the CTC rows (or store it when there is no CTC term) ---------------
+    float* dlog_u = a.dlogits + (size_t)b * T * V;
+    if (a.do_ctc) {
+        if (threadIdx.x == 0) {
+            const unsigned* flag = a.ctrl + 4 + b;
+            while (ld_acquire(flag) == 0u) __nanosleep(200);
+        }
+        __syncthreads();
+    }
+    if ((((size_t)T * V * 4) & 15) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dlog_u);
+        const float4* t4 = reinterpret_cast<const float4*>(ztile);
+        for (int i = threadIdx.x; i < T * V / 4; i += kThreads) {
+            float4 g = t4[i];
+            if (a.do_ctc) {
+                const float4 c = __ldcg(d4 + i);
+                g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w;
+            }
+            d4[i] = g;
+        }
+    } else {
+        for (int i = threadIdx.x; i < T * V; i += kThreads)
+            dlog_u[i] = a.do_ctc ? __ldcg(dlog_u + i) + ztile[i] : ztile[i];
+    }
+}
+
+template <int SPL, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned s_ticket, s_last;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ctrl, 1u);
+    __syncthreads();
+    const unsigned ticket = s_ticket;
+    const unsigned n_ctc = a.do_ctc ? (unsigned)a.B : 0u;
+    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads>(a, (int)ticket, smem_raw);
+    else fused_pg_role<SPL / 2, kThreads>(a, (int)(ticket - n_ctc), smem_raw);
+
+    // ---- second ticket: the last CTA reduces the loss (fixed order) and re-arms the control block ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.ctrl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence();
+        const float* nl = a.nll ? a.nll : a.nll_ws;
+        float pg = 0.0f, ct = 0.0f;
+        for (int b = threadIdx.x; b < a.B; b += 32) {
+            if (a.do_pg) pg += __ldcg(a.loss_terms + b);
+            if (a.do_ctc) ct += __ldcg(nl + b);
+            a.ctrl[4 + b] = 0u;
+        }
+        pg = warp_sum(pg);
+        ct = warp_sum(ct);
+        if (threadIdx.x == 0) {
+            float l = 0.0f;
+            if (a.do_pg) l += a.w_pg * pg / ((float)a.B * (float)a.K);
+            if (a.do_ctc) l += a.w_ctc * ct / (float)a.B;
+            a.loss[0] = l;
+            a.ctrl[0] = 0u;
+            a.ctrl[1] = 0u;
+        }
+    }
+}
+
+struct FusedWs { size_t ctrl, lat, exps, terms, nll, total; };
+
+static FusedWs fused_ws(int B, int T, int spl) {
+    FusedWs w;
+    w.ctrl = align_up((size_t)(4 + B) * sizeof(unsigned), 256);
+    w.lat = align_up((size_t)B * T * spl * 32 * sizeof(double), 256);
+    w.exps = align_up((size_t)B * T * sizeof(int), 256);
+    w.terms = align_up((size_t)B * sizeof(float), 256);
+    w.nll = align_up((size_t)B * sizeof(float), 256);
+    w.total = w.ctrl + w.lat + w.exps + w.terms + w.nll;
+    return w;
+}
+
+static size_t fused_smem(int T, int V, int K, int spl, int threads) {
+    const int RS = ctc_row_stride(V);
+    const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
+    const size_t ctc = (size_t)T * RS * sizeof(double) + 2 * ring + (size_t)2 * (threads / 128) * (V + 2) * sizeof(int);
+    const int Tp = (T + 15) & ~15, W = spl / 2;
+    size_t pg = (((size_t)T * V * 4 + 15) & ~(size_t)15) + (size_t)2 * K * Tp + (size_t)(V + 1) * W * 4 + 16;
+    pg += (size_t)(threads / 32) * kFusedMaxK * 4 + 3 * kFusedMaxK * 4 + 16;
+    return ctc > pg ? ctc : pg;
+}
+
+// 0 when the fused kernel cannot take this shape (the caller then chains the stand-alone kernels)
+size_t fused_workspace_bytes(int B, int T, int V, int K, int Lmax) {
+    const int spl = ctc_spl(Lmax);
+    if (spl == 0 || V > 32 || K > kFusedMaxK) return 0;
+    const int threads = spl <= 8 ? 512 : 256;
+    if (fused_smem(T, V, K, spl, threads) > 220 * 1024) return 0;
+    return fused_ws(B, T, spl).total;
+}
+
+template <int SPL, int kThreads>
+static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
+    PGASR_CUDA_TRY(cudaFuncSetAttribute(pg_ctc_fused_kernel<SPL, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    const int grid = (a.do_ctc ? a.B : 0) + (a.do_pg ? a.B : 0);
+    pg_ctc_fused_kernel<SPL, kThreads><<<grid, kThreads, smem, st>>>(a);
+    PGASR_LAUNCH_CHECK();
+    return PGASR_OK;
+}
+
+int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
+    const int spl = ctc_spl(a.Lmax);
+    const int threads = spl <= 8 ? 512 : 256;
+    const FusedWs w = fused_ws(a.B, a.T, spl);
+    char* p = reinterpret_cast<char*>(workspace);
+    a.ctrl = reinterpret_cast<unsigned*>(p);             p += w.ctrl;
+    a.lattice = reinterpret_cast<double*>(p);            p += w.lat;
+    a.lat_exp = reinterpret_cast<int*>(p);               p += w.exps;
+    a.loss_terms = reinterpret_cast<float*>(p);          p += w.terms;
+    a.nll_ws = reinterpret_cast<float*>(p);
+    const size_t smem = fused_smem(a.T, a.V, a.K, spl, threads);
+    switch (spl) {
+        case 4: return launch_fused<4, 512>(a, smem, st);
+        case 8: return launch_fused<8, 512>(a, smem, st);
+        case 16: return launch_fused<16, 256>(a, smem, st);
+        default: return launch_fused<32, 256>(a, smem, st);
+    }
+}
+
+}  // namespace pgasr

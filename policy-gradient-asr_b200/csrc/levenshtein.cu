@@ -10,7 +10,7 @@
 //    len(ref) cell updates of the DP.
 //  * wavefront_i32: the anti-diagonal DP over the table held in shared memory, one CTA per pair, for
 //    arbitrary int32 tokens (word ids for WER, code points) and as an independent cross-check.
-#include "pgasr_common.cuh"
+#include "myers_core.cuh"
 
 namespace pgasr {
 
@@ -19,76 +19,18 @@ __global__ void myers_u8_kernel(const uint8_t* __restrict__ hyps, const int32_t*
                                 int N, int hyp_stride, const int32_t* __restrict__ refs,
                                 const int32_t* __restrict__ ref_len, int rows_per_ref, int ref_stride,
                                 int vocab, int32_t* __restrict__ dist, int32_t* __restrict__ last_col) {
-    extern __shared__ uint32_t peq[];                 // [vocab][W]
+    extern __shared__ __align__(16) uint32_t peq[];   // [vocab + 1][W]
     const int g = blockIdx.x;
     int m = ref_len ? ref_len[g] : ref_stride;
     m = min(max(m, 0), ref_stride);
-    for (int i = threadIdx.x; i < vocab * W; i += blockDim.x) peq[i] = 0u;
-    __syncthreads();
-    for (int j = threadIdx.x; j < m; j += blockDim.x) {
-        const uint32_t c = (uint32_t)refs[(size_t)g * ref_stride + j];
-        if (c < (uint32_t)vocab) atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
-    }
-    __syncthreads();
+    myers_build_peq<W>(peq, vocab, refs + (size_t)g * ref_stride, m);
     if ((int)threadIdx.x >= rows_per_ref) return;
     const int row = g * rows_per_ref + threadIdx.x;
     if (row >= N) return;
     int n = hyp_len[row];
     n = min(max(n, 0), hyp_stride);
-    const uint8_t* h = hyps + (size_t)row * hyp_stride;
     int32_t* col = kLastCol ? last_col + (size_t)row * (hyp_stride + 1) : nullptr;
-
-    uint32_t VP[W], VN[W], sel[W];
-    const int wm = m > 0 ? (m - 1) >> 5 : 0;
-    const uint32_t bm = m > 0 ? 1u << ((m - 1) & 31) : 0u;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        VP[w] = 0xffffffffu;
-        VN[w] = 0u;
-        sel[w] = (w == wm) ? bm : 0u;
-    }
-    int score = m;
-    if (kLastCol) col[0] = m;
-    for (int i = 0; i < n; ++i) {
-        const uint32_t c = h[i];
-        uint32_t D0[W], HP[W], HN[W];
-        uint32_t carry = 0u;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const uint32_t eq = c < (uint32_t)vocab ? peq[c * W + w] : 0u;
-            const uint64_t s = (uint64_t)(eq & VP[w]) + VP[w] + carry;
-            carry = (uint32_t)(s >> 32);
-            D0[w] = (((uint32_t)s ^ VP[w]) | eq) | VN[w];
-            HP[w] = VN[w] | ~(D0[w] | VP[w]);
-            HN[w] = D0[w] & VP[w];
-        }
-        if (kLastCol) {
-            uint32_t hp = 0u, hn = 0u;
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                hp |= HP[w] & sel[w];
-                hn |= HN[w] & sel[w];
-            }
-            score += (hp != 0u) - (hn != 0u);
-            col[i + 1] = m > 0 ? score : i + 1;
-        }
-#pragma unroll
-        for (int w = W - 1; w >= 0; --w) {
-            const uint32_t hps = (HP[w] << 1) | (w ? HP[w - 1] >> 31 : 1u);
-            const uint32_t hns = (HN[w] << 1) | (w ? HN[w - 1] >> 31 : 0u);
-            VP[w] = hns | ~(D0[w] | hps);
-            VN[w] = hps & D0[w];
-        }
-    }
-    // dp[n, m] = dp[n, 0] + sum_{j<m} (VP_j - VN_j)
-    int d = n;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        const int lo = w * 32;
-        uint32_t msk = m >= lo + 32 ? 0xffffffffu : (m > lo ? (1u << (m - lo)) - 1u : 0u);
-        d += __popc(VP[w] & msk) - __popc(VN[w] & msk);
-    }
-    dist[row] = d;
+    dist[row] = myers_row<W, kLastCol>(hyps + (size_t)row * hyp_stride, n, peq, vocab, m, col);
 }
 
 // Anti-diagonal wavefront.  Cell (i, j), i over the hypothesis, j over the reference, sits on diagonal
@@ -143,7 +85,7 @@ static int launch_myers(const uint8_t* hyps, const int32_t* hyp_len, int N, int 
                         int vocab, int32_t* dist, int32_t* last_col, cudaStream_t st) {
     const int groups = (N + rows_per_ref - 1) / rows_per_ref;
     const int threads = ((rows_per_ref + 31) / 32) * 32;
-    const size_t smem = (size_t)vocab * W * sizeof(uint32_t);
+    const size_t smem = (size_t)(vocab + 1) * W * sizeof(uint32_t);
     if (last_col)
         myers_u8_kernel<W, true><<<groups, threads, smem, st>>>(hyps, hyp_len, N, hyp_stride, refs, ref_len,
                                                                rows_per_ref, ref_stride, vocab, dist, last_col);

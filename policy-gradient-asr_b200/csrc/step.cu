@@ -4,6 +4,19 @@
 
 namespace pgasr {
 
+struct FusedArgs {          // must match fused.cu
+    const float* logits; const int32_t* targets; const int32_t* in_len; const int32_t* tgt_len;
+    const float* uniforms; unsigned long long seed;
+    int B, T, V, K, Lmax, blank, reward_mode, baseline_mode;
+    float baseline_value, w_pg, w_ctc;
+    int do_pg, do_ctc;
+    float* loss; float* dlogits;
+    float* rewards; float* logp; int32_t* hyp_len; int32_t* dist; float* nll; uint8_t* samples;
+    unsigned* ctrl; double* lattice; int* lat_exp; float* loss_terms; float* nll_ws;
+};
+size_t fused_workspace_bytes(int B, int T, int V, int K, int Lmax);
+int fused_step(FusedArgs& a, void* workspace, cudaStream_t st);
+
 thread_local int g_last_cuda_error = 0;
 thread_local unsigned long long g_launches = 0;
 
@@ -56,11 +69,6 @@ __global__ void finalize_loss_kernel(const float* __restrict__ loss_terms, const
     }
 }
 
-__global__ void copy_bytes_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        dst[i] = src[i];
-}
-
 }  // namespace pgasr
 
 extern "C" int pgasr_abi_version(void) { return PGASR_ABI_VERSION; }
@@ -92,7 +100,18 @@ extern "C" int pgasr_device_check(void) {
 
 extern "C" size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax) {
     if (B < 0 || T <= 0 || V <= 0 || K <= 0 || Lmax <= 0) return 0;
-    return pgasr::carve(nullptr, B, T, V, K, Lmax).total;
+    const size_t fused = pgasr::fused_workspace_bytes(B, T, V, K, Lmax);
+    const pgasr::StepWorkspace w = pgasr::carve(nullptr, B, T, V, K, Lmax);
+    if (w.ctc_bytes == 0) return 0;
+    return fused > w.total ? fused : w.total;
+}
+
+extern "C" int pgasr_pg_ctc_step_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+    if (!workspace) return PGASR_ERR_INVALID_ARG;
+    // only the control block at the front has to start at zero; the kernel re-arms it after every step
+    const size_t n = workspace_bytes < 65536 ? workspace_bytes : 65536;
+    PGASR_CUDA_TRY(cudaMemsetAsync(workspace, 0, n, pgasr::as_stream(stream)));
+    return PGASR_OK;
 }
 
 extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, const int32_t* in_len,
@@ -105,10 +124,22 @@ extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, co
     if (!logits || !targets || !loss || !dlogits || !workspace || B <= 0 || T <= 0 || V <= 0 || K <= 0 ||
         Lmax <= 0 || blank < 0 || blank >= V)
         return PGASR_ERR_INVALID_ARG;
+    if (K > 64 || V > 32) return PGASR_ERR_UNSUPPORTED;
+    if (workspace_bytes < pgasr_pg_ctc_step_workspace_bytes(B, T, V, K, Lmax)) return PGASR_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    if ((w_pg != 0.0f || w_ctc != 0.0f) && B + 4 <= 16384 && fused_workspace_bytes(B, T, V, K, Lmax) > 0) {
+        // one launch: heterogeneous CTAs (CTC role / PG role per utterance), see fused.cu
+        FusedArgs a;
+        a.logits = logits; a.targets = targets; a.in_len = in_len; a.tgt_len = tgt_len; a.uniforms = uniforms;
+        a.seed = seed; a.B = B; a.T = T; a.V = V; a.K = K; a.Lmax = Lmax; a.blank = blank;
+        a.reward_mode = reward_mode; a.baseline_mode = baseline_mode; a.baseline_value = baseline_value;
+        a.w_pg = w_pg; a.w_ctc = w_ctc; a.do_pg = w_pg != 0.0f; a.do_ctc = w_ctc != 0.0f;
+        a.loss = loss; a.dlogits = dlogits; a.rewards = rewards; a.logp = logp; a.hyp_len = hyp_len; a.dist = dist;
+        a.nll = nll; a.samples = samples;
+        return fused_step(a, workspace, st);
+    }
     StepWorkspace w = carve(workspace, B, T, V, K, Lmax);
     if (w.ctc_bytes == 0) return PGASR_ERR_UNSUPPORTED;
-    if (workspace_bytes < w.total) return PGASR_ERR_WORKSPACE;
-    cudaStream_t st = as_stream(stream);
     uint8_t* smp = samples ? samples : w.samples;
     float* lp = logp ? logp : w.logp;
     int32_t* hl = hyp_len ? hyp_len : w.hyp_len;

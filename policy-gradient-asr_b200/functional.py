@@ -227,6 +227,8 @@ class StepWorkspace:
         if self.nbytes == 0:
             raise _native.PgasrError("pgasr_pg_ctc_step_workspace_bytes", -2, "unsupported size")
         self.buf = torch.empty((self.nbytes,), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            _native.call("pgasr_pg_ctc_step_workspace_init", _ptr(self.buf), self.nbytes, _stream())
 
 
 def pg_ctc_step(logits, targets, input_lengths=None, target_lengths=None, K=16, blank=0, reward="ed",

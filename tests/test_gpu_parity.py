@@ -301,8 +301,8 @@ def step_case(cuda, B, T, V, K, L, seed, ragged, regime, reward="ed", baseline="
                         reward=reward, baseline=baseline, baseline_value=-2.0, pg_weight=w_pg, ctc_weight=w_ctc,
                         uniforms=None if philox else dev_t(uni, cuda), seed=99,
                         want=("rewards", "nll", "logp", "dist", "hyp_len", "samples"))
-    assert np.array_equal(out["samples"].cpu().numpy(), s_ref)            # bit-exact
     if w_pg:
+        assert np.array_equal(out["samples"].cpu().numpy(), s_ref)        # bit-exact
         assert np.array_equal(out["hyp_len"].cpu().numpy(), hl_ref)
         assert np.array_equal(out["dist"].cpu().numpy(), d_ref)
         assert np.array_equal(out["rewards"].cpu().numpy(), R_ref)
@@ -372,11 +372,13 @@ def test_size_independent_properties_full_size(cuda):
     assert (d >= np.abs(hl - L)).all() and (d <= np.maximum(hl, L)).all()      # Levenshtein bounds
     g = out["dlogits"].cpu().numpy().astype(np.float64)
     assert np.abs(g.sum(-1)).max() < 1e-5            # both gradients are differences of distributions: rows sum to 0
-    # collapse is idempotent; distance to itself is zero
+    # the repeat merge (upstream collapse_fn) is idempotent; the blank drop after it only shortens
     s = out["samples"]
+    m1, k1 = F.collapse(s, blank=None)
+    m2, k2 = F.collapse(m1, k1.reshape(-1), blank=None)
+    assert torch.equal(k1, k2) and torch.equal(m1, m2)
     c1, n1 = F.collapse(s, blank=0)
-    c2, n2 = F.collapse(c1, n1.reshape(-1), blank=0)
-    assert torch.equal(n1, n2) and torch.equal(c1, c2)
+    assert bool((n1 <= k1).all()) and torch.equal(n1, out["hyp_len"])
     same = F.edit_distance(c1[:, 0, :].contiguous(), n1[:, 0].contiguous(), c1[:, 0, :].to(torch.int32).contiguous(),
                            n1[:, 0].contiguous(), rows_per_ref=1, vocab=V)
     assert (same.cpu().numpy() == 0).all()

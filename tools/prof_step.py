@@ -15,8 +15,10 @@ lg, tg, il, tl, _ = make_batch(B, 500, 30, 16, 100, seed=1)
 t = lambda a: torch.from_numpy(a).to(dev)
 lg, tg, il, tl = t(lg), t(tg), t(il), t(tl)
 ws = None
-for i in range(steps):
-    out = F.pg_ctc_step(lg, tg, il, tl, K=16, seed=i, workspace=ws)
-    ws = out["workspace"]
+modes = [(1.0, 1.0), (0.0, 1.0), (1.0, 0.0)] if os.environ.get("PROF_MODES") else [(1.0, 1.0)]
+for wp, wc in modes:
+    for i in range(steps):
+        out = F.pg_ctc_step(lg, tg, il, tl, K=16, seed=i, workspace=ws, pg_weight=wp, ctc_weight=wc)
+        ws = out["workspace"]
 torch.cuda.synchronize()
 print("loss", float(out["loss"]))
