@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpgasr_b200.so")
+LIB_PATH = os.environ.get("PGASR_LIB") or os.path.join(_HERE, "lib", "libpgasr_b200.so")   # PGASR_LIB: tools only
 
 _vp, _i, _f, _u64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_size_t
 

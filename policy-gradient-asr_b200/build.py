@@ -36,6 +36,22 @@ def needs_build():
     return any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps)
 
 
+def build_timing():
+    """Instrumented variant (-DPGASR_TIMING) for tools/phase_timing.py; not used by the product."""
+    out = os.path.join(LIBDIR, "libpgasr_b200_timing.so")
+    os.makedirs(LIBDIR, exist_ok=True)
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    r = subprocess.run([nvcc] + NVCC_FLAGS + ["-DPGASR_TIMING"] + sources() + ["-o", out], env=env,
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building the timing variant")
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
@@ -54,4 +70,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--timing" in sys.argv:
+        print(build_timing())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -346,7 +346,34 @@ struct GradRing {
     int* eslot;                   // [2 * kBatch] exponent of the published values
     int bar_full;                 // named barrier ids: bar_full + k, bar_empty + k for buffer k in {0, 1}
     int bar_empty;
+    const int* cls_off;           // [V + 1] CSR over classes: label positions li with lab[li] == v
+    const int* cls_pos;           // [L]
+    bool dbg;                     // PGASR_TIMING: this CTA records phase stamps
 };
+
+// Label positions grouped by class (counting sort), built once per utterance by one warp.  The gradient workers
+// sum the label occupancies of a class by walking its list: shared-memory atomics cost ~2 cycles per lane on
+// the one atomic unit of the SM (measured: 8 worker warps x 4 ATOMS per frame made the atomics the bottleneck).
+__device__ __forceinline__ void ctc_build_class_lists(const int32_t* __restrict__ lab_u, int L, int V, int* cls_off,
+                                                      int* cls_pos, int* scratch /* V ints */) {
+    const int lane = threadIdx.x & 31;
+    for (int v = lane; v <= V; v += 32) cls_off[v] = 0;
+    for (int v = lane; v < V; v += 32) scratch[v] = 0;
+    __syncwarp();
+    for (int li = lane; li < L; li += 32) {
+        const int c = lab_u[li];
+        if (c >= 0 && c < V) atomicAdd(&cls_off[c + 1], 1);
+    }
+    __syncwarp();
+    if (lane == 0)
+        for (int v = 0; v < V; ++v) cls_off[v + 1] += cls_off[v];
+    __syncwarp();
+    for (int li = lane; li < L; li += 32) {
+        const int c = lab_u[li];
+        if (c >= 0 && c < V) cls_pos[cls_off[c] + atomicAdd(&scratch[c], 1)] = li;
+    }
+    __syncwarp();
+}
 
 template <int SPL>
 __host__ __device__ inline size_t grad_ring_bytes() {
@@ -360,6 +387,7 @@ __device__ __forceinline__ GradRing<SPL> grad_ring_carve(unsigned char* p, int b
     r.eslot = reinterpret_cast<int*>(p + (size_t)2 * kBatch * SPL * 32 * 8);
     r.bar_full = bar_base;
     r.bar_empty = bar_base + 2;
+    r.dbg = false;
     return r;
 }
 
@@ -392,7 +420,84 @@ __device__ __forceinline__ void ctc_presum(CtcLane<SPL>& st, double h0, double h
     }
 }
 
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 // Recurrence warp of one direction over the whole utterance (tile mode).  G: workers of this direction.
+// Lattice / ring layout per frame: [SPL/2][32 lanes] double2, so each lane moves 16 bytes per access and a warp
+// access is one coalesced 512 B line.  The frame body is branch free and unrolled four times; every frame uses
+// the same code (frame 0 starts from a virtual "previous" vector that the recurrence maps onto the CTC start
+// states), so the only branches left are the loop, the rescale test and the batch barriers.
+template <int SPL, bool kAlpha>
+struct CtcWalk {
+    CtcLane<SPL> st;
+    double h0, h1;                // halo values for the frame about to be computed
+    unsigned pa_b, pa[SPL / 2];   // running shared-memory addresses of this lane's probabilities
+    int rstride;
+    bool edge;
+};
+
+template <int SPL, bool kAlpha>
+__device__ __forceinline__ void ctc_walk_halo(CtcWalk<SPL, kAlpha>& w) {
+    if (kAlpha) {
+        w.h0 = __shfl_up_sync(kFull, w.st.a[SPL - 1], 1);
+    } else {
+        w.h0 = __shfl_down_sync(kFull, w.st.a[0], 1);
+        w.h1 = __shfl_down_sync(kFull, w.st.a[1], 1);
+    }
+    w.h0 = w.edge ? 0.0 : w.h0;
+    w.h1 = w.edge ? 0.0 : w.h1;
+}
+
+template <int SPL, bool kAlpha>
+__device__ __forceinline__ void ctc_walk_rescale(CtcWalk<SPL, kAlpha>& w) {
+    int mx = 0;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) mx = max(mx, __double2hiint(w.st.a[j]));
+    mx = __reduce_max_sync(kFull, mx);
+    if (mx >= 0x00100000) {
+        const int e = (mx >> 20) - 1023;
+        const double sc = __hiloint2double((1023 - e) << 20, 0);
+        w.st.E += e;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) w.st.a[j] *= sc;
+        w.h0 *= sc;
+        w.h1 *= sc;
+    }
+}
+
+// kFirst: store the pre-emission sums to the lattice (dst = global), else the post-emission values to the ring
+// (dst = shared).  dst advances by `dstride` double2 per frame; edst (exponent per frame) by estride ints.
+template <int SPL, bool kAlpha, bool kFirst>
+__device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*& dst, ptrdiff_t dstride, int*& edst,
+                                               int estride, bool lane0) {
+    double p[SPL / 2];
+    const double pb = lds_f64(w.pa_b);
+#pragma unroll
+    for (int i = 0; i < SPL / 2; ++i) p[i] = lds_f64(w.pa[i]);
+    w.pa_b += w.rstride;
+#pragma unroll
+    for (int i = 0; i < SPL / 2; ++i) w.pa[i] += w.rstride;
+    ctc_presum<SPL, kAlpha>(w.st, w.h0, w.h1);
+    if (kFirst) {
+#pragma unroll
+        for (int jj = 0; jj < SPL / 2; ++jj) dst[jj * 32] = make_double2(w.st.a[2 * jj], w.st.a[2 * jj + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) w.st.a[j] *= (j & 1) ? p[j >> 1] : pb;
+    ctc_walk_halo<SPL, kAlpha>(w);
+    if (!kFirst) {
+#pragma unroll
+        for (int jj = 0; jj < SPL / 2; ++jj) dst[jj * 32] = make_double2(w.st.a[2 * jj], w.st.a[2 * jj + 1]);
+    }
+    if (lane0) *edst = w.st.E;
+    dst += dstride;
+    edst += estride;
+}
+
 template <int SPL, int G, bool kAlpha, typename Barrier>
 __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t* __restrict__ lab_u, int Tb, int L,
                                               int V, int RS, int blank, float* __restrict__ nll_out,
@@ -400,94 +505,225 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
                                               GradRing<SPL> ring, Barrier mid_barrier) {
     constexpr int kGroup = 32 * (1 + G);                  // this warp + its workers
     const int lane = threadIdx.x & 31;
-    const bool edge = kAlpha ? lane == 0 : lane == 31;
+    const bool lane0 = lane == 0;
     const int S = 2 * L + 1;
     const int tm = Tb / 2;
     const int n_first = kAlpha ? tm : Tb - tm;
-    CtcLane<SPL> st;
-    ctc_lane_init<SPL, kAlpha>(st, lab_u, L, V);
+    const int n2 = Tb - n_first;
+    CtcWalk<SPL, kAlpha> w;
+    ctc_lane_init<SPL, kAlpha>(w.st, lab_u, L, V);
+    w.edge = kAlpha ? lane == 0 : lane == 31;
+    const bool dbg = ring.dbg && lane == 0;
+    PGASR_STAMP(dbg, kAlpha ? 10 : 14);
 
-    for (int step = 0; step < Tb; ++step) {
-        if (step == n_first) mid_barrier();
-        const int t = kAlpha ? step : Tb - 1 - step;
-        const double* row = tile + (size_t)t * RS;
-        // probabilities of this frame (independent of the recurrence: issued first)
-        double p[SPL / 2];
-        const double pb = row[blank];
+    const int t0 = kAlpha ? 0 : Tb - 1;
+    w.rstride = kAlpha ? RS * 8 : -RS * 8;
+    const unsigned row0 = (unsigned)__cvta_generic_to_shared(tile) + (unsigned)(t0 * RS * 8);
+    w.pa_b = row0 + (unsigned)(blank * 8);
 #pragma unroll
-        for (int i = 0; i < SPL / 2; ++i) p[i] = row[st.loff[i]];
+    for (int i = 0; i < SPL / 2; ++i) w.pa[i] = row0 + (unsigned)(w.st.loff[i] * 8);
+    // virtual vector before the first frame: the recurrence turns it into the CTC start (alpha: states 0,1;
+    // beta: states S-1,S-2) -- see DESIGN.md "CTC spec"
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int s = lane * SPL + j;
+        w.st.a[j] = (kAlpha ? s == 0 : s == S - 1) ? 1.0 : 0.0;
+    }
+    w.h0 = w.h1 = 0.0;
+    ctc_walk_halo<SPL, kAlpha>(w);
 
-        if (step == 0) {
+    // ---- first half: pre-emission sums go to the lattice for the other direction -----------------
+    {
+        double2* lp = reinterpret_cast<double2*>(lat_u + (size_t)t0 * (SPL * 32)) + lane;
+        const ptrdiff_t lstride = kAlpha ? (SPL / 2) * 32 : -(SPL / 2) * 32;
+        int* ep = exp_u + t0;
+        const int estride = kAlpha ? 1 : -1;
+        int step = 0;
+        for (; step + 4 <= n_first; step += 4) {
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                const int s = lane * SPL + j;
-                const bool on_ = kAlpha ? (s <= 1 && s < S) : (s < S && s >= S - 2);
-                st.a[j] = on_ ? 1.0 : 0.0;
+            for (int u = 0; u < 4; ++u) ctc_walk_frame<SPL, kAlpha, true>(w, lp, lstride, ep, estride, lane0);
+            if (step & 4) ctc_walk_rescale<SPL, kAlpha>(w);
+        }
+        for (; step < n_first; ++step) ctc_walk_frame<SPL, kAlpha, true>(w, lp, lstride, ep, estride, lane0);
+        ctc_walk_rescale<SPL, kAlpha>(w);
+    }
+    PGASR_STAMP(dbg, kAlpha ? 11 : 15);
+    mid_barrier();
+    PGASR_STAMP(dbg, kAlpha ? 12 : 16);
+
+    // ---- second half: post-emission values go to the workers in batches of kBatch frames -----------
+    for (int q = 0; q < n2; q += kBatch) {
+        const int buf = (q / kBatch) & 1;
+        if (q >= 2 * kBatch) named_bar_sync(ring.bar_empty + buf, kGroup);
+        double2* sp = reinterpret_cast<double2*>(ring.slots + (size_t)(buf * kBatch) * (SPL * 32)) + lane;
+        int* ep = ring.eslot + buf * kBatch;
+        const int nfr = min(kBatch, n2 - q);
+        if (nfr == kBatch) {
+#pragma unroll 1
+            for (int h = 0; h < kBatch / 4; ++h) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ctc_walk_frame<SPL, kAlpha, false>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
             }
         } else {
-            double h0, h1 = 0.0;
-            if (kAlpha) {
-                h0 = __shfl_up_sync(kFull, st.a[SPL - 1], 1);
-            } else {
-                h0 = __shfl_down_sync(kFull, st.a[0], 1);
-                h1 = __shfl_down_sync(kFull, st.a[1], 1);
-            }
-            h0 = edge ? 0.0 : h0;
-            h1 = edge ? 0.0 : h1;
-            ctc_presum<SPL, kAlpha>(st, h0, h1);
+            for (int u = 0; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
         }
-
-        if (step < n_first) {                             // first half: pre-emission sums for the other direction
-            double* lp = lat_u + (size_t)t * (SPL * 32) + lane;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) lp[j * 32] = st.a[j];
-            if (lane == 0) exp_u[t] = st.E;
-        }
-#pragma unroll
-        for (int j = 0; j < SPL; ++j) st.a[j] *= (j & 1) ? p[j >> 1] : pb;
-
-        if (step >= n_first) {                            // second half: hand the post-emission values over
-            const int q = step - n_first;
-            const int buf = (q / kBatch) & 1;
-            if ((q % kBatch) == 0 && q >= 2 * kBatch) named_bar_sync(ring.bar_empty + buf, kGroup);
-            const int slot = q % (2 * kBatch);
-            double* sp = ring.slots + (size_t)slot * (SPL * 32) + lane;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) sp[j * 32] = st.a[j];
-            if (lane == 0) ring.eslot[slot] = st.E;
-            if ((q % kBatch) == kBatch - 1 || step == Tb - 1) named_bar_arrive(ring.bar_full + buf, kGroup);
-        }
-
-        if ((step & 3) == 3) {                            // exact power-of-two rescale
-            int mx = 0;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) mx = max(mx, __double2hiint(st.a[j]));
-            mx = __reduce_max_sync(kFull, mx);
-            if (mx >= 0x00100000) {
-                const int e = (mx >> 20) - 1023;
-                const double sc = __hiloint2double((1023 - e) << 20, 0);
-                st.E += e;
-#pragma unroll
-                for (int j = 0; j < SPL; ++j) st.a[j] *= sc;
-            }
-        }
+        named_bar_arrive(ring.bar_full + buf, kGroup);
+        ctc_walk_rescale<SPL, kAlpha>(w);
     }
-    if (Tb == n_first) mid_barrier();                     // (keeps the barrier counts equal when the half is empty)
+    PGASR_STAMP(dbg, kAlpha ? 13 : 17);
 
     if (kAlpha) {
         double fin = 0.0;
 #pragma unroll
         for (int j = 0; j < SPL; ++j) {
             const int s = lane * SPL + j;
-            if (s < S && s >= S - 2) fin += st.a[j];
+            if (s < S && s >= S - 2) fin += w.st.a[j];
         }
         fin = warp_sum(fin);
         if (lane == 0)
-            *nll_out = fin > 0.0 ? (float)(-(log(fin) + (double)st.E * 0.69314718055994530942)) : INFINITY;
+            *nll_out = fin > 0.0 ? (float)(-(log(fin) + (double)w.st.E * 0.69314718055994530942)) : INFINITY;
     }
 }
 
-// Gradient worker g of one direction: frames q with q % G == g of that direction's second half.
+// Gradient worker g of one direction: frames q with q % G == g of that direction's second half.  The frames a
+// worker owns in one batch are processed side by side (separate accumulators) so their latencies overlap, and the
+// other direction's lattice rows of the NEXT batch are already in flight while the current one is processed.
+template <int SPL, int G, bool kAlpha>
+struct CtcWorker {
+    static constexpr int kPer = kBatch / G;               // frames of a batch per worker
+    static constexpr bool kPrefetch = kPer * SPL <= 32;   // keep the prefetch within the register budget
+    static constexpr int kHold = kPrefetch ? kPer : 1;
+    double2 o[kHold][SPL / 2];
+    int eo[kHold];
+};
+
+template <int SPL, int G, bool kAlpha>
+__device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, int nb, int g, int n_first, int n2,
+                                                 int Tb, const double* __restrict__ lat_u,
+                                                 const int* __restrict__ exp_u) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kHold; ++r) {
+        const int q = nb * kBatch + g + r * G;
+        if (CtcWorker<SPL, G, kAlpha>::kPrefetch && q < n2) {
+            const int step = n_first + q;
+            const int t = kAlpha ? step : Tb - 1 - step;
+            const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lane;
+#pragma unroll
+            for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = __ldcg(lp + jj * 32);
+            wk.eo[r] = __ldcg(exp_u + t);
+        }
+    }
+}
+
+struct WorkerNorm { double invZ0; int E0; bool dead, have; long long tA, tB, tWait, tBusy; };
+
+constexpr int kClsRegs = 8;       // label positions of this lane's class held in registers
+
+template <int SPL, int G, bool kAlpha>
+__device__ __forceinline__ void ctc_worker_batch(CtcWorker<SPL, G, kAlpha>& wk, WorkerNorm& nm, int nb, int g,
+                                                 int n_first, int n2, int Tb, const double* tile, int V, int RS,
+                                                 int blank, float grad_scale, float* __restrict__ dlog_u,
+                                                 const double* __restrict__ lat_u, const int* __restrict__ exp_u,
+                                                 const GradRing<SPL>& ring, int* gam, int ccnt,
+                                                 const int (&cpos)[kClsRegs]) {
+    constexpr int kPer = CtcWorker<SPL, G, kAlpha>::kPer;
+    constexpr bool kPrefetch = CtcWorker<SPL, G, kAlpha>::kPrefetch;
+    constexpr int kGam = 16 * SPL;                        // ints per frame: SPL/2 label occupancies per lane
+    const int lane = threadIdx.x & 31;
+    int gb[kPer];
+#ifdef PGASR_TIMING
+    const long long ta1 = clock64();
+#endif
+    // phase A: occupancies of every owned frame; label states go to gam[frame][label index] (2^-30 fixed point)
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+        const int q = nb * kBatch + g + r * G;
+        gb[r] = 0;
+        if (q < n2) {
+            const int step = n_first + q;
+            const int t = kAlpha ? step : Tb - 1 - step;
+            const int slot = q % (2 * kBatch);
+            const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 32)) + lane;
+            const int rr = kPrefetch ? r : 0;
+            if (!kPrefetch) {
+                const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lane;
+#pragma unroll
+                for (int jj = 0; jj < SPL / 2; ++jj) wk.o[0][jj] = __ldcg(lp + jj * 32);
+                wk.eo[0] = __ldcg(exp_u + t);
+            }
+            double wv[SPL];
+            double zb = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < SPL / 2; ++jj) {
+                const double2 av = sp[jj * 32];
+                wv[2 * jj] = av.x * wk.o[rr][jj].x;
+                wv[2 * jj + 1] = av.y * wk.o[rr][jj].y;
+                zb += wv[2 * jj];
+            }
+            const int E = ring.eslot[slot];
+            if (!nm.have) {                               // this worker's first frame: measure Z0 = P / 2^(E+eo)
+                double zl = 0.0;
+#pragma unroll
+                for (int j = 1; j < SPL; j += 2) zl += wv[j];
+                const double Z0 = warp_sum(zb + zl);
+                nm.dead = !(Z0 > 0.0);
+                nm.invZ0 = nm.dead ? 0.0 : kCtcFix / Z0;
+                nm.E0 = E + wk.eo[rr];
+                nm.have = true;
+            }
+            const double c = nm.invZ0 * pow2i(E + wk.eo[rr] - nm.E0);
+            gb[r] = __reduce_add_sync(kFull, __double2loint(fma(zb, c, kCtcMagic)));
+            int* gr = gam + r * kGam + lane * (SPL / 2);
+#pragma unroll
+            for (int i = 0; i < SPL / 2; ++i) gr[i] = __double2loint(fma(wv[2 * i + 1], c, kCtcMagic));
+        }
+    }
+    __syncwarp();
+#ifdef PGASR_TIMING
+    const long long ta2 = clock64();
+    nm.tA += ta2 - ta1;
+#endif
+    // phase B: gradient rows; lane v sums the label occupancies of class v
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+        const int q = nb * kBatch + g + r * G;
+        if (q < n2) {
+            const int step = n_first + q;
+            const int t = kAlpha ? step : Tb - 1 - step;
+            const double* row = tile + (size_t)t * RS;
+            float* out = dlog_u + (size_t)t * V;
+            const int* gr = gam + r * kGam;
+            if (V <= 32) {
+                int occ = 0;
+#pragma unroll
+                for (int i = 0; i < kClsRegs; ++i)
+                    if (i < ccnt) occ += gr[cpos[i]];
+                for (int i = kClsRegs; i < ccnt; ++i) occ += gr[ring.cls_pos[ring.cls_off[lane] + i]];
+                if (lane == blank) occ = gb[r];
+                if (lane < V) {
+                    const int pfix = __double2loint(fma(row[lane], kCtcFix, kCtcMagic));
+                    const float gval = grad_scale * ((float)(pfix - occ) * kCtcUnfix);
+                    out[lane] = nm.dead ? 0.0f : gval;
+                }
+            } else {
+                for (int v = lane; v < V; v += 32) {
+                    int occ = 0;
+                    for (int i = ring.cls_off[v]; i < ring.cls_off[v + 1]; ++i) occ += gr[ring.cls_pos[i]];
+                    if (v == blank) occ = gb[r];
+                    const int pfix = __double2loint(fma(row[v], kCtcFix, kCtcMagic));
+                    const float gval = grad_scale * ((float)(pfix - occ) * kCtcUnfix);
+                    out[v] = nm.dead ? 0.0f : gval;
+                }
+            }
+        }
+    }
+    __syncwarp();
+#ifdef PGASR_TIMING
+    nm.tB += clock64() - ta2;
+#endif
+}
+
 template <int SPL, int G, bool kAlpha, typename Barrier>
 __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const int32_t* __restrict__ lab_u, int Tb,
                                                 int L, int V, int RS, int blank, float grad_scale,
@@ -496,74 +732,57 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
                                                 Barrier mid_barrier) {
     static_assert(kBatch % G == 0, "workers must divide the batch");
     constexpr int kGroup = 32 * (1 + G);
+    constexpr int kPer = kBatch / G;
     const int lane = threadIdx.x & 31;
     const int tm = Tb / 2;
     const int n_first = kAlpha ? tm : Tb - tm;
     const int n2 = Tb - n_first;
-    int loff[SPL / 2];
+    // label positions of class `lane` (the classes beyond 32, if any, are walked from shared memory)
+    int ccnt = 0, cpos[kClsRegs];
+    if (lane < V) ccnt = ring.cls_off[lane + 1] - ring.cls_off[lane];
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) {
-        const int li = (lane * SPL) / 2 + i;
-        const int c = li < L ? lab_u[li] : -1;
-        loff[i] = c >= 0 ? c : V;
-    }
-    for (int v = lane; v <= V; v += 32) racc[v] = 0;
-    __syncwarp();
+    for (int i = 0; i < kClsRegs; ++i) cpos[i] = (i < ccnt) ? ring.cls_pos[ring.cls_off[lane] + i] : 0;
+    (void)lab_u; (void)L;
     mid_barrier();                                        // the other direction's half-lattice is complete
-    double invZ0 = 0.0;
-    int E0 = 0;
-    bool dead = false, have = false;
+    WorkerNorm nm;
+    nm.invZ0 = 0.0; nm.E0 = 0; nm.dead = false; nm.have = false;
+    nm.tA = nm.tB = nm.tWait = nm.tBusy = 0;
     const int nbatch = (n2 + kBatch - 1) / kBatch;
-    for (int nb = 0; nb < nbatch; ++nb) {
-        const int buf = nb & 1;
-        // this worker's frames of the batch: their lattice rows can be fetched before the batch is ready
-        named_bar_sync(ring.bar_full + buf, kGroup);
-        for (int q = nb * kBatch + g; q < min(n2, (nb + 1) * kBatch); q += G) {
-            const int step = n_first + q;
-            const int t = kAlpha ? step : Tb - 1 - step;
-            const double* lp = lat_u + (size_t)t * (SPL * 32) + lane;
-            double o[SPL];
+    CtcWorker<SPL, G, kAlpha> wa, wb;                     // ping-pong: current batch / next batch
+    ctc_worker_fetch<SPL, G, kAlpha>(wa, 0, g, n_first, n2, Tb, lat_u, exp_u);
+    for (int nb = 0; nb < nbatch; nb += 2) {
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) o[j] = __ldcg(lp + j * 32);
-            const int eo = __ldcg(exp_u + t);
-            const int slot = q % (2 * kBatch);
-            const double* sp = ring.slots + (size_t)slot * (SPL * 32) + lane;
-            double w[SPL];
-            double zb = 0.0;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                w[j] = sp[j * 32] * o[j];
-                if (!(j & 1)) zb += w[j];
-            }
-            const int E = ring.eslot[slot];
-            if (!have) {                                  // this worker's first frame: measure Z0 = P / 2^(E+eo)
-                double zl = 0.0;
-#pragma unroll
-                for (int j = 1; j < SPL; j += 2) zl += w[j];
-                const double Z0 = warp_sum(zb + zl);
-                dead = !(Z0 > 0.0);
-                invZ0 = dead ? 0.0 : kCtcFix / Z0;
-                E0 = E + eo;
-                have = true;
-            }
-            const double c = invZ0 * pow2i(E + eo - E0);
-            const int gb = __reduce_add_sync(kFull, __double2loint(fma(zb, c, kCtcMagic)));
-#pragma unroll
-            for (int j = 1; j < SPL; j += 2) atomicAdd(&racc[loff[j >> 1]], __double2loint(fma(w[j], c, kCtcMagic)));
-            __syncwarp();
-            const double* row = tile + (size_t)t * RS;
-            float* out = dlog_u + (size_t)t * V;
-            for (int v = lane; v < V; v += 32) {
-                const int occ = v == blank ? gb : racc[v];
-                racc[v] = 0;
-                const int pfix = __double2loint(fma(row[v], kCtcFix, kCtcMagic));
-                const float gr = grad_scale * ((float)(pfix - occ) * kCtcUnfix);
-                out[v] = dead ? 0.0f : gr;
-            }
-            __syncwarp();
+        for (int half = 0; half < 2; ++half) {
+            const int b_ = nb + half;
+            if (b_ >= nbatch) break;
+            CtcWorker<SPL, G, kAlpha>& cur = half == 0 ? wa : wb;
+            CtcWorker<SPL, G, kAlpha>& nxt = half == 0 ? wb : wa;
+            if (b_ + 1 < nbatch) ctc_worker_fetch<SPL, G, kAlpha>(nxt, b_ + 1, g, n_first, n2, Tb, lat_u, exp_u);
+            const int buf = b_ & 1;
+#ifdef PGASR_TIMING
+            const long long w0 = clock64();
+#endif
+            named_bar_sync(ring.bar_full + buf, kGroup);
+#ifdef PGASR_TIMING
+            const long long w1 = clock64();
+            nm.tWait += w1 - w0;
+#endif
+            ctc_worker_batch<SPL, G, kAlpha>(cur, nm, b_, g, n_first, n2, Tb, tile, V, RS, blank, grad_scale, dlog_u,
+                                             lat_u, exp_u, ring, racc, ccnt, cpos);
+#ifdef PGASR_TIMING
+            nm.tBusy += clock64() - w1;
+#endif
+            if (b_ + 2 < nbatch) named_bar_arrive(ring.bar_empty + buf, kGroup);   // buffer may be overwritten
         }
-        if (nb + 2 < nbatch) named_bar_arrive(ring.bar_empty + buf, kGroup);   // buffer may be overwritten
     }
+#ifdef PGASR_TIMING
+    if (ring.dbg && lane == 0 && g == 0) {
+        g_dbg[kAlpha ? 20 : 22] = nm.tWait;
+        g_dbg[kAlpha ? 21 : 23] = nm.tBusy;
+        g_dbg[kAlpha ? 25 : 29] = nm.tA;
+        g_dbg[kAlpha ? 26 : 30] = nm.tB;
+    }
+#endif
 }
 
 }  // namespace pgasr

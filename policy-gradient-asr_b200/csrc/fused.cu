@@ -58,6 +58,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     L = min(max(L, 0), a.Lmax);
     float* dlog_u = a.dlogits + (size_t)b * T * V;
     float* nll_u = (a.nll ? a.nll : a.nll_ws) + b;
+    PGASR_STAMP(b == 0 && threadIdx.x == 0, 0);
     for (int i = Tb * V + threadIdx.x; i < T * V; i += kThreads) dlog_u[i] = 0.0f;
     if (Tb == 0) {
         if (threadIdx.x == 0) *nll_u = L == 0 ? 0.0f : INFINITY;
@@ -66,14 +67,73 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         unsigned char* p = smem_raw + (size_t)T * RS * 8;
         GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
         GradRing<SPL> ring_b = grad_ring_carve<SPL>(p, 6);                  p += grad_ring_bytes<SPL>();
-        int* racc_all = reinterpret_cast<int*>(p);                          // [2G][V + 2]
+        int* gam_all = reinterpret_cast<int*>(p);                           // [2 kBatch frames][16 SPL]
+        p += (size_t)2 * kBatch * 16 * SPL * sizeof(int);
+        int* cls_off = reinterpret_cast<int*>(p);                           // [V + 1]
+        int* cls_scr = cls_off + (V + 1);                                   // [V] counting-sort scratch
+        int* cls_pos = cls_scr + V;                                         // [Lmax]
+        ring_a.dbg = ring_b.dbg = (b == 0);
+        PGASR_STAMP(b == 0 && threadIdx.x == 0, 1);
+        // softmax tile.  The raw logits are staged through the (not yet used) ring region with cp.async, then one
+        // thread per frame makes three passes over its row -- max, exp + sum, normalise -- visiting the classes in
+        // a per-thread rotated order so that neither the staged reads (row stride V floats) nor the fp64 tile
+        // writes (row stride RS doubles) collide on a shared-memory bank.
         const float* lg = a.logits + (size_t)b * T * V;
-        for (int t = threadIdx.x; t < Tb; t += kThreads)
-            softmax_row_f64(lg + (size_t)t * V, nullptr, tile + (size_t)t * RS, V, RS);
+        {
+            float* stage = reinterpret_cast<float*>(smem_raw + (size_t)T * RS * 8);
+            const size_t stage_bytes = 2 * grad_ring_bytes<SPL>() + (size_t)2 * kBatch * 16 * SPL * sizeof(int);
+            const int chunk = (int)(stage_bytes / ((size_t)V * 4)) & ~3;
+            const bool al16 = (((size_t)T * V * 4) & 15) == 0;
+            for (int c0 = 0; c0 < Tb; c0 += chunk) {
+                const int n = min(chunk, Tb - c0);
+                const float* src = lg + (size_t)c0 * V;
+                if (al16) {
+                    const int n16 = n * V / 4, rem = n * V - n16 * 4;
+                    for (int i = threadIdx.x; i < n16; i += kThreads)
+                        cp_async16(reinterpret_cast<char*>(stage) + (size_t)i * 16,
+                                   reinterpret_cast<const char*>(src) + (size_t)i * 16);
+                    for (int i = threadIdx.x; i < rem; i += kThreads) cp_async4(stage + n16 * 4 + i, src + n16 * 4 + i);
+                } else {
+                    for (int i = threadIdx.x; i < n * V; i += kThreads) cp_async4(stage + i, src + i);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+                for (int t = threadIdx.x; t < n; t += kThreads) {
+                    float* zr = stage + (size_t)t * V;
+                    double* orow = tile + (size_t)(c0 + t) * RS;
+                    float m = -INFINITY;
+                    for (int k = 0; k < 32; ++k) {
+                        const int idx = (k + t) & 31;
+                        if (idx < V) m = fmaxf(m, zr[idx]);
+                    }
+                    float ssum = 0.0f;
+                    for (int k = 0; k < 32; ++k) {
+                        const int idx = (k + t) & 31;
+                        if (idx < V) {
+                            const float e = __expf(zr[idx] - m);
+                            zr[idx] = e;
+                            ssum += e;
+                        }
+                    }
+                    const float inv = 1.0f / ssum;
+                    for (int k = 0; k < 32; ++k) {
+                        const int idx = (k + t) & 31;
+                        if (idx < RS) orow[idx] = idx < V ? (double)(zr[idx] * inv) : 0.0;
+                    }
+                    for (int idx = 32; idx < RS; ++idx) orow[idx] = 0.0;
+                }
+                __syncthreads();
+            }
+        }
+        const int32_t* lab_u = a.targets + (size_t)b * a.Lmax;
+        if (warp == 0) ctc_build_class_lists(lab_u, L, V, cls_off, cls_pos, cls_scr);
+        ring_a.cls_off = ring_b.cls_off = cls_off;
+        ring_a.cls_pos = ring_b.cls_pos = cls_pos;
         __syncthreads();
+        PGASR_STAMP(b == 0 && threadIdx.x == 0, 2);
         double* lat_u = a.lattice + (size_t)b * T * (SPL * 32);
         int* exp_u = a.lat_exp + (size_t)b * T;
-        const int32_t* lab_u = a.targets + (size_t)b * a.Lmax;
         const float gs = a.w_ctc / (float)a.B;
         auto mid = [] {
             __threadfence_block();
@@ -86,13 +146,14 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
             ctc_walk_tile<SPL, G, false>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_b, mid);
         else if (role == 2)
             ctc_grad_worker<SPL, G, true>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_a,
-                                          racc_all + g * (V + 2), mid);
+                                          gam_all + g * (kBatch / G) * 16 * SPL, mid);
         else if (role == 3)
             ctc_grad_worker<SPL, G, false>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_b,
-                                           racc_all + (G + g) * (V + 2), mid);
+                                           gam_all + (G + g) * (kBatch / G) * 16 * SPL, mid);
     }
     __threadfence();                                       // rows and nll visible device-wide before the flag
     __syncthreads();
+    PGASR_STAMP(b == 0 && threadIdx.x == 0, 3);
     if (threadIdx.x == 0) st_release(a.ctrl + 4 + b, 1u);
 }
 
@@ -122,6 +183,8 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     int* dist_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
     float* misc_s = reinterpret_cast<float*>(smem_raw + off);    // [0] sum of advantages
 
+    const bool dbg = b == 0 && threadIdx.x == 0;
+    PGASR_STAMP(dbg, 30);
     // ---- P0: logits tile -> shared memory ------------------------------------------------------
     const float* lg = a.logits + (size_t)b * T * V;
     if ((((size_t)T * V * 4) & 15) == 0) {
@@ -137,6 +200,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     cp_async_wait<0>();
     __syncthreads();
 
+    PGASR_STAMP(dbg, 31);
     // ---- P1: softmax CDF + K draws, one thread per frame (DESIGN.md "sampler spec") ------------
     const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     for (int t0 = 0; t0 < T; t0 += kThreads) {
@@ -190,6 +254,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     }
     __syncthreads();
 
+    PGASR_STAMP(dbg, 32);
     // ---- P2: collapse (one warp per sample) and the match table of the transcript ---------------
     const int32_t* ref = a.targets + (size_t)b * a.Lmax;
     for (int j = threadIdx.x; j < m; j += kThreads) {
@@ -215,6 +280,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     }
     __syncthreads();
 
+    PGASR_STAMP(dbg, 33);
     // ---- P3: edit distance, one thread per sample ------------------------------------------------
     if ((int)threadIdx.x < K) {
         const int k = threadIdx.x;
@@ -222,6 +288,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     }
     __syncthreads();
 
+    PGASR_STAMP(dbg, 34);
     // ---- P4: rewards, baseline, advantages, loss term (warp 0) -----------------------------------
     if (warp == 0) {
         float sumR = 0.0f;
@@ -260,6 +327,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     }
     __syncthreads();
 
+    PGASR_STAMP(dbg, 35);
     // ---- P5: REINFORCE gradient tile, in place of the logits tile ---------------------------------
     const float coef = a.w_pg / ((float)a.B * (float)K);
     const bool dense = a.baseline_mode != PGASR_BASELINE_MEAN;   // sum_k A_k == 0 under the per-utterance mean
@@ -283,6 +351,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     }
     __syncthreads();
 
+    PGASR_STAMP(dbg, 36);
     // ---- P6: add the tile onto the CTC rows (or store it when there is no CTC term) ---------------
     float* dlog_u = a.dlogits + (size_t)b * T * V;
     if (a.do_ctc) {
@@ -292,6 +361,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
         }
         __syncthreads();
     }
+    PGASR_STAMP(dbg, 37);
     if ((((size_t)T * V * 4) & 15) == 0) {
         float4* d4 = reinterpret_cast<float4*>(dlog_u);
         const float4* t4 = reinterpret_cast<const float4*>(ztile);
@@ -307,6 +377,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
         for (int i = threadIdx.x; i < T * V; i += kThreads)
             dlog_u[i] = a.do_ctc ? __ldcg(dlog_u + i) + ztile[i] : ztile[i];
     }
+    PGASR_STAMP(dbg, 38);
 }
 
 template <int SPL, int kThreads>
@@ -363,7 +434,8 @@ static FusedWs fused_ws(int B, int T, int spl) {
 static size_t fused_smem(int T, int V, int K, int spl, int threads) {
     const int RS = ctc_row_stride(V);
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
-    const size_t ctc = (size_t)T * RS * sizeof(double) + 2 * ring + (size_t)2 * (threads / 128) * (V + 2) * sizeof(int);
+    const size_t ctc = (size_t)T * RS * sizeof(double) + 2 * ring + (size_t)2 * kBatch * 16 * spl * sizeof(int) +
+                       (size_t)(2 * V + 1 + 512) * sizeof(int);
     const int Tp = (T + 15) & ~15, W = spl / 2;
     size_t pg = (((size_t)T * V * 4 + 15) & ~(size_t)15) + (size_t)2 * K * Tp + (size_t)(V + 1) * W * 4 + 16;
     pg += (size_t)(threads / 32) * kFusedMaxK * 4 + 3 * kFusedMaxK * 4 + 16;
@@ -409,3 +481,15 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
 }
 
 }  // namespace pgasr
+
+#ifdef PGASR_TIMING
+extern "C" __attribute__((visibility("default"))) int pgasr_debug_read(long long* host64, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(host64, pgasr::g_dbg, sizeof(long long) * 64) != cudaSuccess) return -5;
+    if (reset) {
+        long long z[64] = {0};
+        cudaMemcpyToSymbol(pgasr::g_dbg, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

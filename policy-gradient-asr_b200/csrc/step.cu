@@ -89,6 +89,8 @@ extern "C" int pgasr_last_cuda_error(void) { return pgasr::g_last_cuda_error; }
 
 extern "C" uint64_t pgasr_launch_count(void) { return pgasr::g_launches; }
 
+
+
 extern "C" int pgasr_device_check(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return PGASR_ERR_NO_DEVICE;

@@ -1,0 +1,40 @@
+"""Phase timing of the fused kernel (CTA of utterance 0) from the -DPGASR_TIMING build:
+    python policy-gradient-asr_b200/build.py --timing
+    PGASR_LIB=policy-gradient-asr_b200/lib/libpgasr_b200_timing.so python tools/phase_timing.py
+"""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from pgasr_b200 import _native, functional as F  # noqa: E402
+from tests.synth import make_batch  # noqa: E402
+
+B = int(os.environ.get("PROF_B", "64"))
+dev = torch.device("cuda:0")
+lg, tg, il, tl, _ = make_batch(B, 500, 30, 16, 100, seed=1)
+t = lambda a: torch.from_numpy(a).to(dev)
+lg, tg, il, tl = t(lg), t(tg), t(il), t(tl)
+lib = _native.lib()
+buf = (ctypes.c_longlong * 64)()
+ws = None
+for mode, (wp, wc) in {"both": (1.0, 1.0), "ctc": (0.0, 1.0), "pg": (1.0, 0.0)}.items():
+    for i in range(3):
+        out = F.pg_ctc_step(lg, tg, il, tl, K=16, seed=i, workspace=ws, pg_weight=wp, ctc_weight=wc)
+        ws = out["workspace"]
+    lib.pgasr_debug_read(buf, 1)
+    out = F.pg_ctc_step(lg, tg, il, tl, K=16, seed=7, workspace=ws, pg_weight=wp, ctc_weight=wc)
+    lib.pgasr_debug_read(buf, 1)
+    d = list(buf)
+    print(f"== {mode} (cycles)")
+    if wc:
+        print(f" ctc: zero-rows {d[1]-d[0]}  softmax-tile {d[2]-d[1]}  lattice+grad {d[3]-d[2]}  total {d[3]-d[0]}")
+        print(f" alpha walker: first-half {d[11]-d[10]}  mid-wait {d[12]-d[11]}  second-half {d[13]-d[12]}")
+        print(f" beta  walker: first-half {d[15]-d[14]}  mid-wait {d[16]-d[15]}  second-half {d[17]-d[16]}")
+        print(f" alpha worker0: waiting {d[20]}  busy {d[21]}   beta worker0: waiting {d[22]}  busy {d[23]}")
+        print(f" alpha worker0: phaseA {d[25]}  phaseB {d[26]}")
+    if wp:
+        names = ["tile-load", "sample", "collapse", "myers", "advantages", "grad-tile", "flag-wait", "rmw-out"]
+        print(" pg:  " + "  ".join(f"{n} {d[31+i]-d[30+i]}" for i, n in enumerate(names)) + f"  total {d[38]-d[30]}")
