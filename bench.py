@@ -235,62 +235,68 @@ def run_ours(args):
     sampler.join(1.0)
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- dominant kernel, timed alone with CUDA events (roofline) --------------------------------
-    probs = [torch.softmax(b["logits"], -1) for b in devb[:min(pool, 8)]]
-    for i in range(3):
-        F.ctc_loss_grad(devb[0]["logits"], devb[0]["targets"], devb[0]["in_len"], devb[0]["tgt_len"], probs=probs[0])
-    torch.cuda.synchronize()
-    ctc_ws_dl = torch.empty_like(devb[0]["logits"])
+    # ---- dominant kernel (roofline): the step IS one launch of pg_ctc_fused_kernel; each launch is bracketed by its
+    # own CUDA event pair on the launching stream (torch's current stream) and the durations are averaged ----------
     nrep = min(args.steps, 200)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ctc_ms = 0.0
-    for i in range(nrep):
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nrep)]
+    launches1 = _native.lib().pgasr_launch_count()
+    for i, (k0, k1) in enumerate(pairs):
         b = devb[i % pool]
-        pr = probs[i % len(probs)] if (i % pool) < len(probs) else None
         k0.record()
-        F.ctc_loss_grad(b["logits"], b["targets"], b["in_len"], b["tgt_len"], probs=pr)
+        step(i, b)
         k1.record()
-        torch.cuda.synchronize()
-        ctc_ms += k0.elapsed_time(k1)
-    ctc_ms /= nrep
+    torch.cuda.synchronize()
+    per_step_launches = (_native.lib().pgasr_launch_count() - launches1) / nrep
+    kernel_ms = sum(k0.elapsed_time(k1) for k0, k1 in pairs) / nrep
     peak, peak_src = measured_peak()
-    ctc_bytes = B * (8 * T * V + 4 * L + 8 + 4)                # K5 algorithmic bytes: probs/logits in, dlogits out, labels, nll
-    achieved = ctc_bytes / (ctc_ms * 1e-3) / 1e9
-    step_bytes = B * algorithmic_bytes_per_utt(T, V, L, K)
-    roofline = {"bound": "hbm", "kernel": "ctc_kernel (CTC alpha-beta, dominant)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": traffic_from_profile(f"B={B},T={T},V={V},L={L}"),
-                "algorithmic_bytes_per_launch": ctc_bytes, "kernel_ms": ctc_ms,
+    step_bytes = B * algorithmic_bytes_per_utt(T, V, L, K)       # 120 540 B/utt at the headline shape
+    achieved = step_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "pg_ctc_fused_kernel<8,512> (the whole step: 1 launch)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peak_src == "measured" else peak_src,
+                "traffic": traffic_from_profile(f"B={B},T={T},V={V},K={K},L={L}"),
+                "algorithmic_bytes_per_launch": step_bytes, "kernel_ms": kernel_ms,
+                "launches_per_step": per_step_launches,
                 "step_achieved_GBps": step_bytes * args.steps / (ms * 1e-3) / 1e9,
-                "step_frac": step_bytes * args.steps / (ms * 1e-3) / 1e9 / peak,
-                "note": "serial-depth bound path (T dependent lattice steps); see DESIGN.md"}
+                "note": "latency bound, not bandwidth bound: T dependent lattice frames per utterance and only "
+                        "2B=128 CTAs of work; see DESIGN.md section 5"}
 
-    # ---- end to end through the public API with host buffers ("e2e") --------------------------------
+    # ---- end to end through the public host-buffer API ("e2e"): pinned HOST inputs and outputs, every step copies
+    # its logits/targets/lengths H2D and its loss, rewards, nll AND the full dlogits D2H inside the timed region;
+    # HostPipeline keeps `depth` steps in flight so the copies of neighbouring steps overlap the kernel ----------
     e2e = None
     if not args.no_e2e:
-        out_host = [torch.empty((B, T, V), dtype=torch.float32).pin_memory() for _ in range(2)]
-        small_host = torch.empty((B * K + B + 1,), dtype=torch.float32).pin_memory()
+        depth = 3
+        pipe = pgasr_b200.HostPipeline(B, T, V, K, L, depth=depth)
+        outs = [pipe.output_buffers() for _ in range(depth)]
 
         def e2e_step(i):
             h = host[i % pool]
-            d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
-            o = step(i, d)
-            out_host[i & 1].copy_(o["dlogits"], non_blocking=True)
-            small = torch.cat([o["rewards"].reshape(-1), o["nll"], o["loss"].reshape(1)])
-            small_host.copy_(small, non_blocking=True)
-        for i in range(3):
+            return pipe.submit(h["logits"], h["targets"], h["in_len"], h["tgt_len"], out=outs[i % depth], seed=0x5EED + i)
+        for i in range(max(args.warmup, 3)):
             e2e_step(i)
+        pipe.wait()
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
             e2e_step(i)
+        pipe.wait()
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
+        # single-step latency (submit + wait, nothing else in flight)
+        lat = []
+        for i in range(20):
+            t1 = time.perf_counter()
+            pipe.wait(e2e_step(i))
+            lat.append(time.perf_counter() - t1)
+        pipe.close()
         h2d = bytes_logits + B * L * 4 + 2 * B * 4
-        d2h = bytes_logits + (B * K + B + 1) * 4
+        d2h = bytes_logits + (B * K + B + 4) * 4
         e2e = {"value": world * B * args.steps / dt, "unit": "utt/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / args.steps,
-               "outputs_to_host": "loss, rewards[B,K], nll[B], dlogits[B,T,V]"}
+               "api": f"HostPipeline.submit/wait (pgasr_host_* C ABI), depth {depth}, pinned host buffers",
+               "outputs_to_host": "loss, rewards[B,K], nll[B], dlogits[B,T,V]",
+               "sync_step_latency_ms": 1e3 * statistics.median(lat)}
 
     # ---- CPU baseline on rank 0 at N=1 ----------------------------------------------------------------
     cpu = None

@@ -19,6 +19,7 @@
  *   pgasr_ctc_loss_grad             (no upstream code)  CTC alpha-beta loss and gradient
  *   pgasr_pg_ctc_step               model.py:235-237    criterion(model_out, t); loss.backward()
  *                                                       -- the whole loss step in one call
+ *   pgasr_host_*                    model.py:317-320    the same step on HOST arrays, pipelined
  * The Python binding a maintainer adds is shown in INTEGRATION.md.
  *
  * Layouts (all contiguous, batch first as upstream: batch_first=True, model.py:44,55):
@@ -143,6 +144,26 @@ PGASR_API int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, con
                       float* loss, float* dlogits, float* rewards, float* logp, int32_t* hyp_len,
                       int32_t* dist, float* nll, uint8_t* samples,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the step on HOST buffers (upstream hands the metric/reward code host arrays: model.py:317-320) ----
+ * A pipeline owns the device buffers for `depth` steps in flight, three streams (copy-in, compute, copy-out)
+ * and the step workspace; create/destroy are the only calls that allocate.  submit() takes HOST pointers
+ * (page-locked for the copies to be asynchronous: pgasr_host_pin, or any pinned allocation), enqueues
+ * H2D -> pgasr_pg_ctc_step -> D2H and returns a ticket without waiting; it blocks only when the step
+ * submitted `depth` steps earlier has not finished.  wait(ticket) returns once the outputs of every step up to
+ * `ticket` are in the caller's host buffers (ticket < 0: all submitted steps).  in_len_h / tgt_len_h may be
+ * NULL (full lengths), rewards_h / nll_h may be NULL.  Sampling is Philox(seed).  One pipeline serves one host
+ * thread at a time.  Host input buffers may be reused as soon as wait() for that step returns.            */
+typedef struct pgasr_host_pipeline pgasr_host_pipeline;
+PGASR_API int pgasr_host_create(int B, int T, int V, int K, int Lmax, int depth, pgasr_host_pipeline** out);
+PGASR_API int pgasr_host_destroy(pgasr_host_pipeline* p);
+PGASR_API int pgasr_host_submit(pgasr_host_pipeline* p, const float* logits_h, const int32_t* targets_h,
+                      const int32_t* in_len_h, const int32_t* tgt_len_h, uint64_t seed, int blank,
+                      int reward_mode, int baseline_mode, float baseline_value, float w_pg, float w_ctc,
+                      float* loss_h, float* dlogits_h, float* rewards_h, float* nll_h, int64_t* ticket);
+PGASR_API int pgasr_host_wait(pgasr_host_pipeline* p, int64_t ticket);
+PGASR_API int pgasr_host_pin(void* ptr, size_t bytes);      /* cudaHostRegister / cudaHostUnregister */
+PGASR_API int pgasr_host_unpin(void* ptr);
 
 #ifdef __cplusplus
 }

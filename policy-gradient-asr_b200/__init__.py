@@ -7,14 +7,16 @@ meaning and error behaviour), backed by the CUDA kernels in csrc/ through the C 
     CTCdecoder.collapse_fn / CTCDecoder                       upstream CTCdecoder.py
     policy_grad.reward                                        upstream policy_grad.py
     loss.customNLLLoss  (+ the new loss.PolicyGradCTCLoss)    upstream loss.py
-    functional.*                                              batched tensor-level operators
+    functional.*                                              batched tensor-level operators (device tensors)
+    host.HostPipeline                                         the step on pinned HOST arrays, pipelined
     distributed.*                                             utterance sharding over ranks
 
 There is no CPU fallback anywhere in this package.
 """
 from . import _native                                        # noqa: F401
 from . import functional                                     # noqa: F401
-from . import metrics, CTCdecoder, policy_grad, loss, distributed   # noqa: F401
+from . import metrics, CTCdecoder, policy_grad, loss, distributed, host   # noqa: F401
 from .loss import PolicyGradCTCLoss, customNLLLoss           # noqa: F401
+from .host import HostPipeline                               # noqa: F401
 
 __version__ = "0.1.0"

@@ -31,6 +31,12 @@ SIGNATURES = {
     "pgasr_pg_ctc_step_workspace_init": (_i, [_vp, _sz, _vp]),
     "pgasr_pg_ctc_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pgasr_host_create": (_i, [_i, _i, _i, _i, _i, _i, _vp]),
+    "pgasr_host_destroy": (_i, [_vp]),
+    "pgasr_host_submit": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "pgasr_host_wait": (_i, [_vp, C.c_int64]),
+    "pgasr_host_pin": (_i, [_vp, _sz]),
+    "pgasr_host_unpin": (_i, [_vp]),
 }
 
 

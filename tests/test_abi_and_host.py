@@ -57,6 +57,9 @@ def test_no_device_is_loud_not_a_fallback():
         pgasr_b200.CTCdecoder.collapse_fn("aab")
     with pytest.raises(TypeError):
         pgasr_b200.loss.customNLLLoss()(torch.zeros(2, 2, 3), torch.zeros(2, 2, dtype=torch.long))
+    with pytest.raises(pgasr_b200._native.PgasrError) as ei:      # the host-buffer API has no CPU path either
+        pgasr_b200.HostPipeline(2, 20, 30, 4, 5)
+    assert ei.value.status == -3
 
 
 def test_workspace_queries_are_pure():

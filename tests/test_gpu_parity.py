@@ -385,3 +385,62 @@ def test_size_independent_properties_full_size(cuda):
     # determinism: the same call twice is bit-identical
     out2 = F.pg_ctc_step(dev_t(logits, cuda), dev_t(targets, cuda), None, None, uniforms=dev_t(uni, cuda), want=("nll",))
     assert torch.equal(out["dlogits"], out2["dlogits"]) and torch.equal(out["nll"], out2["nll"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth", [1, 3])
+def test_host_pipeline_matches_device_step(cuda, depth):
+    """pgasr_host_* on pinned HOST arrays: every step's outputs equal the device-tensor step bit for bit (same
+    Philox seed), with several steps in flight, slots reused, ragged lengths and the oracle as the checker."""
+    import pgasr_b200
+    from pgasr_b200 import functional as F
+    B, T, V, K, L = 6, 90, 30, 8, 14
+    nsteps = 2 * depth + 3
+    batches = [make_batch(B, T, V, K, L, seed=100 + i, ragged=(i % 2 == 0)) for i in range(nsteps)]
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    with pgasr_b200.HostPipeline(B, T, V, K, L, depth=depth, reward="cer", baseline="loo", pg_weight=0.7,
+                                 ctc_weight=1.3) as pipe:
+        outs, tickets, keep = [], [], []
+        for i, (lg, tg, il, tl, _) in enumerate(batches):
+            h = (pin(lg), pin(tg), pin(il), pin(tl))
+            keep.append(h)
+            o = pipe.output_buffers()
+            tickets.append(pipe.submit(*h, out=o, seed=7 + i))
+            outs.append(o)
+        assert tickets == list(range(nsteps))
+        pipe.wait(tickets[1])                       # partial wait, then everything
+        pipe.wait()
+        # full-length variant through the synchronous convenience call
+        lg, tg, _, _, _ = batches[0]
+        o_full = pipe.step(pin(lg), pin(tg), seed=3)
+    for i, (lg, tg, il, tl, _) in enumerate(batches):
+        ref = F.pg_ctc_step(dev_t(lg, cuda), dev_t(tg, cuda), dev_t(il, cuda), dev_t(tl, cuda), K=K, reward="cer",
+                            baseline="loo", pg_weight=0.7, ctc_weight=1.3, seed=7 + i, want=("rewards", "nll", "samples"))
+        assert torch.equal(outs[i]["dlogits"], ref["dlogits"].cpu()), i
+        assert torch.equal(outs[i]["rewards"], ref["rewards"].cpu())
+        assert torch.equal(outs[i]["nll"], ref["nll"].cpu())
+        assert float(outs[i]["loss"][0]) == float(ref["loss"])
+        if i == 0:                                   # and the oracle agrees (Philox seed 7)
+            loss_ref, R_ref, nll_ref, dl_ref = cport.pg_ctc_step(lg, tg, il, tl, None, seed=7, K=K, reward_mode=1,
+                                                                 baseline_mode=2, w_pg=0.7, w_ctc=1.3)
+            assert np.array_equal(outs[0]["rewards"].numpy(), R_ref)
+            assert rel_err(outs[0]["dlogits"].numpy(), dl_ref) < RTOL
+            assert abs(float(outs[0]["loss"][0]) - loss_ref) <= RTOL * abs(loss_ref)
+    ref = F.pg_ctc_step(dev_t(batches[0][0], cuda), dev_t(batches[0][1], cuda), None, None, K=K, reward="cer",
+                        baseline="loo", pg_weight=0.7, ctc_weight=1.3, seed=3)
+    assert torch.equal(o_full["dlogits"], ref["dlogits"].cpu())
+
+
+@pytest.mark.gpu
+def test_host_pipeline_rejects_bad_arguments(cuda):
+    import pgasr_b200
+    from pgasr_b200 import _native
+    with pytest.raises(_native.PgasrError):
+        pgasr_b200.HostPipeline(4, 50, 40, 8, 10)             # V > 32: unsupported
+    with pgasr_b200.HostPipeline(2, 20, 30, 4, 5, depth=2) as pipe:
+        with pytest.raises(TypeError):
+            pipe.submit(torch.zeros(2, 20, 30, device=cuda), torch.zeros(2, 5, dtype=torch.int32))
+        with pytest.raises(ValueError):
+            pipe.submit(torch.zeros(2, 19, 30), torch.zeros(2, 5, dtype=torch.int32))
+    with pytest.raises(RuntimeError):
+        pipe.submit(torch.zeros(2, 20, 30), torch.zeros(2, 5, dtype=torch.int32))
