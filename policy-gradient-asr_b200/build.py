@@ -36,15 +36,15 @@ def needs_build():
     return any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps)
 
 
-def build_timing():
+def build_timing(extra=(), tag=""):
     """Instrumented variant (-DPGASR_TIMING) for tools/phase_timing.py; not used by the product."""
-    out = os.path.join(LIBDIR, "libpgasr_b200_timing.so")
+    out = os.path.join(LIBDIR, f"libpgasr_b200_timing{tag}.so")
     os.makedirs(LIBDIR, exist_ok=True)
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    r = subprocess.run([nvcc] + NVCC_FLAGS + ["-DPGASR_TIMING"] + sources() + ["-o", out], env=env,
+    r = subprocess.run([nvcc] + NVCC_FLAGS + ["-DPGASR_TIMING"] + list(extra) + sources() + ["-o", out], env=env,
                        capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -71,6 +71,8 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     if "--timing" in sys.argv:
-        print(build_timing())
+        extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+        tag = "".join("_" + a[2:].lower() for a in extra)
+        print(build_timing(extra, tag))
         sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -586,15 +586,17 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
 }
 
 // Gradient worker g of one direction: frames q with q % G == g of that direction's second half.  The frames a
-// worker owns in one batch are processed side by side (separate accumulators) so their latencies overlap, and the
-// other direction's lattice rows of the NEXT batch are already in flight while the current one is processed.
+// worker owns in one batch are processed side by side (separate accumulators) so their latencies overlap.
+// The other direction's lattice rows come from L2 (~600 cycles): the loads for the NEXT batch are issued right
+// after phase A has consumed the current ones, into the same registers, so they fly during phase B and the
+// batch barrier.  (A two-register-set ping-pong issued the next loads BEFORE the current ones were consumed;
+// both sets then shared hardware scoreboards and every batch waited out the full L2 latency -- measured:
+// 48k of the 113k second-half cycles.)
 template <int SPL, int G, bool kAlpha>
 struct CtcWorker {
     static constexpr int kPer = kBatch / G;               // frames of a batch per worker
-    static constexpr bool kPrefetch = kPer * SPL <= 32;   // keep the prefetch within the register budget
-    static constexpr int kHold = kPrefetch ? kPer : 1;
-    double2 o[kHold][SPL / 2];
-    int eo[kHold];
+    double2 o[kPer][SPL / 2];
+    int eo[kPer];
 };
 
 template <int SPL, int G, bool kAlpha>
@@ -603,16 +605,20 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
                                                  const int* __restrict__ exp_u) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kHold; ++r) {
-        const int q = nb * kBatch + g + r * G;
-        if (CtcWorker<SPL, G, kAlpha>::kPrefetch && q < n2) {
-            const int step = n_first + q;
-            const int t = kAlpha ? step : Tb - 1 - step;
-            const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lane;
+    for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kPer; ++r) {
+        const int q = min(nb * kBatch + g + r * G, n2 - 1);   // clamped: a stale row is loaded, never used
+        const int step = n_first + q;
+        const int t = kAlpha ? step : Tb - 1 - step;
+        const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lane;
+#ifdef EXP_NO_LATTICE
 #pragma unroll
-            for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = __ldcg(lp + jj * 32);
-            wk.eo[r] = __ldcg(exp_u + t);
-        }
+        for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = make_double2(1.0 + lane, 0.5);
+        wk.eo[r] = 0; (void)lp;
+#else
+#pragma unroll
+        for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = __ldcg(lp + jj * 32);
+        wk.eo[r] = __ldcg(exp_u + t);
+#endif
     }
 }
 
@@ -620,45 +626,29 @@ struct WorkerNorm { double invZ0; int E0; bool dead, have; long long tA, tB, tWa
 
 constexpr int kClsRegs = 8;       // label positions of this lane's class held in registers
 
+// phase A: occupancies of every owned frame of batch nb; label states go to gam[frame][label index] and the
+// blank total to gb[] (2^-30 fixed point)
 template <int SPL, int G, bool kAlpha>
-__device__ __forceinline__ void ctc_worker_batch(CtcWorker<SPL, G, kAlpha>& wk, WorkerNorm& nm, int nb, int g,
-                                                 int n_first, int n2, int Tb, const double* tile, int V, int RS,
-                                                 int blank, float grad_scale, float* __restrict__ dlog_u,
-                                                 const double* __restrict__ lat_u, const int* __restrict__ exp_u,
-                                                 const GradRing<SPL>& ring, int* gam, int ccnt,
-                                                 const int (&cpos)[kClsRegs]) {
+__device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlpha>& wk, WorkerNorm& nm, int nb, int g,
+                                                   int n2, const GradRing<SPL>& ring, int* gam,
+                                                   int (&gb)[kBatch / G]) {
     constexpr int kPer = CtcWorker<SPL, G, kAlpha>::kPer;
-    constexpr bool kPrefetch = CtcWorker<SPL, G, kAlpha>::kPrefetch;
     constexpr int kGam = 16 * SPL;                        // ints per frame: SPL/2 label occupancies per lane
     const int lane = threadIdx.x & 31;
-    int gb[kPer];
-#ifdef PGASR_TIMING
-    const long long ta1 = clock64();
-#endif
-    // phase A: occupancies of every owned frame; label states go to gam[frame][label index] (2^-30 fixed point)
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
         const int q = nb * kBatch + g + r * G;
         gb[r] = 0;
         if (q < n2) {
-            const int step = n_first + q;
-            const int t = kAlpha ? step : Tb - 1 - step;
             const int slot = q % (2 * kBatch);
             const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 32)) + lane;
-            const int rr = kPrefetch ? r : 0;
-            if (!kPrefetch) {
-                const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lane;
-#pragma unroll
-                for (int jj = 0; jj < SPL / 2; ++jj) wk.o[0][jj] = __ldcg(lp + jj * 32);
-                wk.eo[0] = __ldcg(exp_u + t);
-            }
             double wv[SPL];
             double zb = 0.0;
 #pragma unroll
             for (int jj = 0; jj < SPL / 2; ++jj) {
                 const double2 av = sp[jj * 32];
-                wv[2 * jj] = av.x * wk.o[rr][jj].x;
-                wv[2 * jj + 1] = av.y * wk.o[rr][jj].y;
+                wv[2 * jj] = av.x * wk.o[r][jj].x;
+                wv[2 * jj + 1] = av.y * wk.o[r][jj].y;
                 zb += wv[2 * jj];
             }
             const int E = ring.eslot[slot];
@@ -669,22 +659,40 @@ __device__ __forceinline__ void ctc_worker_batch(CtcWorker<SPL, G, kAlpha>& wk, 
                 const double Z0 = warp_sum(zb + zl);
                 nm.dead = !(Z0 > 0.0);
                 nm.invZ0 = nm.dead ? 0.0 : kCtcFix / Z0;
-                nm.E0 = E + wk.eo[rr];
+                nm.E0 = E + wk.eo[r];
                 nm.have = true;
             }
-            const double c = nm.invZ0 * pow2i(E + wk.eo[rr] - nm.E0);
+            const double c = nm.invZ0 * pow2i(E + wk.eo[r] - nm.E0);
             gb[r] = __reduce_add_sync(kFull, __double2loint(fma(zb, c, kCtcMagic)));
-            int* gr = gam + r * kGam + lane * (SPL / 2);
+            if constexpr (SPL >= 8) {
+                int4* gr = reinterpret_cast<int4*>(gam + r * kGam) + lane * (SPL / 8);
 #pragma unroll
-            for (int i = 0; i < SPL / 2; ++i) gr[i] = __double2loint(fma(wv[2 * i + 1], c, kCtcMagic));
+                for (int i = 0; i < SPL / 8; ++i)
+                    gr[i] = make_int4(__double2loint(fma(wv[8 * i + 1], c, kCtcMagic)),
+                                      __double2loint(fma(wv[8 * i + 3], c, kCtcMagic)),
+                                      __double2loint(fma(wv[8 * i + 5], c, kCtcMagic)),
+                                      __double2loint(fma(wv[8 * i + 7], c, kCtcMagic)));
+            } else {
+                reinterpret_cast<int2*>(gam + r * kGam)[lane] =
+                    make_int2(__double2loint(fma(wv[1], c, kCtcMagic)), __double2loint(fma(wv[3], c, kCtcMagic)));
+            }
         }
     }
     __syncwarp();
-#ifdef PGASR_TIMING
-    const long long ta2 = clock64();
-    nm.tA += ta2 - ta1;
-#endif
-    // phase B: gradient rows; lane v sums the label occupancies of class v
+}
+
+// phase B: gradient rows; lane v sums the label occupancies of class v.  cpos[] entries beyond the class's
+// count point at label slot 16*SPL-1, whose state 32*SPL-1 lies beyond S for every transcript (always 0), so the
+// gather is branch free; cmax (warp uniform) bounds the rare tail of classes with more than kClsRegs labels.
+template <int SPL, int G, bool kAlpha>
+__device__ __forceinline__ void ctc_worker_phase_b(const WorkerNorm& nm, int nb, int g, int n_first, int n2, int Tb,
+                                                   const double* tile, int V, int RS, int blank, float grad_scale,
+                                                   float* __restrict__ dlog_u, const GradRing<SPL>& ring,
+                                                   const int* gam, const int (&gb)[kBatch / G], int ccnt, int cmax,
+                                                   const int (&cpos)[kClsRegs]) {
+    constexpr int kPer = kBatch / G;
+    constexpr int kGam = 16 * SPL;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
         const int q = nb * kBatch + g + r * G;
@@ -696,16 +704,21 @@ __device__ __forceinline__ void ctc_worker_batch(CtcWorker<SPL, G, kAlpha>& wk, 
             const int* gr = gam + r * kGam;
             if (V <= 32) {
                 int occ = 0;
+#ifndef EXP_NO_PHASEB
+                int o2 = 0;
 #pragma unroll
-                for (int i = 0; i < kClsRegs; ++i)
-                    if (i < ccnt) occ += gr[cpos[i]];
-                for (int i = kClsRegs; i < ccnt; ++i) occ += gr[ring.cls_pos[ring.cls_off[lane] + i]];
-                if (lane == blank) occ = gb[r];
-                if (lane < V) {
-                    const int pfix = __double2loint(fma(row[lane], kCtcFix, kCtcMagic));
-                    const float gval = grad_scale * ((float)(pfix - occ) * kCtcUnfix);
-                    out[lane] = nm.dead ? 0.0f : gval;
+                for (int i = 0; i < kClsRegs; i += 2) {
+                    occ += gr[cpos[i]];
+                    o2 += gr[cpos[i + 1]];
                 }
+                occ += o2;
+                for (int i = kClsRegs; i < cmax; ++i)
+                    occ += i < ccnt ? gr[ring.cls_pos[ring.cls_off[lane] + i]] : 0;
+#endif
+                occ = lane == blank ? gb[r] : occ;
+                const int pfix = __double2loint(fma(row[min(lane, RS - 1)], kCtcFix, kCtcMagic));
+                const float gval = nm.dead ? 0.0f : grad_scale * ((float)(pfix - occ) * kCtcUnfix);
+                if (lane < V) out[lane] = gval;
             } else {
                 for (int v = lane; v < V; v += 32) {
                     int occ = 0;
@@ -719,16 +732,13 @@ __device__ __forceinline__ void ctc_worker_batch(CtcWorker<SPL, G, kAlpha>& wk, 
         }
     }
     __syncwarp();
-#ifdef PGASR_TIMING
-    nm.tB += clock64() - ta2;
-#endif
 }
 
 template <int SPL, int G, bool kAlpha, typename Barrier>
 __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const int32_t* __restrict__ lab_u, int Tb,
                                                 int L, int V, int RS, int blank, float grad_scale,
                                                 float* __restrict__ dlog_u, const double* __restrict__ lat_u,
-                                                const int* __restrict__ exp_u, GradRing<SPL> ring, int* racc,
+                                                const int* __restrict__ exp_u, GradRing<SPL> ring, int* gam,
                                                 Barrier mid_barrier) {
     static_assert(kBatch % G == 0, "workers must divide the batch");
     constexpr int kGroup = 32 * (1 + G);
@@ -741,39 +751,44 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
     int ccnt = 0, cpos[kClsRegs];
     if (lane < V) ccnt = ring.cls_off[lane + 1] - ring.cls_off[lane];
 #pragma unroll
-    for (int i = 0; i < kClsRegs; ++i) cpos[i] = (i < ccnt) ? ring.cls_pos[ring.cls_off[lane] + i] : 0;
+    for (int i = 0; i < kClsRegs; ++i) cpos[i] = (i < ccnt) ? ring.cls_pos[ring.cls_off[min(lane, V - 1)] + i] : 16 * SPL - 1;
+    const int cmax = __reduce_max_sync(kFull, ccnt);
     (void)lab_u; (void)L;
     mid_barrier();                                        // the other direction's half-lattice is complete
     WorkerNorm nm;
     nm.invZ0 = 0.0; nm.E0 = 0; nm.dead = false; nm.have = false;
     nm.tA = nm.tB = nm.tWait = nm.tBusy = 0;
     const int nbatch = (n2 + kBatch - 1) / kBatch;
-    CtcWorker<SPL, G, kAlpha> wa, wb;                     // ping-pong: current batch / next batch
-    ctc_worker_fetch<SPL, G, kAlpha>(wa, 0, g, n_first, n2, Tb, lat_u, exp_u);
-    for (int nb = 0; nb < nbatch; nb += 2) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int b_ = nb + half;
-            if (b_ >= nbatch) break;
-            CtcWorker<SPL, G, kAlpha>& cur = half == 0 ? wa : wb;
-            CtcWorker<SPL, G, kAlpha>& nxt = half == 0 ? wb : wa;
-            if (b_ + 1 < nbatch) ctc_worker_fetch<SPL, G, kAlpha>(nxt, b_ + 1, g, n_first, n2, Tb, lat_u, exp_u);
-            const int buf = b_ & 1;
+    CtcWorker<SPL, G, kAlpha> wk;
+    int gb[kPer];
+    if (nbatch > 0) ctc_worker_fetch<SPL, G, kAlpha>(wk, 0, g, n_first, n2, Tb, lat_u, exp_u);
+    for (int nb = 0; nb < nbatch; ++nb) {
+        const int buf = nb & 1;
 #ifdef PGASR_TIMING
-            const long long w0 = clock64();
+        const long long w0 = clock64();
 #endif
-            named_bar_sync(ring.bar_full + buf, kGroup);
+        named_bar_sync(ring.bar_full + buf, kGroup);
 #ifdef PGASR_TIMING
-            const long long w1 = clock64();
-            nm.tWait += w1 - w0;
+        const long long w1 = clock64();
+        nm.tWait += w1 - w0;
 #endif
-            ctc_worker_batch<SPL, G, kAlpha>(cur, nm, b_, g, n_first, n2, Tb, tile, V, RS, blank, grad_scale, dlog_u,
-                                             lat_u, exp_u, ring, racc, ccnt, cpos);
+#ifndef EXP_NO_WORKER
+        ctc_worker_phase_a<SPL, G, kAlpha>(wk, nm, nb, g, n2, ring, gam, gb);
 #ifdef PGASR_TIMING
-            nm.tBusy += clock64() - w1;
+        const long long w2 = clock64();
+        nm.tA += w2 - w1;
 #endif
-            if (b_ + 2 < nbatch) named_bar_arrive(ring.bar_empty + buf, kGroup);   // buffer may be overwritten
-        }
+        if (nb + 1 < nbatch) ctc_worker_fetch<SPL, G, kAlpha>(wk, nb + 1, g, n_first, n2, Tb, lat_u, exp_u);
+        ctc_worker_phase_b<SPL, G, kAlpha>(nm, nb, g, n_first, n2, Tb, tile, V, RS, blank, grad_scale, dlog_u, ring,
+                                           gam, gb, ccnt, cmax, cpos);
+#ifdef PGASR_TIMING
+        nm.tB += clock64() - w2;
+#endif
+#endif
+#ifdef PGASR_TIMING
+        nm.tBusy += clock64() - w1;
+#endif
+        if (nb + 2 < nbatch) named_bar_arrive(ring.bar_empty + buf, kGroup);   // buffer may be overwritten
     }
 #ifdef PGASR_TIMING
     if (ring.dbg && lane == 0 && g == 0) {
