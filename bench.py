@@ -266,7 +266,7 @@ def run_ours(args):
     # HostPipeline keeps `depth` steps in flight so the copies of neighbouring steps overlap the kernel ----------
     e2e = None
     if not args.no_e2e:
-        depth = 3
+        depth = 4
         pipe = pgasr_b200.HostPipeline(B, T, V, K, L, depth=depth)
         outs = [pipe.output_buffers() for _ in range(depth)]
 

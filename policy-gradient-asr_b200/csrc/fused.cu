@@ -282,6 +282,8 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
 
     PGASR_STAMP(dbg, 33);
     // ---- P3: edit distance, one thread per sample ------------------------------------------------
+    // (all K samples in the lanes of as few warps as possible: a Myers step is ~25 W dependent integer
+    // instructions, and lanes of one warp share them; one sample per warp was measured 3.6x slower)
     if ((int)threadIdx.x < K) {
         const int k = threadIdx.x;
         dist_s[k] = myers_row<W, false>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, nullptr);
@@ -380,10 +382,22 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     PGASR_STAMP(dbg, 38);
 }
 
+#ifdef PGASR_TIMING
+__device__ unsigned long long g_cta_ns[2048][3];          // per ticket: start, role end, exit (globaltimer ns)
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
+#endif
+
 template <int SPL, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_ticket, s_last;
+#ifdef PGASR_TIMING
+    const unsigned long long t_start = gtime();
+#endif
     if (threadIdx.x == 0) s_ticket = atomicAdd(a.ctrl, 1u);
     __syncthreads();
     const unsigned ticket = s_ticket;
@@ -391,6 +405,9 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     if (ticket < n_ctc) fused_ctc_role<SPL, kThreads>(a, (int)ticket, smem_raw);
     else fused_pg_role<SPL / 2, kThreads>(a, (int)(ticket - n_ctc), smem_raw);
 
+#ifdef PGASR_TIMING
+    if (threadIdx.x == 0 && ticket < 2048) { g_cta_ns[ticket][0] = t_start; g_cta_ns[ticket][1] = gtime(); }
+#endif
     // ---- second ticket: the last CTA reduces the loss (fixed order) and re-arms the control block ----
     __threadfence();
     __syncthreads();
@@ -416,6 +433,9 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
             a.ctrl[1] = 0u;
         }
     }
+#ifdef PGASR_TIMING
+    if (threadIdx.x == 0 && ticket < 2048) g_cta_ns[ticket][2] = gtime();
+#endif
 }
 
 struct FusedWs { size_t ctrl, lat, exps, terms, nll, total; };
@@ -483,6 +503,10 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
 }  // namespace pgasr
 
 #ifdef PGASR_TIMING
+extern "C" __attribute__((visibility("default"))) int pgasr_debug_cta_times(unsigned long long* host, int n) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host, pgasr::g_cta_ns, sizeof(unsigned long long) * 3 * n) == cudaSuccess ? 0 : -5;
+}
 extern "C" __attribute__((visibility("default"))) int pgasr_debug_read(long long* host64, int reset) {
     cudaDeviceSynchronize();
     if (cudaMemcpyFromSymbol(host64, pgasr::g_dbg, sizeof(long long) * 64) != cudaSuccess) return -5;

@@ -3,11 +3,13 @@
 // model.py:317-320; criterion(model_out, t), model.py:235).  `depth` steps are in flight at once: the H2D copy of
 // step n+1 and the D2H copy of step n-1 run on their own streams (and copy engines) while step n's kernel runs.
 //
-//   copy-in stream : [small inputs H2D][logits H2D]  -> ev_in[slot]
-//   compute stream : wait ev_in[slot], ev_out[slot] (of the step that used the slot before) ; fused kernel -> ev_k[slot]
-//   copy-out stream: wait ev_k[slot] ; [dlogits D2H][small outputs D2H] -> ev_out[slot]
+//   copy-in stream : [small inputs H2D][logits H2D] -> ev_in[slot]
+//   compute stream : wait ev_in[slot] ; fused kernel -> ev_k[slot]
+//   copy-out stream: wait ev_k[slot] ; [small outputs D2H][dlogits D2H] -> ev_out[slot]
 // Small inputs (targets, lengths) and small outputs (loss, rewards, nll) are packed into one pinned staging
-// block per slot so that a step costs two copies per direction.
+// block per slot so that a step costs two copies per direction.  All H2D copies share one hardware copy engine
+// and all D2H copies the other whatever stream they are issued on (measured: extra streams did not help).
+#include <chrono>
 #include <cstring>
 #include <new>
 
@@ -23,12 +25,19 @@ struct pgasr_host_pipeline {
         char* small_in_d; char* small_in_h;       // targets [B*Lmax] i32 | in_len [B] | tgt_len [B]
         float* small_out_d; float* small_out_h;   // loss [4] | rewards [B*K] | nll [B]
         cudaEvent_t ev_in, ev_k, ev_out;
+#ifdef PGASR_TIMING
+        cudaEvent_t ev_h0, ev_k0, ev_o0;             // starts of the H2D, kernel and D2H phases (timing build)
+#endif
         long long ticket;                          // step occupying the slot (-1: free)
         bool collected;                            // small outputs already handed to the caller
         float* loss_h; float* rewards_h; float* nll_h;
     }* slots;
     long long next_ticket;
     size_t small_in_bytes, small_out_floats;
+#ifdef PGASR_TIMING
+    cudaEvent_t ev_base;
+    double host_ns_collect, host_ns_enqueue;
+#endif
 };
 
 namespace {
@@ -105,14 +114,23 @@ extern "C" int pgasr_host_create(int B, int T, int V, int K, int Lmax, int depth
         ok(cudaMalloc(&s.small_out_d, p->small_out_floats * sizeof(float)));
         ok(cudaMallocHost(&s.small_in_h, p->small_in_bytes));
         ok(cudaMallocHost(&s.small_out_h, p->small_out_floats * sizeof(float)));
+#ifdef PGASR_TIMING
+        ok(cudaEventCreate(&s.ev_in)); ok(cudaEventCreate(&s.ev_k)); ok(cudaEventCreate(&s.ev_out));
+        ok(cudaEventCreate(&s.ev_h0)); ok(cudaEventCreate(&s.ev_k0)); ok(cudaEventCreate(&s.ev_o0));
+#else
         ok(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
         ok(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
         ok(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+#endif
     }
     if (e == cudaSuccess) {
         const int rc = pgasr_pg_ctc_step_workspace_init(p->workspace, ws, p->s_k);
         if (rc != PGASR_OK) { destroy(p); return rc; }
         ok(cudaStreamSynchronize(p->s_k));
+#ifdef PGASR_TIMING
+        ok(cudaEventCreate(&p->ev_base));
+        ok(cudaEventRecord(p->ev_base, p->s_k));
+#endif
     }
     if (e != cudaSuccess) {
         destroy(p);
@@ -135,8 +153,14 @@ extern "C" int pgasr_host_submit(pgasr_host_pipeline* p, const float* logits_h, 
     if (!p || !logits_h || !targets_h || !loss_h || !dlogits_h) return PGASR_ERR_INVALID_ARG;
     const long long n = p->next_ticket;
     auto& s = p->slots[n % p->depth];
+#ifdef PGASR_TIMING
+    const auto h0 = std::chrono::steady_clock::now();
+#endif
     int rc = collect(p, s);                        // blocks only when step n - depth has not finished yet
     if (rc != PGASR_OK) return rc;
+#ifdef PGASR_TIMING
+    const auto h1 = std::chrono::steady_clock::now();
+#endif
     const int B = p->B, T = p->T, V = p->V, K = p->K, Lmax = p->Lmax;
     const size_t nlog = (size_t)B * T * V * sizeof(float);
     // pack the small inputs (absent lengths mean "full length")
@@ -146,13 +170,19 @@ extern "C" int pgasr_host_submit(pgasr_host_pipeline* p, const float* logits_h, 
     int32_t* tl = il + B;
     for (int b = 0; b < B; ++b) il[b] = in_len_h ? in_len_h[b] : T;
     for (int b = 0; b < B; ++b) tl[b] = tgt_len_h ? tgt_len_h[b] : Lmax;
-    // the slot's device inputs are free once the kernel that last read them has finished
-    if (s.ticket >= 0) PGASR_CUDA_TRY(cudaStreamWaitEvent(p->s_in, s.ev_k, 0));
+    // No stream-side wait guards the slot's device buffers: collect() above has already blocked the HOST until the
+    // D2H copies of the step that used this slot finished, and those were ordered after its kernel.  (Every
+    // cross-stream wait is a semaphore on a copy-engine channel; the redundant ones cost engine time.)
+#ifdef PGASR_TIMING
+    PGASR_CUDA_TRY(cudaEventRecord(s.ev_h0, p->s_in));
+#endif
     PGASR_CUDA_TRY(cudaMemcpyAsync(s.small_in_d, s.small_in_h, p->small_in_bytes, cudaMemcpyHostToDevice, p->s_in));
     PGASR_CUDA_TRY(cudaMemcpyAsync(s.logits_d, logits_h, nlog, cudaMemcpyHostToDevice, p->s_in));
     PGASR_CUDA_TRY(cudaEventRecord(s.ev_in, p->s_in));
     PGASR_CUDA_TRY(cudaStreamWaitEvent(p->s_k, s.ev_in, 0));
-    if (s.ticket >= 0) PGASR_CUDA_TRY(cudaStreamWaitEvent(p->s_k, s.ev_out, 0));   // dlogits_d drained
+#ifdef PGASR_TIMING
+    PGASR_CUDA_TRY(cudaEventRecord(s.ev_k0, p->s_k));
+#endif
     const int32_t* tg_d = reinterpret_cast<const int32_t*>(s.small_in_d);
     rc = pgasr_pg_ctc_step(s.logits_d, tg_d, tg_d + (size_t)B * Lmax, tg_d + (size_t)B * Lmax + B, nullptr, seed, B,
                            T, V, K, Lmax, blank, reward_mode, baseline_mode, baseline_value, w_pg, w_ctc,
@@ -161,15 +191,23 @@ extern "C" int pgasr_host_submit(pgasr_host_pipeline* p, const float* logits_h, 
     if (rc != PGASR_OK) return rc;
     PGASR_CUDA_TRY(cudaEventRecord(s.ev_k, p->s_k));
     PGASR_CUDA_TRY(cudaStreamWaitEvent(p->s_out, s.ev_k, 0));
-    PGASR_CUDA_TRY(cudaMemcpyAsync(dlogits_h, s.dlogits_d, nlog, cudaMemcpyDeviceToHost, p->s_out));
+#ifdef PGASR_TIMING
+    PGASR_CUDA_TRY(cudaEventRecord(s.ev_o0, p->s_out));
+#endif
     PGASR_CUDA_TRY(cudaMemcpyAsync(s.small_out_h, s.small_out_d, p->small_out_floats * sizeof(float),
                                    cudaMemcpyDeviceToHost, p->s_out));
+    PGASR_CUDA_TRY(cudaMemcpyAsync(dlogits_h, s.dlogits_d, nlog, cudaMemcpyDeviceToHost, p->s_out));
     PGASR_CUDA_TRY(cudaEventRecord(s.ev_out, p->s_out));
     s.ticket = n;
     s.collected = false;
     s.loss_h = loss_h; s.rewards_h = rewards_h; s.nll_h = nll_h;
     p->next_ticket = n + 1;
     if (ticket) *ticket = n;
+#ifdef PGASR_TIMING
+    const auto h2 = std::chrono::steady_clock::now();
+    p->host_ns_collect += std::chrono::duration<double, std::nano>(h1 - h0).count();
+    p->host_ns_enqueue += std::chrono::duration<double, std::nano>(h2 - h1).count();
+#endif
     return PGASR_OK;
 }
 
@@ -197,3 +235,20 @@ extern "C" int pgasr_host_unpin(void* ptr) {
     PGASR_CUDA_TRY(cudaHostUnregister(ptr));
     return PGASR_OK;
 }
+
+#ifdef PGASR_TIMING
+// timing build only: ms since pipeline creation of {H2D start, H2D end, kernel start, kernel end, D2H start, D2H end}
+// of the step currently held by slot `slot` (call after pgasr_host_wait)
+extern "C" __attribute__((visibility("default"))) int pgasr_host_debug_host_ns(pgasr_host_pipeline* p, double* out2) {
+    out2[0] = p->host_ns_collect; out2[1] = p->host_ns_enqueue;
+    p->host_ns_collect = p->host_ns_enqueue = 0.0;
+    return 0;
+}
+extern "C" __attribute__((visibility("default"))) int pgasr_host_debug_times(pgasr_host_pipeline* p, int slot, float* ms6) {
+    auto& s = p->slots[slot];
+    cudaEvent_t ev[6] = {s.ev_h0, s.ev_in, s.ev_k0, s.ev_k, s.ev_o0, s.ev_out};
+    for (int i = 0; i < 6; ++i)
+        if (cudaEventElapsedTime(&ms6[i], p->ev_base, ev[i]) != cudaSuccess) return -5;
+    return 0;
+}
+#endif

@@ -75,3 +75,34 @@ for depth in (1, 2, 3, 4, 6):
     dt = time.perf_counter() - t0
     print(f"depth {depth}: {dt / N * 1e6:7.1f} us/step  ({B * N / dt:9.0f} utt/s), host time inside submit {sub / N * 1e6:6.1f} us/step")
     pipe.close()
+
+# can one direction go faster with the copy split over several streams (several copy engines)?
+for parts in (2, 4):
+    ss = [torch.cuda.Stream() for _ in range(parts)]
+    chunk = n // parts
+
+    def h2d_split():
+        for i in range(N):
+            for j, st in enumerate(ss):
+                with torch.cuda.stream(st):
+                    d_in[i % 4][j * chunk:(j + 1) * chunk].copy_(h_in[i % 4][j * chunk:(j + 1) * chunk], non_blocking=True)
+
+    def d2h_split():
+        for i in range(N):
+            for j, st in enumerate(ss):
+                with torch.cuda.stream(st):
+                    h_out[i % 4][j * chunk:(j + 1) * chunk].copy_(d_out[i % 4][j * chunk:(j + 1) * chunk], non_blocking=True)
+
+    def both_split():
+        for i in range(N):
+            for j, st in enumerate(ss):
+                with torch.cuda.stream(st):
+                    d_in[i % 4][j * chunk:(j + 1) * chunk].copy_(h_in[i % 4][j * chunk:(j + 1) * chunk], non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out[i % 4].copy_(d_out[i % 4], non_blocking=True)
+
+    for name, fn in ((f"H2D in {parts} streams", h2d_split), (f"D2H in {parts} streams", d2h_split),
+                     (f"H2D in {parts} streams + D2H", both_split)):
+        fn()
+        us = timed(fn)
+        print(f"{name:26s} {us:7.1f} us per {mb:.2f} MB  -> {mb / us * 1e3:6.1f} GB/s")

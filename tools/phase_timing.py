@@ -38,3 +38,18 @@ for mode, (wp, wc) in {"both": (1.0, 1.0), "ctc": (0.0, 1.0), "pg": (1.0, 0.0)}.
     if wp:
         names = ["tile-load", "sample", "collapse", "myers", "advantages", "grad-tile", "flag-wait", "rmw-out"]
         print(" pg:  " + "  ".join(f"{n} {d[31+i]-d[30+i]}" for i, n in enumerate(names)) + f"  total {d[38]-d[30]}")
+
+# per-CTA wall times of the last fused launch (globaltimer ns): role start/end spread over the grid
+import numpy as np  # noqa: E402
+out = F.pg_ctc_step(lg, tg, il, tl, K=16, seed=9, workspace=ws)
+n = 2 * B
+arr = (ctypes.c_ulonglong * (3 * n))()
+assert lib.pgasr_debug_cta_times(arr, n) == 0
+t = np.array(list(arr), dtype=np.float64).reshape(n, 3)
+t0 = t[:, 0].min()
+t = (t - t0) / 1e3
+for name, sl in (("CTC role CTAs", slice(0, B)), ("PG role CTAs", slice(B, n))):
+    x = t[sl]
+    print(f" {name}: start {x[:,0].min():6.1f}..{x[:,0].max():6.1f} us   role end {x[:,1].min():6.1f}..{x[:,1].max():6.1f} "
+          f"(median {np.median(x[:,1]):6.1f})   exit {x[:,2].min():6.1f}..{x[:,2].max():6.1f}   "
+          f"role duration median {np.median(x[:,1]-x[:,0]):6.1f} max {np.max(x[:,1]-x[:,0]):6.1f}")
