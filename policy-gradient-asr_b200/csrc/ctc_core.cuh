@@ -338,7 +338,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // =====================================================================================================
 namespace pgasr {
 
-constexpr int kBatch = 8;         // frames per hand-off batch; two batches in flight per direction
+constexpr int kBatch = 7;         // frames per hand-off batch; two batches in flight per direction
 
 template <int SPL>
 struct GradRing {
@@ -377,7 +377,7 @@ __device__ __forceinline__ void ctc_build_class_lists(const int32_t* __restrict_
 
 template <int SPL>
 __host__ __device__ inline size_t grad_ring_bytes() {
-    return (size_t)2 * kBatch * SPL * 32 * 8 + 2 * kBatch * 4;
+    return (size_t)2 * kBatch * SPL * 32 * 8 + (((size_t)2 * kBatch * 4 + 15) & ~(size_t)15);   // slots + exponents
 }
 
 template <int SPL>
@@ -559,11 +559,8 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
         int* ep = ring.eslot + buf * kBatch;
         const int nfr = min(kBatch, n2 - q);
         if (nfr == kBatch) {
-#pragma unroll 1
-            for (int h = 0; h < kBatch / 4; ++h) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) ctc_walk_frame<SPL, kAlpha, false>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
-            }
+            for (int u = 0; u < kBatch; ++u) ctc_walk_frame<SPL, kAlpha, false>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
         } else {
             for (int u = 0; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
         }
@@ -594,7 +591,7 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
 // 48k of the 113k second-half cycles.)
 template <int SPL, int G, bool kAlpha>
 struct CtcWorker {
-    static constexpr int kPer = kBatch / G;               // frames of a batch per worker
+    static constexpr int kPer = (kBatch + G - 1) / G;     // frames of a batch per worker (worker g: frames g, g+G, ..)
     double2 o[kPer][SPL / 2];
     int eo[kPer];
 };
@@ -606,7 +603,7 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kPer; ++r) {
-        const int q = min(nb * kBatch + g + r * G, n2 - 1);   // clamped: a stale row is loaded, never used
+        const int q = min(nb * kBatch + min(g + r * G, kBatch - 1), n2 - 1);   // clamped: a stale row is loaded, never used
         const int step = n_first + q;
         const int t = kAlpha ? step : Tb - 1 - step;
         const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lane;
@@ -631,7 +628,7 @@ constexpr int kClsRegs = 8;       // label positions of this lane's class held i
 template <int SPL, int G, bool kAlpha>
 __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlpha>& wk, WorkerNorm& nm, int nb, int g,
                                                    int n2, const GradRing<SPL>& ring, int* gam,
-                                                   int (&gb)[kBatch / G]) {
+                                                   int (&gb)[(kBatch + G - 1) / G]) {
     constexpr int kPer = CtcWorker<SPL, G, kAlpha>::kPer;
     constexpr int kGam = 16 * SPL;                        // ints per frame: SPL/2 label occupancies per lane
     const int lane = threadIdx.x & 31;
@@ -639,7 +636,7 @@ __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlph
     for (int r = 0; r < kPer; ++r) {
         const int q = nb * kBatch + g + r * G;
         gb[r] = 0;
-        if (q < n2) {
+        if (g + r * G < kBatch && q < n2) {
             const int slot = q % (2 * kBatch);
             const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 32)) + lane;
             double wv[SPL];
@@ -688,15 +685,15 @@ template <int SPL, int G, bool kAlpha>
 __device__ __forceinline__ void ctc_worker_phase_b(const WorkerNorm& nm, int nb, int g, int n_first, int n2, int Tb,
                                                    const double* tile, int V, int RS, int blank, float grad_scale,
                                                    float* __restrict__ dlog_u, const GradRing<SPL>& ring,
-                                                   const int* gam, const int (&gb)[kBatch / G], int ccnt, int cmax,
+                                                   const int* gam, const int (&gb)[(kBatch + G - 1) / G], int ccnt, int cmax,
                                                    const int (&cpos)[kClsRegs]) {
-    constexpr int kPer = kBatch / G;
+    constexpr int kPer = (kBatch + G - 1) / G;
     constexpr int kGam = 16 * SPL;
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
         const int q = nb * kBatch + g + r * G;
-        if (q < n2) {
+        if (g + r * G < kBatch && q < n2) {
             const int step = n_first + q;
             const int t = kAlpha ? step : Tb - 1 - step;
             const double* row = tile + (size_t)t * RS;
@@ -740,9 +737,8 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
                                                 float* __restrict__ dlog_u, const double* __restrict__ lat_u,
                                                 const int* __restrict__ exp_u, GradRing<SPL> ring, int* gam,
                                                 Barrier mid_barrier) {
-    static_assert(kBatch % G == 0, "workers must divide the batch");
     constexpr int kGroup = 32 * (1 + G);
-    constexpr int kPer = kBatch / G;
+    constexpr int kPer = (kBatch + G - 1) / G;
     const int lane = threadIdx.x & 31;
     const int tm = Tb / 2;
     const int n_first = kAlpha ? tm : Tb - tm;

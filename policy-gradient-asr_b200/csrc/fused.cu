@@ -43,11 +43,12 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 constexpr int kFusedMaxK = 64;
 
 // ------------------------------------------------------------------------------------------------ CTC role
-// warp 0: alpha recurrence, warp 1: beta recurrence; warps with (warp & 3) == 2: alpha-side gradient workers,
-// (warp & 3) == 3: beta-side workers (they sit on the two schedulers the recurrence warps do not use).
+// warp 0: alpha recurrence, warp 1: beta recurrence; every other warp is a gradient worker, even warps on the
+// alpha side, odd warps on the beta side (G = (warps - 2) / 2 per direction).
 template <int SPL, int kThreads>
 __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw) {
-    constexpr int G = kThreads / 128;                      // gradient workers per direction
+    constexpr int G = (kThreads / 32 - 2) / 2;             // gradient workers per direction
+    constexpr int kPer = (kBatch + G - 1) / G;             // frames of a batch per worker
     constexpr int kMidThreads = 32 * (2 + 2 * G);
     const int warp = threadIdx.x >> 5;
     const int T = a.T, V = a.V;
@@ -67,8 +68,8 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         unsigned char* p = smem_raw + (size_t)T * RS * 8;
         GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
         GradRing<SPL> ring_b = grad_ring_carve<SPL>(p, 6);                  p += grad_ring_bytes<SPL>();
-        int* gam_all = reinterpret_cast<int*>(p);                           // [2 kBatch frames][16 SPL]
-        p += (size_t)2 * kBatch * 16 * SPL * sizeof(int);
+        int* gam_all = reinterpret_cast<int*>(p);                           // [2 G workers][kPer frames][16 SPL]
+        p += (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
         int* cls_off = reinterpret_cast<int*>(p);                           // [V + 1]
         int* cls_scr = cls_off + (V + 1);                                   // [V] counting-sort scratch
         int* cls_pos = cls_scr + V;                                         // [Lmax]
@@ -81,7 +82,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         const float* lg = a.logits + (size_t)b * T * V;
         {
             float* stage = reinterpret_cast<float*>(smem_raw + (size_t)T * RS * 8);
-            const size_t stage_bytes = 2 * grad_ring_bytes<SPL>() + (size_t)2 * kBatch * 16 * SPL * sizeof(int);
+            const size_t stage_bytes = 2 * grad_ring_bytes<SPL>() + (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
             const int chunk = (int)(stage_bytes / ((size_t)V * 4)) & ~3;
             const bool al16 = (((size_t)T * V * 4) & 15) == 0;
             for (int c0 = 0; c0 < Tb; c0 += chunk) {
@@ -139,17 +140,17 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
             __threadfence_block();
             asm volatile("bar.sync 1, %0;\n" ::"n"(kMidThreads) : "memory");
         };
-        const int role = warp & 3, g = warp >> 2;
+        const int g = (warp - 2) >> 1;
         if (warp == 0)
             ctc_walk_tile<SPL, G, true>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid);
         else if (warp == 1)
             ctc_walk_tile<SPL, G, false>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_b, mid);
-        else if (role == 2)
+        else if (g < G && !(warp & 1))
             ctc_grad_worker<SPL, G, true>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_a,
-                                          gam_all + g * (kBatch / G) * 16 * SPL, mid);
-        else if (role == 3)
+                                          gam_all + g * kPer * 16 * SPL, mid);
+        else if (g < G)
             ctc_grad_worker<SPL, G, false>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_b,
-                                           gam_all + (G + g) * (kBatch / G) * 16 * SPL, mid);
+                                           gam_all + (G + g) * kPer * 16 * SPL, mid);
     }
     __threadfence();                                       // rows and nll visible device-wide before the flag
     __syncthreads();
@@ -454,7 +455,8 @@ static FusedWs fused_ws(int B, int T, int spl) {
 static size_t fused_smem(int T, int V, int K, int spl, int threads) {
     const int RS = ctc_row_stride(V);
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
-    const size_t ctc = (size_t)T * RS * sizeof(double) + 2 * ring + (size_t)2 * kBatch * 16 * spl * sizeof(int) +
+    const int G = (threads / 32 - 2) / 2, per = (kBatch + G - 1) / G;
+    const size_t ctc = (size_t)T * RS * sizeof(double) + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) +
                        (size_t)(2 * V + 1 + 512) * sizeof(int);
     const int Tp = (T + 15) & ~15, W = spl / 2;
     size_t pg = (((size_t)T * V * 4 + 15) & ~(size_t)15) + (size_t)2 * K * Tp + (size_t)(V + 1) * W * 4 + 16;
