@@ -74,6 +74,7 @@ def traffic_from_profile(workload_key):
 def cpu_step_fn(args, B):
     from oracle import cport
     from tests.synth import make_batch
+    cport.set_num_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses all cores
     logits, targets, in_len, tgt_len, _ = make_batch(B, args.T, args.V, args.K, args.L, seed=1234, regime=args.regime)
 
     def step(i):

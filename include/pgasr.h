@@ -20,6 +20,7 @@
  *   pgasr_pg_ctc_step               model.py:235-237    criterion(model_out, t); loss.backward()
  *                                                       -- the whole loss step in one call
  *   pgasr_host_*                    model.py:317-320    the same step on HOST arrays, pipelined
+ *   pgasr_ctc_beam_search           CTCdecoder.py:41-116 CTCDecoder.decode(probs, beam_size, blank)
  * The Python binding a maintainer adds is shown in INTEGRATION.md.
  *
  * Layouts (all contiguous, batch first as upstream: batch_first=True, model.py:44,55):
@@ -144,6 +145,16 @@ PGASR_API int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, con
                       float* loss, float* dlogits, float* rewards, float* logp, int32_t* hyp_len,
                       int32_t* dist, float* nll, uint8_t* samples,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- CTC prefix beam search (upstream CTCdecoder.py:41-116, CTCDecoder.decode) -----------------------
+ * probs [N,T,V] fp64 post-softmax (upstream takes the post-softmax array and works in Python floats), frames
+ * t >= in_len[n] ignored (in_len NULL: T).  labels [N,T] int32 receives the best prefix of each utterance (zero
+ * filled beyond label_len[n]), nll[n] = -log(p_blank + p_non_blank) of that prefix, as upstream returns.
+ * One CTA per utterance; V <= 64, beam <= 128.  workspace: pgasr_ctc_beam_search_workspace_bytes(N,T,V,beam).  */
+PGASR_API size_t pgasr_ctc_beam_search_workspace_bytes(int N, int T, int V, int beam);
+PGASR_API int pgasr_ctc_beam_search(const double* probs, const int32_t* in_len, int N, int T, int V, int beam,
+                          int blank, int32_t* labels, int32_t* label_len, double* nll,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- the step on HOST buffers (upstream hands the metric/reward code host arrays: model.py:317-320) ----
  * A pipeline owns the device buffers for `depth` steps in flight, three streams (copy-in, compute, copy-out)

@@ -83,6 +83,13 @@ def max_threads():
     return int(lib().orc_max_threads())
 
 
+def set_num_threads(n):
+    """Use n OpenMP threads from now on (overrides an inherited OMP_NUM_THREADS)."""
+    lib().orc_set_num_threads.argtypes = [C.c_int]
+    lib().orc_set_num_threads.restype = None
+    lib().orc_set_num_threads(int(n))
+
+
 def edit_distance(ref, hyp, last_col=False):
     ref, hyp = _i32(ref), _i32(hyp)
     col = np.zeros(len(hyp) + 1, np.int32) if last_col else None

@@ -35,6 +35,15 @@
 
 ORC_API int orc_version(void) { return 1; }
 
+/* bench.py's CPU arm uses every host core even when a launcher (torchrun) exported OMP_NUM_THREADS=1 */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -2,10 +2,9 @@
 
 collapse_fn(preds: str) -> str keeps a character iff it differs from its predecessor
 (upstream CTCdecoder.py:119-131); it does not remove blanks, exactly like upstream.
-CTCDecoder.decode is the eval-time prefix beam search (upstream CTCdecoder.py:41-116); it is outside the
-training hot path and runs on the host.
+CTCDecoder.decode is the eval-time prefix beam search (upstream CTCdecoder.py:41-116),
+one CTA per utterance on the GPU; decode_batch decodes a whole dev set in one launch.
 """
-import math
 
 import numpy as np
 import torch
@@ -44,55 +43,34 @@ def collapse_fn(preds):
     return collapse_batch([preds])[0]
 
 
-def _lse(*xs):
-    m = max(xs)
-    if m == NEG_INF:
-        return NEG_INF
-    return m + math.log(sum(math.exp(x - m) for x in xs))
-
-
 class CTCDecoder:
     """Prefix beam search with the upstream constructor and decode() signature
     (CTCdecoder.py:23-25, 41-116): decode(probs[T,V] post-softmax, beam_size=100, blank=0)
-    -> (labels tuple, negative log-likelihood)."""
+    -> (labels tuple, negative log-likelihood), computed by the batched GPU kernel (csrc/beam.cu)."""
 
     def __init__(self, alphabet):
         self.alphabet = alphabet
         self.NEG_INF = NEG_INF
 
-    def make_new_beam(self):
-        return {}
-
-    def logsumexp(self, *args):
-        return _lse(*args)
+    def decode_batch(self, probs_list, beam_size=100, blank=0):
+        """decode() for a list of [T_i, V] arrays in one launch (one CTA per utterance)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("pgasr_b200.CTCdecoder.CTCDecoder.decode needs a CUDA device (no CPU fallback)")
+        if not probs_list:
+            return []
+        arrs = [np.asarray(p, dtype=np.float64) for p in probs_list]
+        V = arrs[0].shape[1]
+        T = max(1, max(a.shape[0] for a in arrs))
+        batch = np.zeros((len(arrs), T, V), np.float64)
+        for i, a in enumerate(arrs):
+            if a.ndim != 2 or a.shape[1] != V:
+                raise ValueError("every probs array must be [T, V] with the same V")
+            batch[i, :a.shape[0]] = a
+        dev = torch.device("cuda", torch.cuda.current_device())
+        lens = torch.tensor([a.shape[0] for a in arrs], dtype=torch.int32, device=dev)
+        labels, label_len, nll = F.ctc_beam_search(torch.from_numpy(batch).to(dev), lens, beam_size=beam_size, blank=blank)
+        labels, label_len, nll = labels.cpu().numpy(), label_len.cpu().numpy(), nll.cpu().numpy()
+        return [(tuple(int(x) for x in labels[i, :label_len[i]]), float(nll[i])) for i in range(len(arrs))]
 
     def decode(self, probs, beam_size=100, blank=0):
-        T, V = probs.shape
-        with np.errstate(divide="ignore"):
-            lp = np.log(probs)
-        beam = [((), (0.0, NEG_INF))]
-        for t in range(T):
-            cand = {}        # insertion-ordered: ties in the sort below resolve as upstream's do
-
-            def slot(prefix):
-                if prefix not in cand:
-                    cand[prefix] = [NEG_INF, NEG_INF]
-                return cand[prefix]
-
-            for s in range(V):
-                p = float(lp[t, s])
-                for prefix, (p_b, p_nb) in beam:
-                    if s == blank:
-                        e = slot(prefix)
-                        e[0] = _lse(e[0], p_b + p, p_nb + p)
-                        continue
-                    last = prefix[-1] if prefix else None
-                    e = slot(prefix + (s,))
-                    e[1] = _lse(e[1], p_b + p, p_nb + p) if s != last else _lse(e[1], p_b + p)
-                    if s == last:
-                        e = slot(prefix)
-                        e[1] = _lse(e[1], p_nb + p)
-            ranked = sorted(cand.items(), key=lambda kv: _lse(*kv[1]), reverse=True)
-            beam = [(k, (v[0], v[1])) for k, v in ranked[:beam_size]]
-        labels, (p_b, p_nb) = beam[0]
-        return labels, -_lse(p_b, p_nb)
+        return self.decode_batch([probs], beam_size=beam_size, blank=blank)[0]

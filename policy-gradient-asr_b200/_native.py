@@ -31,6 +31,8 @@ SIGNATURES = {
     "pgasr_pg_ctc_step_workspace_init": (_i, [_vp, _sz, _vp]),
     "pgasr_pg_ctc_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pgasr_ctc_beam_search_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "pgasr_ctc_beam_search": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pgasr_host_create": (_i, [_i, _i, _i, _i, _i, _i, _vp]),
     "pgasr_host_destroy": (_i, [_vp]),
     "pgasr_host_submit": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),

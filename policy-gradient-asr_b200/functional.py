@@ -218,6 +218,24 @@ def nll_sum_backward(target, grad_out, L, B, V, ignore_index=-1):
     return g
 
 
+def ctc_beam_search(probs, input_lengths=None, beam_size=100, blank=0):
+    """SURVEY 8f.2 (upstream CTCdecoder.py:41-116).  probs [N,T,V] fp64 post-softmax on the GPU ->
+    labels [N,T] int32 (best prefix per utterance, zero padded), label_len [N] int32, nll [N] fp64."""
+    probs = _need(probs, torch.float64, "probs", 3)
+    N, T, V = probs.shape
+    in_len = _opt_i32(input_lengths, "input_lengths", N, probs.device)
+    nbytes = _native.lib().pgasr_ctc_beam_search_workspace_bytes(N, T, V, int(beam_size))
+    if nbytes == 0:
+        raise _native.PgasrError("pgasr_ctc_beam_search_workspace_bytes", -2, "unsupported size (V <= 64, beam <= 128)")
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=probs.device)
+    labels = torch.empty((N, T), dtype=torch.int32, device=probs.device)
+    label_len = torch.empty((N,), dtype=torch.int32, device=probs.device)
+    nll = torch.empty((N,), dtype=torch.float64, device=probs.device)
+    _native.call("pgasr_ctc_beam_search", _ptr(probs), _ptr(in_len), N, T, V, int(beam_size), int(blank),
+                 _ptr(labels), _ptr(label_len), _ptr(nll), _ptr(ws), nbytes, _stream())
+    return labels, label_len, nll
+
+
 class StepWorkspace:
     """Device scratch of pgasr_pg_ctc_step, sized once per (B,T,V,K,Lmax) and reused across steps."""
 

@@ -55,6 +55,8 @@ def test_no_device_is_loud_not_a_fallback():
         pgasr_b200.metrics.edit_dist("kitten", "sitting")
     with pytest.raises(RuntimeError):
         pgasr_b200.CTCdecoder.collapse_fn("aab")
+    with pytest.raises(RuntimeError):
+        pgasr_b200.CTCdecoder.CTCDecoder(None).decode(np.full((4, 3), 1 / 3))
     with pytest.raises(TypeError):
         pgasr_b200.loss.customNLLLoss()(torch.zeros(2, 2, 3), torch.zeros(2, 2, dtype=torch.long))
     with pytest.raises(pgasr_b200._native.PgasrError) as ei:      # the host-buffer API has no CPU path either
@@ -107,15 +109,6 @@ def test_dropin_modules_have_upstream_names():
         ["self", "probs", "beam_size", "blank"]
     assert inspect.signature(pgasr_b200.CTCdecoder.CTCDecoder.decode).parameters["beam_size"].default == 100
     assert inspect.signature(pgasr_b200.loss.customNLLLoss.__init__).parameters["ignore_index"].default is None
-
-
-def test_host_beam_search_matches_upstream_vectors(golden):
-    import pgasr_b200
-    dec = pgasr_b200.CTCdecoder.CTCDecoder(alphabet=None)
-    for e in golden["beam_search"]:
-        labels, nll = dec.decode(np.array(e["probs"]), beam_size=e["beam"])
-        assert list(labels) == e["labels"]
-        assert abs(nll - e["nll"]) < 1e-9
 
 
 def test_save_predictions(tmp_path):

@@ -444,3 +444,80 @@ def test_host_pipeline_rejects_bad_arguments(cuda):
             pipe.submit(torch.zeros(2, 19, 30), torch.zeros(2, 5, dtype=torch.int32))
     with pytest.raises(RuntimeError):
         pipe.submit(torch.zeros(2, 20, 30), torch.zeros(2, 5, dtype=torch.int32))
+
+
+# ------------------------------------------------------------------------------- prefix beam search
+def _softmax_rows(z):
+    p = np.exp(z - z.max(-1, keepdims=True))
+    return p / p.sum(-1, keepdims=True)
+
+
+@pytest.mark.gpu
+def test_beam_search_upstream_golden(cuda, golden):
+    """CTCDecoder.decode against the vectors produced by the real upstream decoder (CTCdecoder.py:41-116)."""
+    import pgasr_b200
+    dec = pgasr_b200.CTCdecoder.CTCDecoder(alphabet=None)
+    for e in golden["beam_search"]:
+        labels, nll = dec.decode(np.array(e["probs"]), beam_size=e["beam"])
+        assert list(labels) == e["labels"]
+        assert abs(nll - e["nll"]) < 1e-9
+    # several utterances (of different lengths) in one launch
+    e = golden["beam_search"][2]
+    full = np.array(e["probs"])
+    outs = dec.decode_batch([full, full[:7], full], beam_size=e["beam"])
+    assert list(outs[0][0]) == e["labels"] and list(outs[2][0]) == e["labels"] and abs(outs[2][1] - e["nll"]) < 1e-9
+    assert outs[1] == dec.decode(full[:7], beam_size=e["beam"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,V,beam,peaky", [(40, 5, 1, False), (60, 30, 5, False), (80, 30, 5, True), (50, 8, 100, False),
+                                             (35, 30, 128, True), (120, 4, 16, False), (30, 64, 7, False)])
+def test_beam_search_matches_oracle_random(cuda, T, V, beam, peaky):
+    """Random posteriors (incl. exact zeros and ragged lengths) against the oracle restatement of upstream's decoder."""
+    from oracle import pyref
+    from pgasr_b200 import functional as F
+    rng = np.random.default_rng(T * 1000 + V * 10 + beam)
+    N = 5
+    z = rng.normal(size=(N, T, V)) * (4.0 if peaky else 1.5)
+    if peaky:
+        z[:, :, 0] += 3.0
+    p = _softmax_rows(z)
+    p[0, ::7, 1] = 0.0                                      # log(0) = -inf entries (rows need not sum to one)
+    lens = np.array([T, T - 1, max(T // 2, 1), 1, T], np.int32)
+    labels, label_len, nll = F.ctc_beam_search(dev_t(p, cuda), dev_t(lens, cuda), beam_size=beam)
+    labels, label_len, nll = labels.cpu().numpy(), label_len.cpu().numpy(), nll.cpu().numpy()
+    for n in range(N):
+        with np.errstate(divide="ignore"):
+            ref_labels, ref_nll = pyref.prefix_beam_search(p[n, :lens[n]], beam_size=beam)
+        assert tuple(labels[n, :label_len[n]]) == tuple(ref_labels), n
+        assert abs(nll[n] - ref_nll) <= 1e-9 * max(1.0, abs(ref_nll)), n
+        assert (labels[n, label_len[n]:] == 0).all()
+
+
+@pytest.mark.gpu
+def test_beam_search_properties_full_size(cuda):
+    """T=500, V=30 (upstream's reward() and predict() call it with beam_size=5): beam=1 on one-hot posteriors is
+    the collapsed argmax path; the beam score is bounded by the exact CTC likelihood of the returned labels."""
+    from pgasr_b200 import functional as F
+    rng = np.random.default_rng(3)
+    N, T, V = 16, 500, 30
+    path = rng.integers(0, V, size=(N, T))
+    onehot = np.full((N, T, V), 1e-12)
+    np.put_along_axis(onehot, path[..., None], 1.0, axis=-1)
+    labels, label_len, _ = F.ctc_beam_search(dev_t(onehot, cuda), None, beam_size=1)
+    col, col_len = F.collapse(dev_t(path.astype(np.uint8), cuda), blank=0)
+    for n in range(N):
+        k = int(label_len[n])
+        assert k == int(col_len[n]) and torch.equal(labels[n, :k].to(torch.uint8), col[n, :k])
+    # the beam sums a subset of the alignments of its best prefix: its score can never beat the exact CTC
+    # likelihood of that label sequence (computed by the CTC kernel of this library)
+    p = _softmax_rows(rng.normal(size=(N, T, V)) * 2)
+    logits = dev_t(np.log(p).astype(np.float32), cuda)
+    for beam in (1, 5, 25):
+        labels, label_len, nll = F.ctc_beam_search(dev_t(p, cuda), None, beam_size=beam)
+        assert bool(torch.isfinite(nll).all()) and int(label_len.min()) > 0
+        Lmax = int(label_len.max())
+        exact, _ = F.ctc_loss_grad(logits, labels[:, :Lmax].contiguous(), None, label_len)
+        assert bool((nll.cpu() >= exact.cpu().double() * (1 - 1e-4)).all())
+    with pytest.raises(Exception):
+        F.ctc_beam_search(dev_t(p, cuda), None, beam_size=129)
