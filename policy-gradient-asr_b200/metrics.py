@@ -66,6 +66,23 @@ def evaluate(s1, s2):
     return cer, wer
 
 
+def evaluate_batch(targets, predictions):
+    """evaluate() for a whole list of (target, prediction) string pairs (upstream's predict() loop calls it per
+    utterance, model.py:321-337): two distances per pair, all pairs in one launch per kernel.
+    Returns a list of (cer, wer); an empty target raises ZeroDivisionError like upstream."""
+    if len(targets) != len(predictions):
+        raise ValueError("targets and predictions must pair up")
+    refs, hyps = [], []
+    for s1, s2 in zip(targets, predictions):
+        refs += [s1, s1.split(" ")]
+        hyps += [s2, s2.split(" ")]
+    d = edit_dist_batch(refs, hyps)
+    out = []
+    for i, s1 in enumerate(targets):
+        out.append((d[2 * i] / len(s1), d[2 * i + 1] / len(s1.split(" "))))
+    return out
+
+
 def save_predictions(target, predicted, model_path):
     """Upstream metrics.py:33-37: one `target|prediction` line per utterance in predicted.txt."""
     path = os.path.join(model_path, "predicted.txt")

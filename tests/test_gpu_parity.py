@@ -521,3 +521,16 @@ def test_beam_search_properties_full_size(cuda):
         assert bool((nll.cpu() >= exact.cpu().double() * (1 - 1e-4)).all())
     with pytest.raises(Exception):
         F.ctc_beam_search(dev_t(p, cuda), None, beam_size=129)
+
+
+@pytest.mark.gpu
+def test_evaluate_batch_matches_upstream_golden(cuda, golden):
+    """the predict() loop's per-utterance evaluate() (metrics.py:23-31) as one batched call."""
+    import pgasr_b200
+    ev = golden["evaluate"]
+    got = pgasr_b200.metrics.evaluate_batch([e["ref"] for e in ev], [e["hyp"] for e in ev])
+    for g, e in zip(got, ev):
+        assert g == tuple(e["out"])                  # int / int in Python floats on both sides: exact
+        assert pgasr_b200.metrics.evaluate(e["ref"], e["hyp"]) == tuple(e["out"])
+    with pytest.raises(ZeroDivisionError):
+        pgasr_b200.metrics.evaluate_batch(["ab", ""], ["ab", "x"])
