@@ -621,7 +621,7 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
 
 struct WorkerNorm { double invZ0; int E0; bool dead, have; long long tA, tB, tWait, tBusy; };
 
-constexpr int kClsRegs = 8;       // label positions of this lane's class held in registers
+constexpr int kClsRegs = 12;      // label positions of this lane's class held in registers
 
 // phase A: occupancies of every owned frame of batch nb; label states go to gam[frame][label index] and the
 // blank total to gb[] (2^-30 fixed point)
@@ -705,8 +705,10 @@ __device__ __forceinline__ void ctc_worker_phase_b(const WorkerNorm& nm, int nb,
                 int o2 = 0;
 #pragma unroll
                 for (int i = 0; i < kClsRegs; i += 2) {
-                    occ += gr[cpos[i]];
-                    o2 += gr[cpos[i + 1]];
+                    if (i < cmax) {                            // warp uniform: no class of this transcript is longer
+                        occ += gr[cpos[i]];
+                        o2 += gr[cpos[i + 1]];
+                    }
                 }
                 occ += o2;
                 for (int i = kClsRegs; i < cmax; ++i)

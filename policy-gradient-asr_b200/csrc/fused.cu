@@ -101,26 +101,31 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                 cp_async_wait<0>();
                 __syncthreads();
                 for (int t = threadIdx.x; t < n; t += kThreads) {
-                    float* zr = stage + (size_t)t * V;
+                    // the row lives in registers in rotated order (slot k holds class (k + t) & 31): the order does
+                    // not matter for the max and the sum, every load / exp / store is independent of the others
+                    const float* zr = stage + (size_t)t * V;
                     double* orow = tile + (size_t)(c0 + t) * RS;
-                    float m = -INFINITY;
+                    float x[32];
+#pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const int idx = (k + t) & 31;
-                        if (idx < V) m = fmaxf(m, zr[idx]);
+                        x[k] = idx < V ? zr[idx] : -INFINITY;
                     }
-                    float ssum = 0.0f;
+                    float m4[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+                    for (int k = 4; k < 32; ++k) m4[k & 3] = fmaxf(m4[k & 3], x[k]);
+                    const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                    float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
                     for (int k = 0; k < 32; ++k) {
-                        const int idx = (k + t) & 31;
-                        if (idx < V) {
-                            const float e = __expf(zr[idx] - m);
-                            zr[idx] = e;
-                            ssum += e;
-                        }
+                        x[k] = __expf(x[k] - m);                   // exp(-inf) = 0 for the unused slots
+                        s4[k & 3] += x[k];
                     }
-                    const float inv = 1.0f / ssum;
+                    const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const int idx = (k + t) & 31;
-                        if (idx < RS) orow[idx] = idx < V ? (double)(zr[idx] * inv) : 0.0;
+                        if (idx < RS) orow[idx] = (double)(x[k] * inv);
                     }
                     for (int idx = 32; idx < RS; ++idx) orow[idx] = 0.0;
                 }
@@ -475,8 +480,12 @@ size_t fused_workspace_bytes(int B, int T, int V, int K, int Lmax) {
 
 template <int SPL, int kThreads>
 static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
-    PGASR_CUDA_TRY(cudaFuncSetAttribute(pg_ctc_fused_kernel<SPL, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+    static thread_local size_t smem_set = 0;               // the opt-in is sticky: raise it only when a larger tile comes
+    if (smem > smem_set) {
+        PGASR_CUDA_TRY(cudaFuncSetAttribute(pg_ctc_fused_kernel<SPL, kThreads>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     const int grid = (a.do_ctc ? a.B : 0) + (a.do_pg ? a.B : 0);
     pg_ctc_fused_kernel<SPL, kThreads><<<grid, kThreads, smem, st>>>(a);
     PGASR_LAUNCH_CHECK();

@@ -53,3 +53,13 @@ for name, sl in (("CTC role CTAs", slice(0, B)), ("PG role CTAs", slice(B, n))):
     print(f" {name}: start {x[:,0].min():6.1f}..{x[:,0].max():6.1f} us   role end {x[:,1].min():6.1f}..{x[:,1].max():6.1f} "
           f"(median {np.median(x[:,1]):6.1f})   exit {x[:,2].min():6.1f}..{x[:,2].max():6.1f}   "
           f"role duration median {np.median(x[:,1]-x[:,0]):6.1f} max {np.max(x[:,1]-x[:,0]):6.1f}")
+
+# does a CTC CTA's duration follow the largest class count of its transcript (the gather's tail loop)?
+tgn = tg.cpu().numpy()
+cmax = np.array([np.bincount(tgn[b], minlength=30)[1:].max() for b in range(B)])
+dur = t[:B, 1] - t[:B, 0]
+order = np.argsort(dur)
+print(" CTC role duration by utterance (us) / max labels of one class:")
+print("   fastest: " + "  ".join(f"{dur[i]:.1f}/{cmax[i]}" for i in order[:8]))
+print("   slowest: " + "  ".join(f"{dur[i]:.1f}/{cmax[i]}" for i in order[-8:]))
+print(f"   corr(duration, cmax) = {np.corrcoef(dur, cmax)[0, 1]:.2f}")
