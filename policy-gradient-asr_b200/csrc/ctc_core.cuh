@@ -420,9 +420,10 @@ __device__ __forceinline__ void ctc_presum(CtcLane<SPL>& st, double h0, double h
     }
 }
 
+// (not volatile: the probability tile is read-only while the walkers run, the scheduler may move these loads)
 __device__ __forceinline__ double lds_f64(unsigned addr) {
     double v;
-    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+    asm("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
     return v;
 }
 
@@ -435,9 +436,11 @@ template <int SPL, bool kAlpha>
 struct CtcWalk {
     CtcLane<SPL> st;
     double h0, h1;                // halo values for the frame about to be computed
-    unsigned pa_b, pa[SPL / 2];   // running shared-memory addresses of this lane's probabilities
+    double pb_n, p_n[SPL / 2];    // probabilities of the frame about to be computed (loaded one frame ahead)
+    unsigned pa_b, pa[SPL / 2];   // running shared-memory addresses of this lane's probabilities: the frame after
     int rstride;
     bool edge;
+    bool act;                     // this lane holds at least one state < S (lanes beyond never touch the lattice)
 };
 
 template <int SPL, bool kAlpha>
@@ -475,17 +478,24 @@ template <int SPL, bool kAlpha, bool kFirst>
 __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*& dst, ptrdiff_t dstride, int*& edst,
                                                int estride, bool lane0) {
     double p[SPL / 2];
-    const double pb = lds_f64(w.pa_b);
+    const double pb = w.pb_n;
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) p[i] = lds_f64(w.pa[i]);
+    for (int i = 0; i < SPL / 2; ++i) p[i] = w.p_n[i];
+    w.pb_n = lds_f64(w.pa_b);                             // next frame's values fly while this frame is computed
+#pragma unroll
+    for (int i = 0; i < SPL / 2; ++i) w.p_n[i] = lds_f64(w.pa[i]);
     w.pa_b += w.rstride;
 #pragma unroll
     for (int i = 0; i < SPL / 2; ++i) w.pa[i] += w.rstride;
     ctc_presum<SPL, kAlpha>(w.st, w.h0, w.h1);
+#ifndef EXP_NO_LATSTORE
     if (kFirst) {
+        if (w.act) {
 #pragma unroll
-        for (int jj = 0; jj < SPL / 2; ++jj) dst[jj * 32] = make_double2(w.st.a[2 * jj], w.st.a[2 * jj + 1]);
+            for (int jj = 0; jj < SPL / 2; ++jj) dst[jj * 32] = make_double2(w.st.a[2 * jj], w.st.a[2 * jj + 1]);
+        }
     }
+#endif
 #pragma unroll
     for (int j = 0; j < SPL; ++j) w.st.a[j] *= (j & 1) ? p[j >> 1] : pb;
     ctc_walk_halo<SPL, kAlpha>(w);
@@ -513,15 +523,23 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
     CtcWalk<SPL, kAlpha> w;
     ctc_lane_init<SPL, kAlpha>(w.st, lab_u, L, V);
     w.edge = kAlpha ? lane == 0 : lane == 31;
+    w.act = lane * SPL < S;
     const bool dbg = ring.dbg && lane == 0;
     PGASR_STAMP(dbg, kAlpha ? 10 : 14);
 
     const int t0 = kAlpha ? 0 : Tb - 1;
     w.rstride = kAlpha ? RS * 8 : -RS * 8;
-    const unsigned row0 = (unsigned)__cvta_generic_to_shared(tile) + (unsigned)(t0 * RS * 8);
-    w.pa_b = row0 + (unsigned)(blank * 8);
+    unsigned row0 = (unsigned)__cvta_generic_to_shared(tile) + (unsigned)(t0 * RS * 8);
+    // every tile load below takes its address from this opaque copy, so none of them (plain asm, free to be
+    // scheduled) can be moved above this point, i.e. above the barrier that published the tile
+    asm volatile("mov.u32 %0, %0;\n" : "+r"(row0) : : "memory");
+    w.pb_n = lds_f64(row0 + (unsigned)(blank * 8));
+    w.pa_b = row0 + (unsigned)(blank * 8) + w.rstride;
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) w.pa[i] = row0 + (unsigned)(w.st.loff[i] * 8);
+    for (int i = 0; i < SPL / 2; ++i) {
+        w.p_n[i] = lds_f64(row0 + (unsigned)(w.st.loff[i] * 8));
+        w.pa[i] = row0 + (unsigned)(w.st.loff[i] * 8) + w.rstride;
+    }
     // virtual vector before the first frame: the recurrence turns it into the CTC start (alpha: states 0,1;
     // beta: states S-1,S-2) -- see DESIGN.md "CTC spec"
 #pragma unroll
@@ -598,9 +616,10 @@ struct CtcWorker {
 
 template <int SPL, int G, bool kAlpha>
 __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, int nb, int g, int n_first, int n2,
-                                                 int Tb, const double* __restrict__ lat_u,
+                                                 int Tb, int S, const double* __restrict__ lat_u,
                                                  const int* __restrict__ exp_u) {
     const int lane = threadIdx.x & 31;
+    const bool act = lane * SPL < S;                      // the other direction never stored the lanes beyond S
 #pragma unroll
     for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kPer; ++r) {
         const int q = min(nb * kBatch + min(g + r * G, kBatch - 1), n2 - 1);   // clamped: a stale row is loaded, never used
@@ -613,7 +632,7 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
         wk.eo[r] = 0; (void)lp;
 #else
 #pragma unroll
-        for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = __ldcg(lp + jj * 32);
+        for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = act ? __ldcg(lp + jj * 32) : make_double2(0.0, 0.0);
         wk.eo[r] = __ldcg(exp_u + t);
 #endif
     }
@@ -751,7 +770,7 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
 #pragma unroll
     for (int i = 0; i < kClsRegs; ++i) cpos[i] = (i < ccnt) ? ring.cls_pos[ring.cls_off[min(lane, V - 1)] + i] : 16 * SPL - 1;
     const int cmax = __reduce_max_sync(kFull, ccnt);
-    (void)lab_u; (void)L;
+    (void)lab_u;
     mid_barrier();                                        // the other direction's half-lattice is complete
     WorkerNorm nm;
     nm.invZ0 = 0.0; nm.E0 = 0; nm.dead = false; nm.have = false;
@@ -759,7 +778,8 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
     const int nbatch = (n2 + kBatch - 1) / kBatch;
     CtcWorker<SPL, G, kAlpha> wk;
     int gb[kPer];
-    if (nbatch > 0) ctc_worker_fetch<SPL, G, kAlpha>(wk, 0, g, n_first, n2, Tb, lat_u, exp_u);
+    const int S = 2 * L + 1;
+    if (nbatch > 0) ctc_worker_fetch<SPL, G, kAlpha>(wk, 0, g, n_first, n2, Tb, S, lat_u, exp_u);
     for (int nb = 0; nb < nbatch; ++nb) {
         const int buf = nb & 1;
 #ifdef PGASR_TIMING
@@ -776,7 +796,7 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
         const long long w2 = clock64();
         nm.tA += w2 - w1;
 #endif
-        if (nb + 1 < nbatch) ctc_worker_fetch<SPL, G, kAlpha>(wk, nb + 1, g, n_first, n2, Tb, lat_u, exp_u);
+        if (nb + 1 < nbatch) ctc_worker_fetch<SPL, G, kAlpha>(wk, nb + 1, g, n_first, n2, Tb, S, lat_u, exp_u);
         ctc_worker_phase_b<SPL, G, kAlpha>(nm, nb, g, n_first, n2, Tb, tile, V, RS, blank, grad_scale, dlog_u, ring,
                                            gam, gb, ccnt, cmax, cpos);
 #ifdef PGASR_TIMING

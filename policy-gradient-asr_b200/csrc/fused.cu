@@ -64,8 +64,10 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     if (Tb == 0) {
         if (threadIdx.x == 0) *nll_u = L == 0 ? 0.0f : INFINITY;
     } else {
-        double* tile = reinterpret_cast<double*>(smem_raw);                 // [T][RS]
-        unsigned char* p = smem_raw + (size_t)T * RS * 8;
+        // [T][RS] between two guard rows: the walkers load the probabilities one frame ahead and run one row past
+        // either end (the guard values are loaded and never used)
+        double* tile = reinterpret_cast<double*>(smem_raw) + RS;
+        unsigned char* p = smem_raw + (size_t)(T + 2) * RS * 8;
         GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
         GradRing<SPL> ring_b = grad_ring_carve<SPL>(p, 6);                  p += grad_ring_bytes<SPL>();
         int* gam_all = reinterpret_cast<int*>(p);                           // [2 G workers][kPer frames][16 SPL]
@@ -81,7 +83,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         // writes (row stride RS doubles) collide on a shared-memory bank.
         const float* lg = a.logits + (size_t)b * T * V;
         {
-            float* stage = reinterpret_cast<float*>(smem_raw + (size_t)T * RS * 8);
+            float* stage = reinterpret_cast<float*>(smem_raw + (size_t)(T + 2) * RS * 8);
             const size_t stage_bytes = 2 * grad_ring_bytes<SPL>() + (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
             const int chunk = (int)(stage_bytes / ((size_t)V * 4)) & ~3;
             const bool al16 = (((size_t)T * V * 4) & 15) == 0;
@@ -461,7 +463,7 @@ static size_t fused_smem(int T, int V, int K, int spl, int threads) {
     const int RS = ctc_row_stride(V);
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
     const int G = (threads / 32 - 2) / 2, per = (kBatch + G - 1) / G;
-    const size_t ctc = (size_t)T * RS * sizeof(double) + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) +
+    const size_t ctc = (size_t)(T + 2) * RS * sizeof(double) + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) +
                        (size_t)(2 * V + 1 + 512) * sizeof(int);
     const int Tp = (T + 15) & ~15, W = spl / 2;
     size_t pg = (((size_t)T * V * 4 + 15) & ~(size_t)15) + (size_t)2 * K * Tp + (size_t)(V + 1) * W * 4 + 16;
