@@ -53,28 +53,33 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     const int warp = threadIdx.x >> 5;
     const int T = a.T, V = a.V;
     const int RS = ctc_row_stride(V);
+    // shared-memory carve-up (see fused_smem)
+    // [T][RS] between two guard rows: the walkers load the probabilities one frame ahead and run one row past
+    // either end (the guard values are loaded and never used)
+    double* tile = reinterpret_cast<double*>(smem_raw) + RS;
+    unsigned char* p = smem_raw + (size_t)(T + 2) * RS * 8;
+    GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
+    GradRing<SPL> ring_b = grad_ring_carve<SPL>(p, 6);                  p += grad_ring_bytes<SPL>();
+    int* gam_all = reinterpret_cast<int*>(p);                           // [2 G workers][kPer frames][16 SPL]
+    p += (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
+    int* cls_off = reinterpret_cast<int*>(p);                           // [V + 1]
+    int* cls_scr = cls_off + (V + 1);                                   // [V] counting-sort scratch
+    int* cls_pos = cls_scr + V;                                         // [512]
+    int* lab_s = cls_pos + 512;                                         // [512] the transcript
+    // The transcript and the lengths may live in mapped HOST memory (pgasr_host_*: a PCIe round trip per dependent
+    // access), so everything is fetched here in one go and the transcript is used from shared memory afterwards.
+    for (int i = threadIdx.x; i < a.Lmax; i += kThreads) lab_s[i] = a.targets[(size_t)b * a.Lmax + i];
     int Tb = a.in_len ? a.in_len[b] : T;
     Tb = min(max(Tb, 0), T);
     int L = a.tgt_len ? a.tgt_len[b] : a.Lmax;
     L = min(max(L, 0), a.Lmax);
     float* dlog_u = a.dlogits + (size_t)b * T * V;
-    float* nll_u = (a.nll ? a.nll : a.nll_ws) + b;
+    float* nll_u = a.nll_ws + b;
     PGASR_STAMP(b == 0 && threadIdx.x == 0, 0);
     for (int i = Tb * V + threadIdx.x; i < T * V; i += kThreads) dlog_u[i] = 0.0f;
     if (Tb == 0) {
         if (threadIdx.x == 0) *nll_u = L == 0 ? 0.0f : INFINITY;
     } else {
-        // [T][RS] between two guard rows: the walkers load the probabilities one frame ahead and run one row past
-        // either end (the guard values are loaded and never used)
-        double* tile = reinterpret_cast<double*>(smem_raw) + RS;
-        unsigned char* p = smem_raw + (size_t)(T + 2) * RS * 8;
-        GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
-        GradRing<SPL> ring_b = grad_ring_carve<SPL>(p, 6);                  p += grad_ring_bytes<SPL>();
-        int* gam_all = reinterpret_cast<int*>(p);                           // [2 G workers][kPer frames][16 SPL]
-        p += (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
-        int* cls_off = reinterpret_cast<int*>(p);                           // [V + 1]
-        int* cls_scr = cls_off + (V + 1);                                   // [V] counting-sort scratch
-        int* cls_pos = cls_scr + V;                                         // [Lmax]
         ring_a.dbg = ring_b.dbg = (b == 0);
         PGASR_STAMP(b == 0 && threadIdx.x == 0, 1);
         // softmax tile.  The raw logits are staged through the (not yet used) ring region with cp.async, then one
@@ -134,7 +139,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                 __syncthreads();
             }
         }
-        const int32_t* lab_u = a.targets + (size_t)b * a.Lmax;
+        const int32_t* lab_u = lab_s;                      // (published by the barriers of the tile loop above)
         if (warp == 0) ctc_build_class_lists(lab_u, L, V, cls_off, cls_pos, cls_scr);
         ring_a.cls_off = ring_b.cls_off = cls_off;
         ring_a.cls_pos = ring_b.cls_pos = cls_pos;
@@ -162,7 +167,10 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     __threadfence();                                       // rows and nll visible device-wide before the flag
     __syncthreads();
     PGASR_STAMP(b == 0 && threadIdx.x == 0, 3);
-    if (threadIdx.x == 0) st_release(a.ctrl + 4 + b, 1u);
+    if (threadIdx.x == 0) {
+        if (a.nll) a.nll[b] = *nll_u;                      // the caller's copy (possibly host memory); the loss reads nll_ws
+        st_release(a.ctrl + 4 + b, 1u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ PG role
@@ -203,6 +211,14 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
         for (int i = threadIdx.x; i < T * V; i += kThreads) cp_async4(ztile + i, lg + i);
     }
     cp_async_commit();
+    // the transcript may live in mapped host memory: fetch it now, it is needed after the sampling phase
+    const int32_t* ref = a.targets + (size_t)b * a.Lmax;
+    int ref_r[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int j = threadIdx.x + q * kThreads;
+        ref_r[q] = j < m ? ref[j] : -1;
+    }
     for (int i = threadIdx.x; i < kWarps * kFusedMaxK; i += kThreads) warp_acc[i] = 0.0f;
     for (int i = threadIdx.x; i < (V + 1) * W; i += kThreads) peq[i] = 0u;
     cp_async_wait<0>();
@@ -264,8 +280,13 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
 
     PGASR_STAMP(dbg, 32);
     // ---- P2: collapse (one warp per sample) and the match table of the transcript ---------------
-    const int32_t* ref = a.targets + (size_t)b * a.Lmax;
-    for (int j = threadIdx.x; j < m; j += kThreads) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int j = threadIdx.x + q * kThreads;
+        const uint32_t c = (uint32_t)ref_r[q];
+        if (j < m && c < (uint32_t)V) atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+    }
+    for (int j = threadIdx.x + 2 * kThreads; j < m; j += kThreads) {     // (Lmax > 2 * threads: never with Lmax <= 511)
         const uint32_t c = (uint32_t)ref[j];
         if (c < (uint32_t)V) atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
     }
@@ -423,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     __syncthreads();
     if (s_last && threadIdx.x < 32) {
         __threadfence();
-        const float* nl = a.nll ? a.nll : a.nll_ws;
+        const float* nl = a.nll_ws;
         float pg = 0.0f, ct = 0.0f;
         for (int b = threadIdx.x; b < a.B; b += 32) {
             if (a.do_pg) pg += __ldcg(a.loss_terms + b);
@@ -464,7 +485,7 @@ static size_t fused_smem(int T, int V, int K, int spl, int threads) {
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
     const int G = (threads / 32 - 2) / 2, per = (kBatch + G - 1) / G;
     const size_t ctc = (size_t)(T + 2) * RS * sizeof(double) + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) +
-                       (size_t)(2 * V + 1 + 512) * sizeof(int);
+                       (size_t)(2 * V + 1 + 512 + 512) * sizeof(int);
     const int Tp = (T + 15) & ~15, W = spl / 2;
     size_t pg = (((size_t)T * V * 4 + 15) & ~(size_t)15) + (size_t)2 * K * Tp + (size_t)(V + 1) * W * 4 + 16;
     pg += (size_t)(threads / 32) * kFusedMaxK * 4 + 3 * kFusedMaxK * 4 + 16;

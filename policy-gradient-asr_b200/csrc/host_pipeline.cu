@@ -3,13 +3,13 @@
 // model.py:317-320; criterion(model_out, t), model.py:235).  `depth` steps are in flight at once: the H2D copy of
 // step n+1 and the D2H copy of step n-1 run on their own streams (and copy engines) while step n's kernel runs.
 //
-//   copy-in stream : [small inputs H2D][logits H2D] -> ev_in[slot]
+//   copy-in stream : logits H2D -> ev_in[slot]
 //   compute stream : wait ev_in[slot] ; fused kernel -> ev_k[slot]
-//   copy-out stream: wait ev_k[slot] ; [small outputs D2H][dlogits D2H] -> ev_out[slot]
-// Small inputs (targets, lengths) and small outputs (loss, rewards, nll) are packed into one pinned staging
-// block per slot so that a step costs two copies per direction.  All H2D copies share one hardware copy engine
-// and all D2H copies the other whatever stream they are issued on (measured: extra streams did not help).
+//   copy-out stream: wait ev_k[slot] ; dlogits D2H -> ev_out[slot]
+// Small inputs (targets, lengths) and small outputs (loss, rewards, nll) are packed into one pinned, device-mapped
+// staging block per slot that the kernel accesses directly (zero copy): a step costs ONE DMA per direction.
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -31,7 +31,9 @@ struct pgasr_host_pipeline {
         long long ticket;                          // step occupying the slot (-1: free)
         bool collected;                            // small outputs already handed to the caller
         float* loss_h; float* rewards_h; float* nll_h;
+        cudaStream_t st; void* ws;                 // per-slot mode: the slot's own stream and step workspace
     }* slots;
+    bool per_slot;                                 // one in-order stream per slot instead of one stream per engine
     long long next_ticket;
     size_t small_in_bytes, small_out_floats;
 #ifdef PGASR_TIMING
@@ -50,11 +52,13 @@ void destroy(pgasr_host_pipeline* p) {
         for (int i = 0; i < p->depth; ++i) {
             auto& s = p->slots[i];
             if (s.ev_out) cudaEventSynchronize(s.ev_out);
-            cudaFree(s.logits_d); cudaFree(s.dlogits_d); cudaFree(s.small_in_d); cudaFree(s.small_out_d);
+            cudaFree(s.logits_d); cudaFree(s.dlogits_d);
             cudaFreeHost(s.small_in_h); cudaFreeHost(s.small_out_h);
             if (s.ev_in) cudaEventDestroy(s.ev_in);
             if (s.ev_k) cudaEventDestroy(s.ev_k);
             if (s.ev_out) cudaEventDestroy(s.ev_out);
+            if (s.st) cudaStreamDestroy(s.st);
+            cudaFree(s.ws);
         }
         delete[] p->slots;
     }
@@ -105,15 +109,25 @@ extern "C" int pgasr_host_create(int B, int T, int V, int K, int Lmax, int depth
     ok(cudaStreamCreateWithFlags(&p->s_k, cudaStreamNonBlocking));
     ok(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
     ok(cudaMalloc(&p->workspace, ws));
+    const char* mode = std::getenv("PGASR_HOST_PIPELINE");
+    p->per_slot = mode && std::strcmp(mode, "slot") == 0;
     for (int i = 0; i < depth && e == cudaSuccess; ++i) {
         auto& s = p->slots[i];
         s.ticket = -1;
         ok(cudaMalloc(&s.logits_d, nlog));
         ok(cudaMalloc(&s.dlogits_d, nlog));
-        ok(cudaMalloc(&s.small_in_d, p->small_in_bytes));
-        ok(cudaMalloc(&s.small_out_d, p->small_out_floats * sizeof(float)));
-        ok(cudaMallocHost(&s.small_in_h, p->small_in_bytes));
-        ok(cudaMallocHost(&s.small_out_h, p->small_out_floats * sizeof(float)));
+        if (p->per_slot) {
+            ok(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            ok(cudaMalloc(&s.ws, ws));
+            if (e == cudaSuccess && pgasr_pg_ctc_step_workspace_init(s.ws, ws, s.st) != PGASR_OK) e = cudaErrorUnknown;
+            ok(cudaStreamSynchronize(s.st));
+        }
+        ok(cudaHostAlloc(&s.small_in_h, p->small_in_bytes, cudaHostAllocMapped));
+        ok(cudaHostAlloc(&s.small_out_h, p->small_out_floats * sizeof(float), cudaHostAllocMapped));
+        if (e == cudaSuccess) {                        // device-side aliases of the two staging blocks
+            ok(cudaHostGetDevicePointer(reinterpret_cast<void**>(&s.small_in_d), s.small_in_h, 0));
+            ok(cudaHostGetDevicePointer(reinterpret_cast<void**>(&s.small_out_d), s.small_out_h, 0));
+        }
 #ifdef PGASR_TIMING
         ok(cudaEventCreate(&s.ev_in)); ok(cudaEventCreate(&s.ev_k)); ok(cudaEventCreate(&s.ev_out));
         ok(cudaEventCreate(&s.ev_h0)); ok(cudaEventCreate(&s.ev_k0)); ok(cudaEventCreate(&s.ev_o0));
@@ -173,31 +187,40 @@ extern "C" int pgasr_host_submit(pgasr_host_pipeline* p, const float* logits_h, 
     // No stream-side wait guards the slot's device buffers: collect() above has already blocked the HOST until the
     // D2H copies of the step that used this slot finished, and those were ordered after its kernel.  (Every
     // cross-stream wait is a semaphore on a copy-engine channel; the redundant ones cost engine time.)
+    cudaStream_t q_in = p->per_slot ? s.st : p->s_in, q_k = p->per_slot ? s.st : p->s_k, q_out = p->per_slot ? s.st : p->s_out;
+    void* wsp = p->per_slot ? s.ws : p->workspace;
 #ifdef PGASR_TIMING
-    PGASR_CUDA_TRY(cudaEventRecord(s.ev_h0, p->s_in));
+    PGASR_CUDA_TRY(cudaEventRecord(s.ev_h0, q_in));
 #endif
-    PGASR_CUDA_TRY(cudaMemcpyAsync(s.small_in_d, s.small_in_h, p->small_in_bytes, cudaMemcpyHostToDevice, p->s_in));
-    PGASR_CUDA_TRY(cudaMemcpyAsync(s.logits_d, logits_h, nlog, cudaMemcpyHostToDevice, p->s_in));
-    PGASR_CUDA_TRY(cudaEventRecord(s.ev_in, p->s_in));
-    PGASR_CUDA_TRY(cudaStreamWaitEvent(p->s_k, s.ev_in, 0));
+    PGASR_CUDA_TRY(cudaMemcpyAsync(s.logits_d, logits_h, nlog, cudaMemcpyHostToDevice, q_in));
+    if (!p->per_slot) {
+        PGASR_CUDA_TRY(cudaEventRecord(s.ev_in, q_in));
+        PGASR_CUDA_TRY(cudaStreamWaitEvent(q_k, s.ev_in, 0));
+    }
 #ifdef PGASR_TIMING
-    PGASR_CUDA_TRY(cudaEventRecord(s.ev_k0, p->s_k));
+    if (p->per_slot) PGASR_CUDA_TRY(cudaEventRecord(s.ev_in, q_in));
+    PGASR_CUDA_TRY(cudaEventRecord(s.ev_k0, q_k));
 #endif
+    // The small inputs and outputs are NOT copied: the kernel reads the transcripts and lengths from, and writes the
+    // loss / rewards / nll to, the slot's pinned staging block through its device mapping (zero copy).  A 26 KB DMA
+    // queued next to the 3.8 MB one cost ~15 us of copy-engine time per direction per step (measured,
+    // tools/interference_probe.py: 101 -> 131 us/step); the kernel-side cost is one PCIe round trip at CTA start.
     const int32_t* tg_d = reinterpret_cast<const int32_t*>(s.small_in_d);
     rc = pgasr_pg_ctc_step(s.logits_d, tg_d, tg_d + (size_t)B * Lmax, tg_d + (size_t)B * Lmax + B, nullptr, seed, B,
                            T, V, K, Lmax, blank, reward_mode, baseline_mode, baseline_value, w_pg, w_ctc,
                            s.small_out_d, s.dlogits_d, s.small_out_d + 4, nullptr, nullptr, nullptr,
-                           s.small_out_d + 4 + (size_t)B * K, nullptr, p->workspace, p->workspace_bytes, p->s_k);
+                           s.small_out_d + 4 + (size_t)B * K, nullptr, wsp, p->workspace_bytes, q_k);
     if (rc != PGASR_OK) return rc;
-    PGASR_CUDA_TRY(cudaEventRecord(s.ev_k, p->s_k));
-    PGASR_CUDA_TRY(cudaStreamWaitEvent(p->s_out, s.ev_k, 0));
+    if (!p->per_slot) {
+        PGASR_CUDA_TRY(cudaEventRecord(s.ev_k, q_k));
+        PGASR_CUDA_TRY(cudaStreamWaitEvent(q_out, s.ev_k, 0));
+    }
 #ifdef PGASR_TIMING
-    PGASR_CUDA_TRY(cudaEventRecord(s.ev_o0, p->s_out));
+    if (p->per_slot) PGASR_CUDA_TRY(cudaEventRecord(s.ev_k, q_k));
+    PGASR_CUDA_TRY(cudaEventRecord(s.ev_o0, q_out));
 #endif
-    PGASR_CUDA_TRY(cudaMemcpyAsync(s.small_out_h, s.small_out_d, p->small_out_floats * sizeof(float),
-                                   cudaMemcpyDeviceToHost, p->s_out));
-    PGASR_CUDA_TRY(cudaMemcpyAsync(dlogits_h, s.dlogits_d, nlog, cudaMemcpyDeviceToHost, p->s_out));
-    PGASR_CUDA_TRY(cudaEventRecord(s.ev_out, p->s_out));
+    PGASR_CUDA_TRY(cudaMemcpyAsync(dlogits_h, s.dlogits_d, nlog, cudaMemcpyDeviceToHost, q_out));
+    PGASR_CUDA_TRY(cudaEventRecord(s.ev_out, q_out));
     s.ticket = n;
     s.collected = false;
     s.loss_h = loss_h; s.rewards_h = rewards_h; s.nll_h = nll_h;
