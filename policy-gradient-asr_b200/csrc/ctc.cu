@@ -20,6 +20,7 @@
 // 2^52+2^51 magic constant, the blank column is summed with one integer redux.sync, label columns with integer
 // shared-memory atomics (exact, order independent => deterministic).
 #include "ctc_core.cuh"
+#include "fused_args.cuh"
 
 namespace pgasr {
 
@@ -107,11 +108,15 @@ static int launch_ctc(const float* logits, const float* probs, const int32_t* ta
 
 }  // namespace pgasr
 
+// one call runs either the single-launch kernel (CTC role only; its workspace + 256 B for its loss scalar) or the
+// classic kernel: the two layouts share the buffer
 extern "C" size_t pgasr_ctc_workspace_bytes(int B, int T, int V, int Lmax) {
     using namespace pgasr;
     const int spl = ctc_spl(Lmax);
     if (spl == 0 || B < 0 || T <= 0 || V <= 0) return 0;
-    return ctc_ws(B, T, V, spl).total;
+    const size_t fused = (fused_capability(T, V, 1, Lmax) & 1) ? align256(fused_workspace_bytes(B, T, V, 1, Lmax)) + 256 : 0;
+    const size_t classic = ctc_ws(B, T, V, spl).total;
+    return fused > classic ? fused : classic;
 }
 
 extern "C" int pgasr_ctc_loss_grad(const float* logits, const float* probs, const int32_t* targets,
@@ -125,10 +130,27 @@ extern "C" int pgasr_ctc_loss_grad(const float* logits, const float* probs, cons
     const int spl = ctc_spl(Lmax);
     if (spl == 0) return PGASR_ERR_UNSUPPORTED;
     const CtcWs w = ctc_ws(B, T, V, spl);
-    if (workspace_bytes < w.total) return PGASR_ERR_WORKSPACE;
+    if (workspace_bytes < pgasr_ctc_workspace_bytes(B, T, V, Lmax)) return PGASR_ERR_WORKSPACE;
     if (B == 0) return PGASR_OK;
-    char* base = reinterpret_cast<char*>(workspace);
     cudaStream_t st = as_stream(stream);
+    const bool fusable = logits && (fused_capability(T, V, 1, Lmax) & 1) && B + 4 <= 16384;
+    const size_t fused_bytes = (fused_capability(T, V, 1, Lmax) & 1) ? align256(fused_workspace_bytes(B, T, V, 1, Lmax)) + 256 : 0;
+    if (fusable && !accumulate) {
+        // the walker / gradient-worker kernel of the fused step, CTC role only (3x the classic kernel at T = 500);
+        // it takes the softmax from the logits itself (`probs` is only a shortcut for the classic kernel)
+        FusedArgs a;
+        a.logits = logits; a.targets = targets; a.in_len = in_len; a.tgt_len = tgt_len; a.uniforms = nullptr;
+        a.seed = 0; a.B = B; a.T = T; a.V = V; a.K = 1; a.Lmax = Lmax; a.blank = blank;
+        a.reward_mode = 0; a.baseline_mode = 1; a.baseline_value = 0.0f;
+        a.w_pg = 0.0f; a.w_ctc = grad_scale * (float)B;   // the kernel scales the rows by w_ctc / B
+        a.do_pg = 0; a.do_ctc = 1;
+        a.loss = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + fused_bytes - 256);
+        a.dlogits = dlogits; a.rewards = nullptr; a.logp = nullptr; a.hyp_len = nullptr; a.dist = nullptr;
+        a.nll = nll; a.samples = nullptr;
+        PGASR_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)(4 + B) * sizeof(unsigned), st));   // arm the control block
+        return fused_step(a, workspace, st);
+    }
+    char* base = reinterpret_cast<char*>(workspace);
     switch (spl) {
         case 4: return launch_ctc<4>(logits, probs, targets, in_len, tgt_len, B, T, V, Lmax, blank, grad_scale, accumulate, nll, dlogits, base, w, st);
         case 8: return launch_ctc<8>(logits, probs, targets, in_len, tgt_len, B, T, V, Lmax, blank, grad_scale, accumulate, nll, dlogits, base, w, st);

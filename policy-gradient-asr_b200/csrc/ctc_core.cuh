@@ -427,6 +427,13 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
     return v;
 }
 
+// volatile flavour for the streaming ring: ordered after the cp.async waits (volatile asm keeps its order)
+__device__ __forceinline__ double lds_f64_v(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // Recurrence warp of one direction over the whole utterance (tile mode).  G: workers of this direction.
 // Lattice / ring layout per frame: [SPL/2][32 lanes] double2, so each lane moves 16 bytes per access and a warp
 // access is one coalesced 512 B line.  The frame body is branch free and unrolled four times; every frame uses
@@ -441,7 +448,33 @@ struct CtcWalk {
     int rstride;
     bool edge;
     bool act;                     // this lane holds at least one state < S (lanes beyond never touch the lattice)
+    // global-tile mode (long utterances): the probability rows stream from global memory through a 32-row ring
+    unsigned ring_base, ring_mask;        // shared-memory address of the ring (aligned to its size), size - 1
+    const double* tile_g;                 // row 0 of this utterance's fp64 tile in global memory (guard rows around it)
+    int gstep, row_next, row_dir, row_lo, row_hi, RS, RSR;
 };
+
+constexpr int kPRows = 32;        // rows of the streaming ring
+constexpr int kPGroup = 8;        // rows per cp.async group
+
+// rows [first, first + kPGroup) in walking order -> ring slots (row & 31); one 16-byte cp.async per lane and piece
+template <int SPL, bool kAlpha>
+__device__ __forceinline__ void ctc_walk_issue_group(CtcWalk<SPL, kAlpha>& w, unsigned ring_generic_lo) {
+    (void)ring_generic_lo;
+    const int lane = threadIdx.x & 31;
+    const int per_row = w.RS / 2;                         // 16-byte pieces per row
+    for (int i = lane; i < kPGroup * per_row; i += 32) {
+        const int r = i / per_row, c = i - r * per_row;
+        int row = w.row_next + w.row_dir * r;
+        row = min(max(row, w.row_lo), w.row_hi);          // guard rows: loaded, never used
+        const unsigned dst = w.ring_base + (unsigned)(((row & (kPRows - 1)) * w.RSR + 2 * c) * 8);
+        const double* src = w.tile_g + (ptrdiff_t)row * w.RS + 2 * c;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+    }
+    cp_async_commit();
+    w.row_next += w.row_dir * kPGroup;
+}
+
 
 template <int SPL, bool kAlpha>
 __device__ __forceinline__ void ctc_walk_halo(CtcWalk<SPL, kAlpha>& w) {
@@ -474,19 +507,34 @@ __device__ __forceinline__ void ctc_walk_rescale(CtcWalk<SPL, kAlpha>& w) {
 
 // kFirst: store the pre-emission sums to the lattice (dst = global), else the post-emission values to the ring
 // (dst = shared).  dst advances by `dstride` double2 per frame; edst (exponent per frame) by estride ints.
-template <int SPL, bool kAlpha, bool kFirst>
+template <int SPL, bool kAlpha, bool kFirst, bool kGT = false>
 __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*& dst, ptrdiff_t dstride, int*& edst,
                                                int estride, bool lane0) {
+    if (kGT) {
+        // every 8 frames: the two groups about to be read are complete, the slot of the group just left is refilled
+        if ((w.gstep & (kPGroup - 1)) == 0) {
+            cp_async_wait<1>();
+            __syncwarp();
+            ctc_walk_issue_group<SPL, kAlpha>(w, 0u);
+        }
+        ++w.gstep;
+    }
     double p[SPL / 2];
     const double pb = w.pb_n;
 #pragma unroll
     for (int i = 0; i < SPL / 2; ++i) p[i] = w.p_n[i];
-    w.pb_n = lds_f64(w.pa_b);                             // next frame's values fly while this frame is computed
+    w.pb_n = kGT ? lds_f64_v(w.pa_b) : lds_f64(w.pa_b);   // next frame's values fly while this frame is computed
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) w.p_n[i] = lds_f64(w.pa[i]);
-    w.pa_b += w.rstride;
+    for (int i = 0; i < SPL / 2; ++i) w.p_n[i] = kGT ? lds_f64_v(w.pa[i]) : lds_f64(w.pa[i]);
+    if (kGT) {
+        w.pa_b = w.ring_base | ((w.pa_b + w.rstride) & w.ring_mask);
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) w.pa[i] += w.rstride;
+        for (int i = 0; i < SPL / 2; ++i) w.pa[i] = w.ring_base | ((w.pa[i] + w.rstride) & w.ring_mask);
+    } else {
+        w.pa_b += w.rstride;
+#pragma unroll
+        for (int i = 0; i < SPL / 2; ++i) w.pa[i] += w.rstride;
+    }
     ctc_presum<SPL, kAlpha>(w.st, w.h0, w.h1);
 #ifndef EXP_NO_LATSTORE
     if (kFirst) {
@@ -508,11 +556,14 @@ __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*
     edst += estride;
 }
 
-template <int SPL, int G, bool kAlpha, typename Barrier>
+// kGT: `tile` is row 0 of the utterance's tile in GLOBAL memory ([T] rows of RS doubles between two guard rows),
+// `pring` the 32-row shared-memory ring of this walker (aligned to its size, row stride RSR doubles).
+template <int SPL, int G, bool kAlpha, bool kGT = false, typename Barrier>
 __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t* __restrict__ lab_u, int Tb, int L,
                                               int V, int RS, int blank, float* __restrict__ nll_out,
                                               double* __restrict__ lat_u, int* __restrict__ exp_u,
-                                              GradRing<SPL> ring, Barrier mid_barrier) {
+                                              GradRing<SPL> ring, Barrier mid_barrier, double* pring = nullptr,
+                                              int RSR = 0, int T = 0) {
     constexpr int kGroup = 32 * (1 + G);                  // this warp + its workers
     const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;
@@ -528,17 +579,42 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
     PGASR_STAMP(dbg, kAlpha ? 10 : 14);
 
     const int t0 = kAlpha ? 0 : Tb - 1;
-    w.rstride = kAlpha ? RS * 8 : -RS * 8;
-    unsigned row0 = (unsigned)__cvta_generic_to_shared(tile) + (unsigned)(t0 * RS * 8);
+    unsigned row0;
+    if (kGT) {
+        w.tile_g = tile; w.RS = RS; w.RSR = RSR;
+        w.ring_base = (unsigned)__cvta_generic_to_shared(pring);
+        w.ring_mask = (unsigned)(kPRows * RSR * 8 - 1);
+        w.rstride = kAlpha ? RSR * 8 : -RSR * 8;
+        w.row_dir = kAlpha ? 1 : -1;
+        w.row_lo = -1; w.row_hi = T;
+        w.row_next = t0;
+        w.gstep = 0;
+        // three groups in flight, the first two complete before the first frame
+        ctc_walk_issue_group<SPL, kAlpha>(w, 0u);
+        ctc_walk_issue_group<SPL, kAlpha>(w, 0u);
+        ctc_walk_issue_group<SPL, kAlpha>(w, 0u);
+        cp_async_wait<1>();
+        __syncwarp();
+        row0 = w.ring_base + (unsigned)((t0 & (kPRows - 1)) * RSR * 8);
+    } else {
+        w.rstride = kAlpha ? RS * 8 : -RS * 8;
+        row0 = (unsigned)__cvta_generic_to_shared(tile) + (unsigned)(t0 * RS * 8);
+    }
     // every tile load below takes its address from this opaque copy, so none of them (plain asm, free to be
     // scheduled) can be moved above this point, i.e. above the barrier that published the tile
     asm volatile("mov.u32 %0, %0;\n" : "+r"(row0) : : "memory");
-    w.pb_n = lds_f64(row0 + (unsigned)(blank * 8));
-    w.pa_b = row0 + (unsigned)(blank * 8) + w.rstride;
+    w.pb_n = lds_f64_v(row0 + (unsigned)(blank * 8));
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) {
-        w.p_n[i] = lds_f64(row0 + (unsigned)(w.st.loff[i] * 8));
-        w.pa[i] = row0 + (unsigned)(w.st.loff[i] * 8) + w.rstride;
+    for (int i = 0; i < SPL / 2; ++i) w.p_n[i] = lds_f64_v(row0 + (unsigned)(w.st.loff[i] * 8));
+    if (kGT) {
+        w.pa_b = w.ring_base | ((row0 + (unsigned)(blank * 8) + w.rstride) & w.ring_mask);
+#pragma unroll
+        for (int i = 0; i < SPL / 2; ++i)
+            w.pa[i] = w.ring_base | ((row0 + (unsigned)(w.st.loff[i] * 8) + w.rstride) & w.ring_mask);
+    } else {
+        w.pa_b = row0 + (unsigned)(blank * 8) + w.rstride;
+#pragma unroll
+        for (int i = 0; i < SPL / 2; ++i) w.pa[i] = row0 + (unsigned)(w.st.loff[i] * 8) + w.rstride;
     }
     // virtual vector before the first frame: the recurrence turns it into the CTC start (alpha: states 0,1;
     // beta: states S-1,S-2) -- see DESIGN.md "CTC spec"
@@ -559,10 +635,10 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
         int step = 0;
         for (; step + 4 <= n_first; step += 4) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) ctc_walk_frame<SPL, kAlpha, true>(w, lp, lstride, ep, estride, lane0);
+            for (int u = 0; u < 4; ++u) ctc_walk_frame<SPL, kAlpha, true, kGT>(w, lp, lstride, ep, estride, lane0);
             if (step & 4) ctc_walk_rescale<SPL, kAlpha>(w);
         }
-        for (; step < n_first; ++step) ctc_walk_frame<SPL, kAlpha, true>(w, lp, lstride, ep, estride, lane0);
+        for (; step < n_first; ++step) ctc_walk_frame<SPL, kAlpha, true, kGT>(w, lp, lstride, ep, estride, lane0);
         ctc_walk_rescale<SPL, kAlpha>(w);
     }
     PGASR_STAMP(dbg, kAlpha ? 11 : 15);
@@ -578,14 +654,15 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
         const int nfr = min(kBatch, n2 - q);
         if (nfr == kBatch) {
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) ctc_walk_frame<SPL, kAlpha, false>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
+            for (int u = 0; u < kBatch; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
         } else {
-            for (int u = 0; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
+            for (int u = 0; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
         }
         named_bar_arrive(ring.bar_full + buf, kGroup);
         ctc_walk_rescale<SPL, kAlpha>(w);
     }
     PGASR_STAMP(dbg, kAlpha ? 13 : 17);
+    if (kGT) cp_async_wait<0>();                          // nothing of this warp may still be landing in the ring
 
     if (kAlpha) {
         double fin = 0.0;
@@ -612,12 +689,14 @@ struct CtcWorker {
     static constexpr int kPer = (kBatch + G - 1) / G;     // frames of a batch per worker (worker g: frames g, g+G, ..)
     double2 o[kPer][SPL / 2];
     int eo[kPer];
+    double prow[kPer];            // global-tile mode: p_t(lane) of the frame, fetched with the lattice row
 };
 
-template <int SPL, int G, bool kAlpha>
+template <int SPL, int G, bool kAlpha, bool kGT = false>
 __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, int nb, int g, int n_first, int n2,
                                                  int Tb, int S, const double* __restrict__ lat_u,
-                                                 const int* __restrict__ exp_u) {
+                                                 const int* __restrict__ exp_u, const double* tile = nullptr,
+                                                 int RS = 0) {
     const int lane = threadIdx.x & 31;
     const bool act = lane * SPL < S;                      // the other direction never stored the lanes beyond S
 #pragma unroll
@@ -634,6 +713,7 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
 #pragma unroll
         for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = act ? __ldcg(lp + jj * 32) : make_double2(0.0, 0.0);
         wk.eo[r] = __ldcg(exp_u + t);
+        if (kGT) wk.prow[r] = __ldcg(tile + (size_t)t * RS + lane);
 #endif
     }
 }
@@ -700,8 +780,9 @@ __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlph
 // phase B: gradient rows; lane v sums the label occupancies of class v.  cpos[] entries beyond the class's
 // count point at label slot 16*SPL-1, whose state 32*SPL-1 lies beyond S for every transcript (always 0), so the
 // gather is branch free; cmax (warp uniform) bounds the rare tail of classes with more than kClsRegs labels.
-template <int SPL, int G, bool kAlpha>
-__device__ __forceinline__ void ctc_worker_phase_b(const WorkerNorm& nm, int nb, int g, int n_first, int n2, int Tb,
+template <int SPL, int G, bool kAlpha, bool kGT = false>
+__device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlpha>& wk, const double (&prow)[(kBatch + G - 1) / G],
+                                                   const WorkerNorm& nm, int nb, int g, int n_first, int n2, int Tb,
                                                    const double* tile, int V, int RS, int blank, float grad_scale,
                                                    float* __restrict__ dlog_u, const GradRing<SPL>& ring,
                                                    const int* gam, const int (&gb)[(kBatch + G - 1) / G], int ccnt, int cmax,
@@ -734,7 +815,8 @@ __device__ __forceinline__ void ctc_worker_phase_b(const WorkerNorm& nm, int nb,
                     occ += i < ccnt ? gr[ring.cls_pos[ring.cls_off[lane] + i]] : 0;
 #endif
                 occ = lane == blank ? gb[r] : occ;
-                const int pfix = __double2loint(fma(row[min(lane, RS - 1)], kCtcFix, kCtcMagic));
+                const double pv = kGT ? prow[r] : row[min(lane, RS - 1)];
+                const int pfix = __double2loint(fma(pv, kCtcFix, kCtcMagic));
                 const float gval = nm.dead ? 0.0f : grad_scale * ((float)(pfix - occ) * kCtcUnfix);
                 if (lane < V) out[lane] = gval;
             } else {
@@ -752,7 +834,7 @@ __device__ __forceinline__ void ctc_worker_phase_b(const WorkerNorm& nm, int nb,
     __syncwarp();
 }
 
-template <int SPL, int G, bool kAlpha, typename Barrier>
+template <int SPL, int G, bool kAlpha, bool kGT = false, typename Barrier>
 __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const int32_t* __restrict__ lab_u, int Tb,
                                                 int L, int V, int RS, int blank, float grad_scale,
                                                 float* __restrict__ dlog_u, const double* __restrict__ lat_u,
@@ -779,7 +861,8 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
     CtcWorker<SPL, G, kAlpha> wk;
     int gb[kPer];
     const int S = 2 * L + 1;
-    if (nbatch > 0) ctc_worker_fetch<SPL, G, kAlpha>(wk, 0, g, n_first, n2, Tb, S, lat_u, exp_u);
+    double prow[kPer];
+    if (nbatch > 0) ctc_worker_fetch<SPL, G, kAlpha, kGT>(wk, 0, g, n_first, n2, Tb, S, lat_u, exp_u, tile, RS);
     for (int nb = 0; nb < nbatch; ++nb) {
         const int buf = nb & 1;
 #ifdef PGASR_TIMING
@@ -796,9 +879,13 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
         const long long w2 = clock64();
         nm.tA += w2 - w1;
 #endif
-        if (nb + 1 < nbatch) ctc_worker_fetch<SPL, G, kAlpha>(wk, nb + 1, g, n_first, n2, Tb, S, lat_u, exp_u);
-        ctc_worker_phase_b<SPL, G, kAlpha>(nm, nb, g, n_first, n2, Tb, tile, V, RS, blank, grad_scale, dlog_u, ring,
-                                           gam, gb, ccnt, cmax, cpos);
+        if (kGT) {                                        // keep this batch's p_t(lane) before the registers are refilled
+#pragma unroll
+            for (int r = 0; r < kPer; ++r) prow[r] = wk.prow[r];
+        }
+        if (nb + 1 < nbatch) ctc_worker_fetch<SPL, G, kAlpha, kGT>(wk, nb + 1, g, n_first, n2, Tb, S, lat_u, exp_u, tile, RS);
+        ctc_worker_phase_b<SPL, G, kAlpha, kGT>(wk, prow, nm, nb, g, n_first, n2, Tb, tile, V, RS, blank, grad_scale,
+                                                dlog_u, ring, gam, gb, ccnt, cmax, cpos);
 #ifdef PGASR_TIMING
         nm.tB += clock64() - w2;
 #endif

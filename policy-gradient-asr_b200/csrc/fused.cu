@@ -15,21 +15,11 @@
 // dlogits is written once by the CTC role and updated once by the PG role; every sum is order independent or
 // fixed-order, so the step is bit-reproducible run to run.
 #include "ctc_core.cuh"
+#include "fused_args.cuh"
 #include "myers_core.cuh"
 
 namespace pgasr {
 
-struct FusedArgs {
-    const float* logits; const int32_t* targets; const int32_t* in_len; const int32_t* tgt_len;
-    const float* uniforms; unsigned long long seed;
-    int B, T, V, K, Lmax, blank, reward_mode, baseline_mode;
-    float baseline_value, w_pg, w_ctc;
-    int do_pg, do_ctc;
-    float* loss; float* dlogits;
-    float* rewards; float* logp; int32_t* hyp_len; int32_t* dist; float* nll; uint8_t* samples;   // optional
-    unsigned* ctrl;          // [0] role ticket, [1] done ticket, [4 + b] CTC-done flag of utterance b
-    double* lattice; int* lat_exp; float* loss_terms; float* nll_ws;
-};
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
@@ -45,7 +35,10 @@ constexpr int kFusedMaxK = 64;
 // ------------------------------------------------------------------------------------------------ CTC role
 // warp 0: alpha recurrence, warp 1: beta recurrence; every other warp is a gradient worker, even warps on the
 // alpha side, odd warps on the beta side (G = (warps - 2) / 2 per direction).
-template <int SPL, int kThreads>
+// kGT (long utterances): the fp64 softmax tile does not fit in shared memory; it is written to the global
+// workspace instead, the walkers stream it back through 32-row cp.async rings and the workers fetch their
+// p_t(lane) with the lattice row.  Shared memory then no longer depends on T.
+template <int SPL, int kThreads, bool kGT>
 __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw) {
     constexpr int G = (kThreads / 32 - 2) / 2;             // gradient workers per direction
     constexpr int kPer = (kBatch + G - 1) / G;             // frames of a batch per worker
@@ -56,8 +49,25 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     // shared-memory carve-up (see fused_smem)
     // [T][RS] between two guard rows: the walkers load the probabilities one frame ahead and run one row past
     // either end (the guard values are loaded and never used)
-    double* tile = reinterpret_cast<double*>(smem_raw) + RS;
-    unsigned char* p = smem_raw + (size_t)(T + 2) * RS * 8;
+    const int RSR = RS <= 32 ? 32 : 64;                                  // ring row stride (power of two)
+    const size_t pring_bytes = (size_t)kPRows * RSR * 8;
+    double* tile;
+    double* pring_a = nullptr;
+    double* pring_b = nullptr;
+    unsigned char* p;
+    if (kGT) {
+        tile = a.tile_g + ((size_t)b * (T + 2) + 1) * RS;
+        // the dynamic shared memory window is 1 KB aligned at least; align the rings to their size by address
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw);
+        const unsigned pad = (unsigned)((pring_bytes - (base & (pring_bytes - 1))) & (pring_bytes - 1));
+        pring_a = reinterpret_cast<double*>(smem_raw + pad);
+        pring_b = reinterpret_cast<double*>(smem_raw + pad + pring_bytes);
+        p = smem_raw + pad + 2 * pring_bytes;
+    } else {
+        tile = reinterpret_cast<double*>(smem_raw) + RS;
+        p = smem_raw + (size_t)(T + 2) * RS * 8;
+    }
+    unsigned char* const stage_base = p;
     GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
     GradRing<SPL> ring_b = grad_ring_carve<SPL>(p, 6);                  p += grad_ring_bytes<SPL>();
     int* gam_all = reinterpret_cast<int*>(p);                           // [2 G workers][kPer frames][16 SPL]
@@ -88,7 +98,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         // writes (row stride RS doubles) collide on a shared-memory bank.
         const float* lg = a.logits + (size_t)b * T * V;
         {
-            float* stage = reinterpret_cast<float*>(smem_raw + (size_t)(T + 2) * RS * 8);
+            float* stage = reinterpret_cast<float*>(stage_base);
             const size_t stage_bytes = 2 * grad_ring_bytes<SPL>() + (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
             const int chunk = (int)(stage_bytes / ((size_t)V * 4)) & ~3;
             const bool al16 = (((size_t)T * V * 4) & 15) == 0;
@@ -136,6 +146,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                     }
                     for (int idx = 32; idx < RS; ++idx) orow[idx] = 0.0;
                 }
+                if (kGT) __threadfence_block();            // the rows go to global memory: order them before the barrier
                 __syncthreads();
             }
         }
@@ -154,15 +165,17 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         };
         const int g = (warp - 2) >> 1;
         if (warp == 0)
-            ctc_walk_tile<SPL, G, true>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid);
+            ctc_walk_tile<SPL, G, true, kGT>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid, pring_a,
+                                             RSR, T);
         else if (warp == 1)
-            ctc_walk_tile<SPL, G, false>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_b, mid);
+            ctc_walk_tile<SPL, G, false, kGT>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_b, mid,
+                                              pring_b, RSR, T);
         else if (g < G && !(warp & 1))
-            ctc_grad_worker<SPL, G, true>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_a,
-                                          gam_all + g * kPer * 16 * SPL, mid);
+            ctc_grad_worker<SPL, G, true, kGT>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_a,
+                                               gam_all + g * kPer * 16 * SPL, mid);
         else if (g < G)
-            ctc_grad_worker<SPL, G, false>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_b,
-                                           gam_all + (G + g) * kPer * 16 * SPL, mid);
+            ctc_grad_worker<SPL, G, false, kGT>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_b,
+                                                gam_all + (G + g) * kPer * 16 * SPL, mid);
     }
     __threadfence();                                       // rows and nll visible device-wide before the flag
     __syncthreads();
@@ -420,7 +433,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #endif
 
-template <int SPL, int kThreads>
+template <int SPL, int kThreads, bool kGT>
 __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_ticket, s_last;
@@ -431,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     __syncthreads();
     const unsigned ticket = s_ticket;
     const unsigned n_ctc = a.do_ctc ? (unsigned)a.B : 0u;
-    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads>(a, (int)ticket, smem_raw);
+    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT>(a, (int)ticket, smem_raw);
     else fused_pg_role<SPL / 2, kThreads>(a, (int)(ticket - n_ctc), smem_raw);
 
 #ifdef PGASR_TIMING
@@ -467,70 +480,104 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
 #endif
 }
 
-struct FusedWs { size_t ctrl, lat, exps, terms, nll, total; };
+constexpr size_t kFusedSmemLimit = 220 * 1024;
 
-static FusedWs fused_ws(int B, int T, int spl) {
+struct FusedWs { size_t ctrl, lat, exps, terms, nll, tile, total; };
+
+static FusedWs fused_ws(int B, int T, int V, int spl, bool gt) {
     FusedWs w;
     w.ctrl = align_up((size_t)(4 + B) * sizeof(unsigned), 256);
     w.lat = align_up((size_t)B * T * spl * 32 * sizeof(double), 256);
     w.exps = align_up((size_t)B * T * sizeof(int), 256);
     w.terms = align_up((size_t)B * sizeof(float), 256);
     w.nll = align_up((size_t)B * sizeof(float), 256);
-    w.total = w.ctrl + w.lat + w.exps + w.terms + w.nll;
+    w.tile = gt ? align_up((size_t)B * (T + 2) * ctc_row_stride(V) * sizeof(double), 256) : 0;
+    w.total = w.ctrl + w.lat + w.exps + w.terms + w.nll + w.tile;
     return w;
 }
 
-static size_t fused_smem(int T, int V, int K, int spl, int threads) {
+static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
     const int RS = ctc_row_stride(V);
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
     const int G = (threads / 32 - 2) / 2, per = (kBatch + G - 1) / G;
-    const size_t ctc = (size_t)(T + 2) * RS * sizeof(double) + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) +
-                       (size_t)(2 * V + 1 + 512 + 512) * sizeof(int);
+    const size_t pring = (size_t)kPRows * (RS <= 32 ? 32 : 64) * 8;
+    const size_t tile = gt ? 3 * pring /* two rings + alignment slack */ : (size_t)(T + 2) * RS * sizeof(double);
+    return tile + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int);
+}
+
+static size_t pg_role_smem(int T, int V, int K, int spl, int threads) {
     const int Tp = (T + 15) & ~15, W = spl / 2;
     size_t pg = (((size_t)T * V * 4 + 15) & ~(size_t)15) + (size_t)2 * K * Tp + (size_t)(V + 1) * W * 4 + 16;
     pg += (size_t)(threads / 32) * kFusedMaxK * 4 + 3 * kFusedMaxK * 4 + 16;
-    return ctc > pg ? ctc : pg;
+    return pg;
 }
 
-// 0 when the fused kernel cannot take this shape (the caller then chains the stand-alone kernels)
+// What the single-launch kernel can take for this shape.
+struct FusedPlan { int spl, threads; bool ctc_ok, gt, pg_ok; };
+
+static FusedPlan fused_plan(int T, int V, int K, int Lmax) {
+    FusedPlan pl;
+    pl.spl = ctc_spl(Lmax);
+    pl.threads = 512;
+    pl.ctc_ok = pl.gt = pl.pg_ok = false;
+    if (pl.spl == 0 || pl.spl == 32 || V > 32 || K > kFusedMaxK) return pl;   // SPL 32: the hand-off rings alone exceed an SM
+    if (ctc_role_smem(T, V, pl.spl, pl.threads, false) <= kFusedSmemLimit) {
+        pl.ctc_ok = true;
+    } else if (ctc_role_smem(T, V, pl.spl, pl.threads, true) <= kFusedSmemLimit) {
+        pl.ctc_ok = pl.gt = true;
+    }
+    pl.pg_ok = pl.ctc_ok && pg_role_smem(T, V, K, pl.spl, pl.threads) <= kFusedSmemLimit;
+    return pl;
+}
+
+// bit 0: the CTC role fits (tile in shared memory or streamed from the workspace), bit 1: the PG role fits too
+int fused_capability(int T, int V, int K, int Lmax) {
+    const FusedPlan pl = fused_plan(T, V, K, Lmax);
+    return (pl.ctc_ok ? 1 : 0) | (pl.pg_ok ? 2 : 0);
+}
+
+// 0 when the fused kernel cannot take this shape at all (the caller then chains the stand-alone kernels)
 size_t fused_workspace_bytes(int B, int T, int V, int K, int Lmax) {
-    const int spl = ctc_spl(Lmax);
-    if (spl == 0 || V > 32 || K > kFusedMaxK) return 0;
-    const int threads = spl <= 8 ? 512 : 256;
-    if (fused_smem(T, V, K, spl, threads) > 220 * 1024) return 0;
-    return fused_ws(B, T, spl).total;
+    const FusedPlan pl = fused_plan(T, V, K, Lmax);
+    if (!pl.ctc_ok) return 0;
+    return fused_ws(B, T, V, pl.spl, pl.gt).total;
 }
 
-template <int SPL, int kThreads>
+template <int SPL, int kThreads, bool kGT>
 static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
     static thread_local size_t smem_set = 0;               // the opt-in is sticky: raise it only when a larger tile comes
     if (smem > smem_set) {
-        PGASR_CUDA_TRY(cudaFuncSetAttribute(pg_ctc_fused_kernel<SPL, kThreads>,
+        PGASR_CUDA_TRY(cudaFuncSetAttribute(pg_ctc_fused_kernel<SPL, kThreads, kGT>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     const int grid = (a.do_ctc ? a.B : 0) + (a.do_pg ? a.B : 0);
-    pg_ctc_fused_kernel<SPL, kThreads><<<grid, kThreads, smem, st>>>(a);
+    pg_ctc_fused_kernel<SPL, kThreads, kGT><<<grid, kThreads, smem, st>>>(a);
     PGASR_LAUNCH_CHECK();
     return PGASR_OK;
 }
 
+// a.do_pg must be 0 when the PG role does not fit (fused_capability bit 1)
 int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
-    const int spl = ctc_spl(a.Lmax);
-    const int threads = spl <= 8 ? 512 : 256;
-    const FusedWs w = fused_ws(a.B, a.T, spl);
+    const FusedPlan pl = fused_plan(a.T, a.V, a.K, a.Lmax);
+    if (!pl.ctc_ok || (a.do_pg && !pl.pg_ok)) return PGASR_ERR_UNSUPPORTED;
+    const FusedWs w = fused_ws(a.B, a.T, a.V, pl.spl, pl.gt);
     char* p = reinterpret_cast<char*>(workspace);
     a.ctrl = reinterpret_cast<unsigned*>(p);             p += w.ctrl;
     a.lattice = reinterpret_cast<double*>(p);            p += w.lat;
     a.lat_exp = reinterpret_cast<int*>(p);               p += w.exps;
     a.loss_terms = reinterpret_cast<float*>(p);          p += w.terms;
-    a.nll_ws = reinterpret_cast<float*>(p);
-    const size_t smem = fused_smem(a.T, a.V, a.K, spl, threads);
-    switch (spl) {
-        case 4: return launch_fused<4, 512>(a, smem, st);
-        case 8: return launch_fused<8, 512>(a, smem, st);
-        case 16: return launch_fused<16, 256>(a, smem, st);
-        default: return launch_fused<32, 256>(a, smem, st);
+    a.nll_ws = reinterpret_cast<float*>(p);              p += w.nll;
+    a.tile_g = pl.gt ? reinterpret_cast<double*>(p) : nullptr;
+    size_t smem = a.do_ctc ? ctc_role_smem(a.T, a.V, pl.spl, pl.threads, pl.gt) : 0;
+    if (a.do_pg) smem = smem > pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads) ? smem : pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads);
+    switch (pl.spl * 2 + (pl.gt ? 1 : 0)) {
+        case 8: return launch_fused<4, 512, false>(a, smem, st);
+        case 9: return launch_fused<4, 512, true>(a, smem, st);
+        case 16: return launch_fused<8, 512, false>(a, smem, st);
+        case 17: return launch_fused<8, 512, true>(a, smem, st);
+        case 32: return launch_fused<16, 512, false>(a, smem, st);
+        default: return launch_fused<16, 512, true>(a, smem, st);
     }
 }
 

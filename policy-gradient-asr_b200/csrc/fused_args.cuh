@@ -1,0 +1,29 @@
+// Arguments of the single-launch kernel (fused.cu) and the host-side entry points other translation units call.
+#pragma once
+#include "pgasr_common.cuh"
+
+namespace pgasr {
+
+struct FusedArgs {
+    const float* logits; const int32_t* targets; const int32_t* in_len; const int32_t* tgt_len;
+    const float* uniforms; unsigned long long seed;
+    int B, T, V, K, Lmax, blank, reward_mode, baseline_mode;
+    float baseline_value, w_pg, w_ctc;
+    int do_pg, do_ctc;
+    float* loss; float* dlogits;
+    float* rewards; float* logp; int32_t* hyp_len; int32_t* dist; float* nll; uint8_t* samples;   // optional
+    unsigned* ctrl;          // [0] role ticket, [1] done ticket, [4 + b] CTC-done flag of utterance b
+    double* lattice; int* lat_exp; float* loss_terms; float* nll_ws;
+    double* tile_g;          // global-tile mode: [B][T + 2][RS] fp64 softmax rows (guard row before and after)
+};
+
+// bit 0: the CTC role fits (tile in shared memory or streamed from the workspace), bit 1: the PG role fits too
+int fused_capability(int T, int V, int K, int Lmax);
+// 0 when the fused kernel cannot take this shape at all
+size_t fused_workspace_bytes(int B, int T, int V, int K, int Lmax);
+// a.do_pg must be 0 when the PG role does not fit; the control block at the start of `workspace` must be zero
+// (armed once: the kernel re-arms it when it finishes)
+int fused_step(FusedArgs& a, void* workspace, cudaStream_t st);
+size_t align256(size_t x);
+
+}  // namespace pgasr

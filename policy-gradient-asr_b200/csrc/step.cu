@@ -1,26 +1,15 @@
 // The whole loss step behind one C-ABI call (upstream call site: criterion(model_out, t) followed by
 // loss.backward(), model.py:235-237), plus the small ABI utilities.
-#include "pgasr_common.cuh"
+#include "fused_args.cuh"
 
 namespace pgasr {
 
-struct FusedArgs {          // must match fused.cu
-    const float* logits; const int32_t* targets; const int32_t* in_len; const int32_t* tgt_len;
-    const float* uniforms; unsigned long long seed;
-    int B, T, V, K, Lmax, blank, reward_mode, baseline_mode;
-    float baseline_value, w_pg, w_ctc;
-    int do_pg, do_ctc;
-    float* loss; float* dlogits;
-    float* rewards; float* logp; int32_t* hyp_len; int32_t* dist; float* nll; uint8_t* samples;
-    unsigned* ctrl; double* lattice; int* lat_exp; float* loss_terms; float* nll_ws;
-};
-size_t fused_workspace_bytes(int B, int T, int V, int K, int Lmax);
-int fused_step(FusedArgs& a, void* workspace, cudaStream_t st);
+
 
 thread_local int g_last_cuda_error = 0;
 thread_local unsigned long long g_launches = 0;
 
-static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct StepWorkspace {
     uint8_t* samples; uint8_t* hyps;
@@ -45,7 +34,8 @@ static StepWorkspace carve(void* base, int B, int T, int V, int K, int Lmax) {
     w.loss_terms = reinterpret_cast<float*>(take((size_t)B * 4));
     w.nll = reinterpret_cast<float*>(take((size_t)B * 4));
     w.probs = reinterpret_cast<float*>(take((size_t)B * T * V * 4));
-    w.ctc_bytes = pgasr_ctc_workspace_bytes(B, T, V, Lmax);
+    // the classic CTC kernel is only chained when the single-launch kernel cannot take the shape
+    w.ctc_bytes = (fused_capability(T, V, K, Lmax) & 1) ? 256 : pgasr_ctc_workspace_bytes(B, T, V, Lmax);
     w.ctc = take(w.ctc_bytes);
     w.total = off;
     return w;
@@ -100,12 +90,13 @@ extern "C" int pgasr_device_check(void) {
     return major == 10 ? PGASR_OK : PGASR_ERR_NO_DEVICE;
 }
 
+// layout: [fused-kernel workspace (control block first)][scratch of the stand-alone kernels]
 extern "C" size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax) {
     if (B < 0 || T <= 0 || V <= 0 || K <= 0 || Lmax <= 0) return 0;
-    const size_t fused = pgasr::fused_workspace_bytes(B, T, V, K, Lmax);
+    const size_t fused = pgasr::align256(pgasr::fused_workspace_bytes(B, T, V, K, Lmax));
     const pgasr::StepWorkspace w = pgasr::carve(nullptr, B, T, V, K, Lmax);
     if (w.ctc_bytes == 0) return 0;
-    return fused > w.total ? fused : w.total;
+    return fused + w.total;
 }
 
 extern "C" int pgasr_pg_ctc_step_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
@@ -129,18 +120,23 @@ extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, co
     if (K > 64 || V > 32) return PGASR_ERR_UNSUPPORTED;
     if (workspace_bytes < pgasr_pg_ctc_step_workspace_bytes(B, T, V, K, Lmax)) return PGASR_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
-    if ((w_pg != 0.0f || w_ctc != 0.0f) && B + 4 <= 16384 && fused_workspace_bytes(B, T, V, K, Lmax) > 0) {
+    const bool do_pg = w_pg != 0.0f, do_ctc = w_ctc != 0.0f;
+    const int cap = B + 4 <= 16384 ? fused_capability(T, V, K, Lmax) : 0;
+    FusedArgs a;
+    a.logits = logits; a.targets = targets; a.in_len = in_len; a.tgt_len = tgt_len; a.uniforms = uniforms;
+    a.seed = seed; a.B = B; a.T = T; a.V = V; a.K = K; a.Lmax = Lmax; a.blank = blank;
+    a.reward_mode = reward_mode; a.baseline_mode = baseline_mode; a.baseline_value = baseline_value;
+    a.w_pg = w_pg; a.w_ctc = w_ctc; a.do_pg = do_pg; a.do_ctc = do_ctc;
+    a.loss = loss; a.dlogits = dlogits; a.rewards = rewards; a.logp = logp; a.hyp_len = hyp_len; a.dist = dist;
+    a.nll = nll; a.samples = samples;
+    if ((do_pg || do_ctc) && (cap & 1) && (!do_pg || (cap & 2))) {
         // one launch: heterogeneous CTAs (CTC role / PG role per utterance), see fused.cu
-        FusedArgs a;
-        a.logits = logits; a.targets = targets; a.in_len = in_len; a.tgt_len = tgt_len; a.uniforms = uniforms;
-        a.seed = seed; a.B = B; a.T = T; a.V = V; a.K = K; a.Lmax = Lmax; a.blank = blank;
-        a.reward_mode = reward_mode; a.baseline_mode = baseline_mode; a.baseline_value = baseline_value;
-        a.w_pg = w_pg; a.w_ctc = w_ctc; a.do_pg = w_pg != 0.0f; a.do_ctc = w_ctc != 0.0f;
-        a.loss = loss; a.dlogits = dlogits; a.rewards = rewards; a.logp = logp; a.hyp_len = hyp_len; a.dist = dist;
-        a.nll = nll; a.samples = samples;
         return fused_step(a, workspace, st);
     }
-    StepWorkspace w = carve(workspace, B, T, V, K, Lmax);
+    // long utterances: the PG role's tiles do not fit one SM -- the PG part runs as the chain of stand-alone
+    // kernels, the CTC part still as the single-launch kernel (tile streamed from the workspace) when it fits
+    const size_t fused_bytes = align256(fused_workspace_bytes(B, T, V, K, Lmax));
+    StepWorkspace w = carve(reinterpret_cast<char*>(workspace) + fused_bytes, B, T, V, K, Lmax);
     if (w.ctc_bytes == 0) return PGASR_ERR_UNSUPPORTED;
     uint8_t* smp = samples ? samples : w.samples;
     float* lp = logp ? logp : w.logp;
@@ -148,7 +144,6 @@ extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, co
     int32_t* ds = dist ? dist : w.dist;
     float* rw = rewards ? rewards : w.rewards;
     float* nl = nll ? nll : w.nll;
-    const bool do_pg = w_pg != 0.0f, do_ctc = w_ctc != 0.0f;
     const bool dense = baseline_mode != PGASR_BASELINE_MEAN;   // sum_k A_k == 0 under the per-utterance mean
     int rc;
     if (do_pg || do_ctc) {
@@ -165,7 +160,12 @@ extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, co
                                  w.adv, w.loss_terms, stream);
         if (rc) return rc;
     }
-    if (do_ctc) {
+    if (do_ctc && (cap & 1)) {
+        a.do_pg = 0; a.rewards = nullptr; a.logp = nullptr; a.hyp_len = nullptr; a.dist = nullptr; a.samples = nullptr;
+        a.nll = nl;
+        rc = fused_step(a, workspace, st);                 // dlogits = (w_ctc / B) g_ctc, nll; loss is finalised below
+        if (rc) return rc;
+    } else if (do_ctc) {
         rc = pgasr_ctc_loss_grad(logits, w.probs, targets, in_len, tgt_len, B, T, V, Lmax, blank,
                                  w_ctc / (float)B, 0, nl, dlogits, w.ctc, w.ctc_bytes, stream);
         if (rc) return rc;

@@ -70,7 +70,7 @@ def test_workspace_queries_are_pure():
     assert L.pgasr_ctc_workspace_bytes(64, 500, 30, 100) >= 64 * 500 * 201 * 8
     assert L.pgasr_ctc_workspace_bytes(1, 10, 5, 600) == 0          # Lmax over the documented limit
     a = L.pgasr_pg_ctc_step_workspace_bytes(64, 500, 30, 16, 100)
-    assert a > L.pgasr_ctc_workspace_bytes(64, 500, 30, 100)
+    assert a >= 64 * 500 * 256 * 8                                   # the fp64 half-lattice of the fused kernel
     assert L.pgasr_pg_ctc_step_workspace_bytes(0 - 1, 500, 30, 16, 100) == 0
 
 
