@@ -738,39 +738,58 @@ __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlph
         if (g + r * G < kBatch && q < n2) {
             const int slot = q % (2 * kBatch);
             const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 32)) + lane;
+            // Occupancy of state s in 2^-30 fixed point = a(s) o(s) c with c = invZ0 2^(E + eo - E0).  The product
+            // a(s) o(s) alone can underflow fp64 although both factors and the final value are in range (alpha and
+            // beta peak far apart when T >> L with diffuse posteriors), so the power of two is split between the
+            // two factors before they are multiplied: (a 2^h1) (o invZ0 2^h2), h1 + h2 = E + eo - E0.
+            double2 av[SPL / 2];
+#pragma unroll
+            for (int jj = 0; jj < SPL / 2; ++jj) av[jj] = sp[jj * 32];
+            const int E = ring.eslot[slot];
+            if (!nm.have) {                               // this worker's first frame: fix the normalisation
+                int emax = -1;                            // largest exponent-field sum of a product with both factors > 0
+#pragma unroll
+                for (int jj = 0; jj < SPL / 2; ++jj) {
+                    const int ax = (__double2hiint(av[jj].x) >> 20) & 0x7ff, ox = (__double2hiint(wk.o[r][jj].x) >> 20) & 0x7ff;
+                    const int ay = (__double2hiint(av[jj].y) >> 20) & 0x7ff, oy = (__double2hiint(wk.o[r][jj].y) >> 20) & 0x7ff;
+                    if (ax && ox) emax = max(emax, ax + ox);
+                    if (ay && oy) emax = max(emax, ay + oy);
+                }
+                emax = __reduce_max_sync(kFull, emax);
+                nm.dead = emax < 0;
+                const int ex0 = nm.dead ? 0 : 2046 - emax;            // brings the largest product to about 2^0
+                const double s1 = pow2i(ex0 >> 1), s2 = pow2i(ex0 - (ex0 >> 1));
+                double z = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < SPL / 2; ++jj)
+                    z += (av[jj].x * s1) * (wk.o[r][jj].x * s2) + (av[jj].y * s1) * (wk.o[r][jj].y * s2);
+                const double Z0 = warp_sum(z);
+                nm.dead = nm.dead || !(Z0 > 0.0);
+                nm.invZ0 = nm.dead ? 0.0 : kCtcFix / Z0;
+                nm.E0 = E + wk.eo[r] - ex0;
+                nm.have = true;
+            }
+            const int ex = E + wk.eo[r] - nm.E0;
+            const int h1 = (ex >> 1) - 15;                // invZ0 <= 2^30 rides on the smaller half
+            const double s1 = nm.invZ0 * pow2i(h1), s2 = pow2i(ex - h1);
             double wv[SPL];
             double zb = 0.0;
 #pragma unroll
             for (int jj = 0; jj < SPL / 2; ++jj) {
-                const double2 av = sp[jj * 32];
-                wv[2 * jj] = av.x * wk.o[r][jj].x;
-                wv[2 * jj + 1] = av.y * wk.o[r][jj].y;
+                wv[2 * jj] = (av[jj].x * s1) * (wk.o[r][jj].x * s2);
+                wv[2 * jj + 1] = (av[jj].y * s1) * (wk.o[r][jj].y * s2);
                 zb += wv[2 * jj];
             }
-            const int E = ring.eslot[slot];
-            if (!nm.have) {                               // this worker's first frame: measure Z0 = P / 2^(E+eo)
-                double zl = 0.0;
-#pragma unroll
-                for (int j = 1; j < SPL; j += 2) zl += wv[j];
-                const double Z0 = warp_sum(zb + zl);
-                nm.dead = !(Z0 > 0.0);
-                nm.invZ0 = nm.dead ? 0.0 : kCtcFix / Z0;
-                nm.E0 = E + wk.eo[r];
-                nm.have = true;
-            }
-            const double c = nm.invZ0 * pow2i(E + wk.eo[r] - nm.E0);
-            gb[r] = __reduce_add_sync(kFull, __double2loint(fma(zb, c, kCtcMagic)));
+            gb[r] = __reduce_add_sync(kFull, __double2loint(zb + kCtcMagic));
             if constexpr (SPL >= 8) {
                 int4* gr = reinterpret_cast<int4*>(gam + r * kGam) + lane * (SPL / 8);
 #pragma unroll
                 for (int i = 0; i < SPL / 8; ++i)
-                    gr[i] = make_int4(__double2loint(fma(wv[8 * i + 1], c, kCtcMagic)),
-                                      __double2loint(fma(wv[8 * i + 3], c, kCtcMagic)),
-                                      __double2loint(fma(wv[8 * i + 5], c, kCtcMagic)),
-                                      __double2loint(fma(wv[8 * i + 7], c, kCtcMagic)));
+                    gr[i] = make_int4(__double2loint(wv[8 * i + 1] + kCtcMagic), __double2loint(wv[8 * i + 3] + kCtcMagic),
+                                      __double2loint(wv[8 * i + 5] + kCtcMagic), __double2loint(wv[8 * i + 7] + kCtcMagic));
             } else {
                 reinterpret_cast<int2*>(gam + r * kGam)[lane] =
-                    make_int2(__double2loint(fma(wv[1], c, kCtcMagic)), __double2loint(fma(wv[3], c, kCtcMagic)));
+                    make_int2(__double2loint(wv[1] + kCtcMagic), __double2loint(wv[3] + kCtcMagic));
             }
         }
     }

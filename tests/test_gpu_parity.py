@@ -225,7 +225,10 @@ def ctc_case(cuda, B, T, V, L, seed, ragged, regime="random", repeat=False):
                                                    (64, 500, 30, 100, False, "random"), (8, 500, 30, 100, True, "peaky"),
                                                    (3, 64, 5, 63, True, "random"), (2, 300, 30, 127, False, "random"),
                                                    (2, 600, 30, 128, False, "random"), (2, 900, 12, 255, True, "peaky"),
-                                                   (2, 1100, 30, 400, False, "random"), (3, 9, 4, 1, False, "random")])
+                                                   (2, 1100, 30, 400, False, "random"), (3, 9, 4, 1, False, "random"),
+                                                   # long utterances: tile streamed from the workspace (any T)
+                                                   (3, 1203, 32, 60, True, "random"), (2, 2000, 30, 250, False, "peaky"),
+                                                   (2, 1501, 2, 100, True, "random"), (4, 4000, 30, 30, True, "random")])
 def test_ctc_matches_oracle(cuda, B, T, V, L, ragged, regime):
     ctc_case(cuda, B, T, V, L, seed=T + L, ragged=ragged, regime=regime, repeat=True)
 
