@@ -537,3 +537,21 @@ def test_evaluate_batch_matches_upstream_golden(cuda, golden):
         assert pgasr_b200.metrics.evaluate(e["ref"], e["hyp"]) == tuple(e["out"])
     with pytest.raises(ZeroDivisionError):
         pgasr_b200.metrics.evaluate_batch(["ab", ""], ["ab", "x"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V,K,L", [(64, 500, 30, 16, 100), (24, 1000, 30, 8, 200), (148, 96, 30, 4, 20)])
+def test_step_soak_bit_reproducible(cuda, B, T, V, K, L):
+    """The walker / worker hand-off (named barriers, rings, flags between CTAs) under repetition: the same step
+    300 times must give bit-identical gradients every time (a lost or early hand-off would show as a diff)."""
+    from pgasr_b200 import functional as F
+    lg, tg, il, tl, _ = make_batch(B, T, V, K, L, seed=11, ragged=True)
+    lg, tg, il, tl = dev_t(lg, cuda), dev_t(tg, cuda), dev_t(il, cuda), dev_t(tl, cuda)
+    first = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=5, want=("nll", "rewards"))
+    ws = first["workspace"]
+    bad = torch.zeros((), dtype=torch.int64, device=cuda)
+    for i in range(300):
+        out = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=5, workspace=ws, want=("nll", "rewards"))
+        bad += (out["dlogits"] != first["dlogits"]).sum() + (out["nll"] != first["nll"]).sum() + \
+            (out["rewards"] != first["rewards"]).sum() + (out["loss"] != first["loss"]).sum()
+    assert int(bad) == 0
