@@ -9,13 +9,14 @@ meaning and error behaviour), backed by the CUDA kernels in csrc/ through the C 
     loss.customNLLLoss  (+ the new loss.PolicyGradCTCLoss)    upstream loss.py
     functional.*                                              batched tensor-level operators (device tensors)
     host.HostPipeline                                         the step on pinned HOST arrays, pipelined
+    predict.decode_and_score                                  upstream predict()'s inner loop, batched (model.py:321-334)
     distributed.*                                             utterance sharding over ranks
 
 There is no CPU fallback anywhere in this package.
 """
 from . import _native                                        # noqa: F401
 from . import functional                                     # noqa: F401
-from . import metrics, CTCdecoder, policy_grad, loss, distributed, host   # noqa: F401
+from . import metrics, CTCdecoder, policy_grad, loss, distributed, host, predict   # noqa: F401
 from .loss import PolicyGradCTCLoss, customNLLLoss           # noqa: F401
 from .host import HostPipeline                               # noqa: F401
 

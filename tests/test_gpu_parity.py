@@ -555,3 +555,30 @@ def test_step_soak_bit_reproducible(cuda, B, T, V, K, L):
         bad += (out["dlogits"] != first["dlogits"]).sum() + (out["nll"] != first["nll"]).sum() + \
             (out["rewards"] != first["rewards"]).sum() + (out["loss"] != first["loss"]).sum()
     assert int(bad) == 0
+
+
+@pytest.mark.gpu
+def test_predict_inner_loop_matches_upstream_semantics(cuda):
+    """predict.decode_and_score against upstream's per-utterance loop (model.py:321-334) replayed with the oracle."""
+    import pgasr_b200
+    from oracle import pyref
+    rng = np.random.default_rng(5)
+    B, T, V, L = 6, 40, 8, 12
+    ind2char = {0: "_", 1: " ", 2: "a", 3: "b", 4: "c", 5: "d", 6: "e", 7: "l"}
+    z = rng.normal(size=(B, T, V)) * 2.5
+    logp = z - np.log(np.exp(z).sum(-1, keepdims=True))
+    t = rng.integers(1, V, size=(B, L))
+    t[:, 0] = 2                                                  # no leading space: every reference has a first word
+    tmask = np.zeros((B, L), np.int64)
+    for i in range(B):
+        tmask[i, :rng.integers(3, L + 1)] = 1
+    targets, predicted, cers, wers = pgasr_b200.predict.decode_and_score(logp, t, tmask, ind2char, beam_size=5)
+    for i in range(B):
+        pad = int(tmask[i].sum())
+        with np.errstate(divide="ignore"):
+            seq, _ = pyref.prefix_beam_search(np.exp(logp[i][:pad]), beam_size=5)
+        hyp = pyref.collapse_fn("".join(ind2char[s] for s in seq))
+        tgt = "".join(ind2char[s] for s in t[i][:pad])
+        assert targets[i] == tgt and predicted[i] == hyp
+        cer, wer = pyref.evaluate(tgt, hyp)
+        assert cers[i] == cer and wers[i] == wer
