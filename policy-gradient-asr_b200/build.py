@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-    "--shared", "-cudart", "static",
+    "--shared", "-cudart", "static", "--threads", "0",
 ]
 
 
