@@ -338,7 +338,11 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // =====================================================================================================
 namespace pgasr {
 
-constexpr int kBatch = 7;         // frames per hand-off batch; two batches in flight per direction
+// frames per hand-off batch (two batches in flight per direction); 32 states per lane make a frame 8 KB, so the
+// rings of that variant hold fewer frames
+template <int SPL>
+constexpr int kBatchOf = SPL >= 32 ? 4 : 7;
+inline int batch_of(int spl) { return spl >= 32 ? 4 : 7; }
 
 template <int SPL>
 struct GradRing {
@@ -377,14 +381,14 @@ __device__ __forceinline__ void ctc_build_class_lists(const int32_t* __restrict_
 
 template <int SPL>
 __host__ __device__ inline size_t grad_ring_bytes() {
-    return (size_t)2 * kBatch * SPL * 32 * 8 + (((size_t)2 * kBatch * 4 + 15) & ~(size_t)15);   // slots + exponents
+    return (size_t)2 * kBatchOf<SPL> * SPL * 32 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15);   // slots + exponents
 }
 
 template <int SPL>
 __device__ __forceinline__ GradRing<SPL> grad_ring_carve(unsigned char* p, int bar_base) {   // p 16-byte aligned
     GradRing<SPL> r;
     r.slots = reinterpret_cast<double*>(p);
-    r.eslot = reinterpret_cast<int*>(p + (size_t)2 * kBatch * SPL * 32 * 8);
+    r.eslot = reinterpret_cast<int*>(p + (size_t)2 * kBatchOf<SPL> * SPL * 32 * 8);
     r.bar_full = bar_base;
     r.bar_empty = bar_base + 2;
     r.dbg = false;
@@ -646,15 +650,15 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
     PGASR_STAMP(dbg, kAlpha ? 12 : 16);
 
     // ---- second half: post-emission values go to the workers in batches of kBatch frames -----------
-    for (int q = 0; q < n2; q += kBatch) {
-        const int buf = (q / kBatch) & 1;
-        if (q >= 2 * kBatch) named_bar_sync(ring.bar_empty + buf, kGroup);
-        double2* sp = reinterpret_cast<double2*>(ring.slots + (size_t)(buf * kBatch) * (SPL * 32)) + lane;
-        int* ep = ring.eslot + buf * kBatch;
-        const int nfr = min(kBatch, n2 - q);
-        if (nfr == kBatch) {
+    for (int q = 0; q < n2; q += kBatchOf<SPL>) {
+        const int buf = (q / kBatchOf<SPL>) & 1;
+        if (q >= 2 * kBatchOf<SPL>) named_bar_sync(ring.bar_empty + buf, kGroup);
+        double2* sp = reinterpret_cast<double2*>(ring.slots + (size_t)(buf * kBatchOf<SPL>) * (SPL * 32)) + lane;
+        int* ep = ring.eslot + buf * kBatchOf<SPL>;
+        const int nfr = min(kBatchOf<SPL>, n2 - q);
+        if (nfr == kBatchOf<SPL>) {
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
+            for (int u = 0; u < kBatchOf<SPL>; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
         } else {
             for (int u = 0; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
         }
@@ -686,7 +690,7 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
 // 48k of the 113k second-half cycles.)
 template <int SPL, int G, bool kAlpha>
 struct CtcWorker {
-    static constexpr int kPer = (kBatch + G - 1) / G;     // frames of a batch per worker (worker g: frames g, g+G, ..)
+    static constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;     // frames of a batch per worker (worker g: frames g, g+G, ..)
     double2 o[kPer][SPL / 2];
     int eo[kPer];
     double prow[kPer];            // global-tile mode: p_t(lane) of the frame, fetched with the lattice row
@@ -701,7 +705,7 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
     const bool act = lane * SPL < S;                      // the other direction never stored the lanes beyond S
 #pragma unroll
     for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kPer; ++r) {
-        const int q = min(nb * kBatch + min(g + r * G, kBatch - 1), n2 - 1);   // clamped: a stale row is loaded, never used
+        const int q = min(nb * kBatchOf<SPL> + min(g + r * G, kBatchOf<SPL> - 1), n2 - 1);   // clamped: a stale row is loaded, never used
         const int step = n_first + q;
         const int t = kAlpha ? step : Tb - 1 - step;
         const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lane;
@@ -727,16 +731,16 @@ constexpr int kClsRegs = 12;      // label positions of this lane's class held i
 template <int SPL, int G, bool kAlpha>
 __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlpha>& wk, WorkerNorm& nm, int nb, int g,
                                                    int n2, const GradRing<SPL>& ring, int* gam,
-                                                   int (&gb)[(kBatch + G - 1) / G]) {
+                                                   int (&gb)[(kBatchOf<SPL> + G - 1) / G]) {
     constexpr int kPer = CtcWorker<SPL, G, kAlpha>::kPer;
     constexpr int kGam = 16 * SPL;                        // ints per frame: SPL/2 label occupancies per lane
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
-        const int q = nb * kBatch + g + r * G;
+        const int q = nb * kBatchOf<SPL> + g + r * G;
         gb[r] = 0;
-        if (g + r * G < kBatch && q < n2) {
-            const int slot = q % (2 * kBatch);
+        if (g + r * G < kBatchOf<SPL> && q < n2) {
+            const int slot = q % (2 * kBatchOf<SPL>);
             const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 32)) + lane;
             // Occupancy of state s in 2^-30 fixed point = a(s) o(s) c with c = invZ0 2^(E + eo - E0).  The product
             // a(s) o(s) alone can underflow fp64 although both factors and the final value are in range (alpha and
@@ -800,19 +804,19 @@ __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlph
 // count point at label slot 16*SPL-1, whose state 32*SPL-1 lies beyond S for every transcript (always 0), so the
 // gather is branch free; cmax (warp uniform) bounds the rare tail of classes with more than kClsRegs labels.
 template <int SPL, int G, bool kAlpha, bool kGT = false>
-__device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlpha>& wk, const double (&prow)[(kBatch + G - 1) / G],
+__device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlpha>& wk, const double (&prow)[(kBatchOf<SPL> + G - 1) / G],
                                                    const WorkerNorm& nm, int nb, int g, int n_first, int n2, int Tb,
                                                    const double* tile, int V, int RS, int blank, float grad_scale,
                                                    float* __restrict__ dlog_u, const GradRing<SPL>& ring,
-                                                   const int* gam, const int (&gb)[(kBatch + G - 1) / G], int ccnt, int cmax,
+                                                   const int* gam, const int (&gb)[(kBatchOf<SPL> + G - 1) / G], int ccnt, int cmax,
                                                    const int (&cpos)[kClsRegs]) {
-    constexpr int kPer = (kBatch + G - 1) / G;
+    constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;
     constexpr int kGam = 16 * SPL;
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
-        const int q = nb * kBatch + g + r * G;
-        if (g + r * G < kBatch && q < n2) {
+        const int q = nb * kBatchOf<SPL> + g + r * G;
+        if (g + r * G < kBatchOf<SPL> && q < n2) {
             const int step = n_first + q;
             const int t = kAlpha ? step : Tb - 1 - step;
             const double* row = tile + (size_t)t * RS;
@@ -860,7 +864,7 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
                                                 const int* __restrict__ exp_u, GradRing<SPL> ring, int* gam,
                                                 Barrier mid_barrier) {
     constexpr int kGroup = 32 * (1 + G);
-    constexpr int kPer = (kBatch + G - 1) / G;
+    constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;
     const int lane = threadIdx.x & 31;
     const int tm = Tb / 2;
     const int n_first = kAlpha ? tm : Tb - tm;
@@ -876,7 +880,7 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
     WorkerNorm nm;
     nm.invZ0 = 0.0; nm.E0 = 0; nm.dead = false; nm.have = false;
     nm.tA = nm.tB = nm.tWait = nm.tBusy = 0;
-    const int nbatch = (n2 + kBatch - 1) / kBatch;
+    const int nbatch = (n2 + kBatchOf<SPL> - 1) / kBatchOf<SPL>;
     CtcWorker<SPL, G, kAlpha> wk;
     int gb[kPer];
     const int S = 2 * L + 1;

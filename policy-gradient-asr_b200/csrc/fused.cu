@@ -41,7 +41,7 @@ constexpr int kFusedMaxK = 64;
 template <int SPL, int kThreads, bool kGT>
 __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw) {
     constexpr int G = (kThreads / 32 - 2) / 2;             // gradient workers per direction
-    constexpr int kPer = (kBatch + G - 1) / G;             // frames of a batch per worker
+    constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;      // frames of a batch per worker
     constexpr int kMidThreads = 32 * (2 + 2 * G);
     const int warp = threadIdx.x >> 5;
     const int T = a.T, V = a.V;
@@ -499,7 +499,7 @@ static FusedWs fused_ws(int B, int T, int V, int spl, bool gt) {
 static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
     const int RS = ctc_row_stride(V);
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
-    const int G = (threads / 32 - 2) / 2, per = (kBatch + G - 1) / G;
+    const int G = (threads / 32 - 2) / 2, per = (batch_of(spl) + G - 1) / G;
     const size_t pring = (size_t)kPRows * (RS <= 32 ? 32 : 64) * 8;
     const size_t tile = gt ? 3 * pring /* two rings + alignment slack */ : (size_t)(T + 2) * RS * sizeof(double);
     return tile + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int);
@@ -518,9 +518,9 @@ struct FusedPlan { int spl, threads; bool ctc_ok, gt, pg_ok; };
 static FusedPlan fused_plan(int T, int V, int K, int Lmax) {
     FusedPlan pl;
     pl.spl = ctc_spl(Lmax);
-    pl.threads = 512;
+    pl.threads = pl.spl >= 32 ? 256 : 512;             // 32 states per lane need the 255-register budget
     pl.ctc_ok = pl.gt = pl.pg_ok = false;
-    if (pl.spl == 0 || pl.spl == 32 || V > 32 || K > kFusedMaxK) return pl;   // SPL 32: the hand-off rings alone exceed an SM
+    if (pl.spl == 0 || V > 32 || K > kFusedMaxK) return pl;
     if (ctc_role_smem(T, V, pl.spl, pl.threads, false) <= kFusedSmemLimit) {
         pl.ctc_ok = true;
     } else if (ctc_role_smem(T, V, pl.spl, pl.threads, true) <= kFusedSmemLimit) {
@@ -577,7 +577,9 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
         case 16: return launch_fused<8, 512, false>(a, smem, st);
         case 17: return launch_fused<8, 512, true>(a, smem, st);
         case 32: return launch_fused<16, 512, false>(a, smem, st);
-        default: return launch_fused<16, 512, true>(a, smem, st);
+        case 33: return launch_fused<16, 512, true>(a, smem, st);
+        case 64: return launch_fused<32, 256, false>(a, smem, st);
+        default: return launch_fused<32, 256, true>(a, smem, st);
     }
 }
 
