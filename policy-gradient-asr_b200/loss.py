@@ -88,6 +88,11 @@ class PolicyGradCTCLoss(nn.Module):
         return s
 
     def forward(self, logits, targets, input_lengths=None, target_lengths=None, uniforms=None):
-        if self.reward == "cer" and target_lengths is not None and bool((torch.as_tensor(target_lengths) == 0).any()):
-            raise ZeroDivisionError("division by zero")      # metrics.evaluate on an empty reference
+        # metrics.evaluate raises ZeroDivisionError on an empty reference.  Lengths that live on the host are checked
+        # here; lengths already on the GPU are not (the check would cost a device synchronisation per step) -- an
+        # empty transcript then yields reward -inf / nan for that utterance instead of an exception.
+        if self.reward == "cer" and target_lengths is not None:
+            tl = target_lengths if isinstance(target_lengths, torch.Tensor) else torch.as_tensor(target_lengths)
+            if not tl.is_cuda and bool((tl == 0).any()):
+                raise ZeroDivisionError("division by zero")
         return _PGCTCFn.apply(logits, self, targets, input_lengths, target_lengths, uniforms)

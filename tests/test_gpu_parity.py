@@ -582,3 +582,15 @@ def test_predict_inner_loop_matches_upstream_semantics(cuda):
         assert targets[i] == tgt and predicted[i] == hyp
         cer, wer = pyref.evaluate(tgt, hyp)
         assert cers[i] == cer and wers[i] == wer
+
+
+@pytest.mark.gpu
+def test_acoustic_harness_trains(cuda):
+    """the criterion slot in a real training step (stock BLSTM + head): finite loss, parameters move."""
+    import subprocess, sys, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "acoustic_harness.py"), "--global-batch", "8", "--T", "120",
+                        "--L", "20", "--K", "4", "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert np.isfinite(out["loss"]) and out["ms_per_step"] > 0 and -1.5 * 120 / 20 <= out["mean_reward"] <= 0
