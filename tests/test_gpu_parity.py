@@ -594,3 +594,49 @@ def test_acoustic_harness_trains(cuda):
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert np.isfinite(out["loss"]) and out["ms_per_step"] > 0 and -1.5 * 120 / 20 <= out["mean_reward"] <= 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V,K,L,philox", [(1, 33, 30, 1, 4, False), (2, 70, 9, 5, 11, True), (3, 65, 32, 7, 6, False),
+                                               (2, 500, 30, 64, 100, True), (5, 48, 3, 2, 47, False)])
+def test_step_odd_shapes(cuda, B, T, V, K, L, philox):
+    """K not a multiple of the Philox block, single utterance / single sample, V = 32 (row stride 34), tiny V."""
+    step_case(cuda, B, T, V, K, L, seed=B + K, ragged=True, regime="random", philox=philox)
+
+
+@pytest.mark.gpu
+def test_step_empty_utterances_and_nonzero_blank(cuda):
+    """in_len = 0 (nothing to sample or align), an empty transcript, and a blank id other than 0."""
+    from pgasr_b200 import functional as F
+    B, T, V, K, L = 4, 40, 6, 4, 5
+    logits, targets, in_len, tgt_len, uni = make_batch(B, T, V, K, L, seed=21)
+    in_len[0] = 0                                   # no frames: every hypothesis is empty, CTC has no alignment
+    tgt_len[1] = 0; targets[1] = 0                  # empty transcript: only the all-blank path
+    in_len[2] = 3; tgt_len[2] = 5                   # fewer frames than labels: infeasible
+    loss_ref, R_ref, nll_ref, dl_ref = cport.pg_ctc_step(logits, targets, in_len, tgt_len, uni, w_pg=1.0, w_ctc=0.0)
+    out = F.pg_ctc_step(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda),
+                        uniforms=dev_t(uni, cuda), ctc_weight=0.0, want=("rewards", "hyp_len", "dist"))
+    assert np.array_equal(out["rewards"].cpu().numpy(), R_ref)
+    assert rel_err(out["dlogits"].cpu().numpy(), dl_ref) < RTOL       # (the oracle's scalar is 0 * inf = nan here)
+    assert np.isfinite(float(out["loss"]))
+    assert (out["hyp_len"][0].cpu().numpy() == 0).all() and (out["dist"][0].cpu().numpy() == L).all()
+    nll_ref, g_ref = cport.ctc_loss_grad(logits, targets, in_len, tgt_len)
+    out = F.pg_ctc_step(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda),
+                        uniforms=dev_t(uni, cuda), pg_weight=0.0, want=("nll",))
+    nll = out["nll"].cpu().numpy()
+    assert np.isinf(nll[0]) and np.isinf(nll[2]) and np.array_equal(np.isfinite(nll), np.isfinite(nll_ref))
+    fin = np.isfinite(nll_ref)
+    assert np.abs(nll[fin] / nll_ref[fin] - 1).max() < RTOL
+    g = out["dlogits"].cpu().numpy() * B
+    assert (g[0] == 0).all() and (g[2] == 0).all() and rel_err(g[fin], g_ref[fin]) < RTOL
+    # blank id 2: labels avoid it
+    logits, targets, in_len, tgt_len, uni = make_batch(3, 50, 6, 4, 7, seed=22, ragged=True)
+    targets = np.where(targets == 2, 5, targets).astype(np.int32)
+    for b in range(3):
+        targets[b, tgt_len[b]:] = 0
+    loss_ref, R_ref, nll_ref, dl_ref = cport.pg_ctc_step(logits, targets, in_len, tgt_len, uni, blank=2)
+    out = F.pg_ctc_step(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda),
+                        uniforms=dev_t(uni, cuda), blank=2, want=("rewards", "nll"))
+    assert np.array_equal(out["rewards"].cpu().numpy(), R_ref)
+    assert np.abs(out["nll"].cpu().numpy() / nll_ref - 1).max() < RTOL
+    assert rel_err(out["dlogits"].cpu().numpy(), dl_ref) < RTOL
