@@ -1,0 +1,551 @@
+#pragma once
+// (implementation header: included by fused_spl*.cu, one translation unit per states-per-lane variant)
+// The whole PG + CTC loss step as ONE kernel launch (upstream call site: criterion(model_out, t) followed by
+// loss.backward(), model.py:235-237; SURVEY.md rows a1-a8 chained).
+//
+// Grid = 2B CTAs that pick their role from an atomic ticket (tickets < B: CTC role of utterance `ticket`;
+// the rest: PG role of utterance `ticket - B`), so the long-pole CTC CTAs are always resident before any PG CTA
+// waits on them.  Both roles of an utterance run at the same time on different SMs:
+//   CTC role: softmax of the utterance into an fp64 shared-memory tile, then warp 0 / warp 1 walk alpha / beta
+//             (ctc_core.cuh) and write the CTC gradient rows; finally a release flag.
+//   PG role:  logits tile -> shared memory (cp.async), one thread per frame: softmax CDF + K inverse-CDF draws
+//             (Philox or injected uniforms), one warp per sample: ballot/popc collapse, one thread per sample:
+//             bit-parallel Levenshtein against the transcript, warp 0: rewards / baseline / advantages, then the
+//             REINFORCE gradient tile is built in place of the logits tile, the CTA acquires the CTC role's flag
+//             and adds its tile onto the CTC rows with coalesced float4 read-modify-writes.
+// The last CTA to finish (second ticket) reduces the loss in a fixed order and re-arms the control block.
+// dlogits is written once by the CTC role and updated once by the PG role; every sum is order independent or
+// fixed-order, so the step is bit-reproducible run to run.
+#include "ctc_core.cuh"
+#include "fused_args.cuh"
+#include "myers_core.cuh"
+
+namespace pgasr {
+
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int kFusedMaxK = 64;
+
+// ------------------------------------------------------------------------------------------------ CTC role
+// warp 0: alpha recurrence, warp 1: beta recurrence; every other warp is a gradient worker, even warps on the
+// alpha side, odd warps on the beta side (G = (warps - 2) / 2 per direction).
+// kGT (long utterances): the fp64 softmax tile does not fit in shared memory; it is written to the global
+// workspace instead, the walkers stream it back through 32-row cp.async rings and the workers fetch their
+// p_t(lane) with the lattice row.  Shared memory then no longer depends on T.
+template <int SPL, int kThreads, bool kGT>
+__device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw) {
+    constexpr int G = (kThreads / 32 - 2) / 2;             // gradient workers per direction
+    constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;      // frames of a batch per worker
+    constexpr int kMidThreads = 32 * (2 + 2 * G);
+    const int warp = threadIdx.x >> 5;
+    const int T = a.T, V = a.V;
+    const int RS = ctc_row_stride(V);
+    // shared-memory carve-up (see fused_smem)
+    // [T][RS] between two guard rows: the walkers load the probabilities one frame ahead and run one row past
+    // either end (the guard values are loaded and never used)
+    const int RSR = RS <= 32 ? 32 : 64;                                  // ring row stride (power of two)
+    const size_t pring_bytes = (size_t)kPRows * RSR * 8;
+    double* tile;
+    double* pring_a = nullptr;
+    double* pring_b = nullptr;
+    unsigned char* p;
+    if (kGT) {
+        tile = a.tile_g + ((size_t)b * (T + 2) + 1) * RS;
+        // the dynamic shared memory window is 1 KB aligned at least; align the rings to their size by address
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw);
+        const unsigned pad = (unsigned)((pring_bytes - (base & (pring_bytes - 1))) & (pring_bytes - 1));
+        pring_a = reinterpret_cast<double*>(smem_raw + pad);
+        pring_b = reinterpret_cast<double*>(smem_raw + pad + pring_bytes);
+        p = smem_raw + pad + 2 * pring_bytes;
+    } else {
+        tile = reinterpret_cast<double*>(smem_raw) + RS;
+        p = smem_raw + (size_t)(T + 2) * RS * 8;
+    }
+    unsigned char* const stage_base = p;
+    GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
+    GradRing<SPL> ring_b = grad_ring_carve<SPL>(p, 6);                  p += grad_ring_bytes<SPL>();
+    int* gam_all = reinterpret_cast<int*>(p);                           // [2 G workers][kPer frames][16 SPL]
+    p += (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
+    int* cls_off = reinterpret_cast<int*>(p);                           // [V + 1]
+    int* cls_scr = cls_off + (V + 1);                                   // [V] counting-sort scratch
+    int* cls_pos = cls_scr + V;                                         // [512]
+    int* lab_s = cls_pos + 512;                                         // [512] the transcript
+    // The transcript and the lengths may live in mapped HOST memory (pgasr_host_*: a PCIe round trip per dependent
+    // access), so everything is fetched here in one go and the transcript is used from shared memory afterwards.
+    for (int i = threadIdx.x; i < a.Lmax; i += kThreads) lab_s[i] = a.targets[(size_t)b * a.Lmax + i];
+    int Tb = a.in_len ? a.in_len[b] : T;
+    Tb = min(max(Tb, 0), T);
+    int L = a.tgt_len ? a.tgt_len[b] : a.Lmax;
+    L = min(max(L, 0), a.Lmax);
+    float* dlog_u = a.dlogits + (size_t)b * T * V;
+    float* nll_u = a.nll_ws + b;
+    PGASR_STAMP(b == 0 && threadIdx.x == 0, 0);
+    for (int i = Tb * V + threadIdx.x; i < T * V; i += kThreads) dlog_u[i] = 0.0f;
+    if (Tb == 0) {
+        if (threadIdx.x == 0) *nll_u = L == 0 ? 0.0f : INFINITY;
+    } else {
+        ring_a.dbg = ring_b.dbg = (b == 0);
+        PGASR_STAMP(b == 0 && threadIdx.x == 0, 1);
+        // softmax tile.  The raw logits are staged through the (not yet used) ring region with cp.async, then one
+        // thread per frame makes three passes over its row -- max, exp + sum, normalise -- visiting the classes in
+        // a per-thread rotated order so that neither the staged reads (row stride V floats) nor the fp64 tile
+        // writes (row stride RS doubles) collide on a shared-memory bank.
+        const float* lg = a.logits + (size_t)b * T * V;
+        {
+            float* stage = reinterpret_cast<float*>(stage_base);
+            const size_t stage_bytes = 2 * grad_ring_bytes<SPL>() + (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
+            const int chunk = (int)(stage_bytes / ((size_t)V * 4)) & ~3;
+            const bool al16 = (((size_t)T * V * 4) & 15) == 0;
+            for (int c0 = 0; c0 < Tb; c0 += chunk) {
+                const int n = min(chunk, Tb - c0);
+                const float* src = lg + (size_t)c0 * V;
+                if (al16) {
+                    const int n16 = n * V / 4, rem = n * V - n16 * 4;
+                    for (int i = threadIdx.x; i < n16; i += kThreads)
+                        cp_async16(reinterpret_cast<char*>(stage) + (size_t)i * 16,
+                                   reinterpret_cast<const char*>(src) + (size_t)i * 16);
+                    for (int i = threadIdx.x; i < rem; i += kThreads) cp_async4(stage + n16 * 4 + i, src + n16 * 4 + i);
+                } else {
+                    for (int i = threadIdx.x; i < n * V; i += kThreads) cp_async4(stage + i, src + i);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+                for (int t = threadIdx.x; t < n; t += kThreads) {
+                    // the row lives in registers in rotated order (slot k holds class (k + t) & 31): the order does
+                    // not matter for the max and the sum, every load / exp / store is independent of the others
+                    const float* zr = stage + (size_t)t * V;
+                    double* orow = tile + (size_t)(c0 + t) * RS;
+                    float x[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const int idx = (k + t) & 31;
+                        x[k] = idx < V ? zr[idx] : -INFINITY;
+                    }
+                    float m4[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+                    for (int k = 4; k < 32; ++k) m4[k & 3] = fmaxf(m4[k & 3], x[k]);
+                    const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                    float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        x[k] = __expf(x[k] - m);                   // exp(-inf) = 0 for the unused slots
+                        s4[k & 3] += x[k];
+                    }
+                    const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const int idx = (k + t) & 31;
+                        if (idx < RS) orow[idx] = (double)(x[k] * inv);
+                    }
+                    for (int idx = 32; idx < RS; ++idx) orow[idx] = 0.0;
+                }
+                if (kGT) __threadfence_block();            // the rows go to global memory: order them before the barrier
+                __syncthreads();
+            }
+        }
+        const int32_t* lab_u = lab_s;                      // (published by the barriers of the tile loop above)
+        if (warp == 0) ctc_build_class_lists(lab_u, L, V, cls_off, cls_pos, cls_scr);
+        ring_a.cls_off = ring_b.cls_off = cls_off;
+        ring_a.cls_pos = ring_b.cls_pos = cls_pos;
+        __syncthreads();
+        PGASR_STAMP(b == 0 && threadIdx.x == 0, 2);
+        double* lat_u = a.lattice + (size_t)b * T * (SPL * 32);
+        int* exp_u = a.lat_exp + (size_t)b * T;
+        const float gs = a.w_ctc / (float)a.B;
+        auto mid = [] {
+            __threadfence_block();
+            asm volatile("bar.sync 1, %0;\n" ::"n"(kMidThreads) : "memory");
+        };
+        const int g = (warp - 2) >> 1;
+        if (warp == 0)
+            ctc_walk_tile<SPL, G, true, kGT>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid, pring_a,
+                                             RSR, T);
+        else if (warp == 1)
+            ctc_walk_tile<SPL, G, false, kGT>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_b, mid,
+                                              pring_b, RSR, T);
+        else if (g < G && !(warp & 1))
+            ctc_grad_worker<SPL, G, true, kGT>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_a,
+                                               gam_all + g * kPer * 16 * SPL, mid);
+        else if (g < G)
+            ctc_grad_worker<SPL, G, false, kGT>(g, tile, lab_u, Tb, L, V, RS, a.blank, gs, dlog_u, lat_u, exp_u, ring_b,
+                                                gam_all + (G + g) * kPer * 16 * SPL, mid);
+    }
+    __threadfence();                                       // rows and nll visible device-wide before the flag
+    __syncthreads();
+    PGASR_STAMP(b == 0 && threadIdx.x == 0, 3);
+    if (threadIdx.x == 0) {
+        if (a.nll) a.nll[b] = *nll_u;                      // the caller's copy (possibly host memory); the loss reads nll_ws
+        st_release(a.ctrl + 4 + b, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ PG role
+// kStream (long utterances): no [T][V] tile in shared memory -- a thread reads its frame's logits straight from
+// global memory, and the gradient rows are formed in registers and added to dlogits row by row.
+template <int W, int kThreads, bool kStream>
+__device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw) {
+    constexpr int kWarps = kThreads / 32;
+    constexpr int VP = 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int T = a.T, V = a.V, K = a.K;
+    const int Tp = (T + 15) & ~15;
+    int Tb = a.in_len ? a.in_len[b] : T;
+    Tb = min(max(Tb, 0), T);
+    int m = a.tgt_len ? a.tgt_len[b] : a.Lmax;
+    m = min(max(m, 0), a.Lmax);
+
+    // shared-memory carve-up
+    float* ztile = reinterpret_cast<float*>(smem_raw);                                // [T][V] (tile mode only)
+    size_t off = kStream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15);
+    uint8_t* samples_s = smem_raw + off;            off += (size_t)K * Tp;            // [K][Tp]
+    uint8_t* hyp_s = smem_raw + off;                off += (size_t)K * Tp;            // [K][Tp]
+    uint32_t* peq = reinterpret_cast<uint32_t*>(smem_raw + off); off += (size_t)(V + 1) * W * 4;
+    off = (off + 15) & ~(size_t)15;
+    float* warp_acc = reinterpret_cast<float*>(smem_raw + off);  off += (size_t)kWarps * kFusedMaxK * 4;
+    float* adv_s = reinterpret_cast<float*>(smem_raw + off);     off += kFusedMaxK * 4;
+    int* hlen_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
+    int* dist_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
+    float* misc_s = reinterpret_cast<float*>(smem_raw + off);    // [0] sum of advantages
+
+    const bool dbg = b == 0 && threadIdx.x == 0;
+    PGASR_STAMP(dbg, 30);
+    // ---- P0: logits tile -> shared memory ------------------------------------------------------
+    const float* lg = a.logits + (size_t)b * T * V;
+    if (!kStream) {
+        if ((((size_t)T * V * 4) & 15) == 0) {
+            const int n16 = T * V / 4;
+            for (int i = threadIdx.x; i < n16; i += kThreads)
+                cp_async16(reinterpret_cast<char*>(ztile) + (size_t)i * 16, reinterpret_cast<const char*>(lg) + (size_t)i * 16);
+        } else {
+            for (int i = threadIdx.x; i < T * V; i += kThreads) cp_async4(ztile + i, lg + i);
+        }
+        cp_async_commit();
+    }
+    // the transcript may live in mapped host memory: fetch it now, it is needed after the sampling phase
+    const int32_t* ref = a.targets + (size_t)b * a.Lmax;
+    int ref_r[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int j = threadIdx.x + q * kThreads;
+        ref_r[q] = j < m ? ref[j] : -1;
+    }
+    for (int i = threadIdx.x; i < kWarps * kFusedMaxK; i += kThreads) warp_acc[i] = 0.0f;
+    for (int i = threadIdx.x; i < (V + 1) * W; i += kThreads) peq[i] = 0u;
+    cp_async_wait<0>();
+    __syncthreads();
+
+    PGASR_STAMP(dbg, 31);
+    // ---- P1: softmax CDF + K draws, one thread per frame (DESIGN.md "sampler spec") ------------
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    for (int t0 = 0; t0 < T; t0 += kThreads) {
+        const int t = t0 + threadIdx.x;
+        const bool live = t < Tb;
+        const float* z = (kStream ? lg : ztile) + (size_t)(live ? t : 0) * V;
+        float cdf[VP];
+        float mx = -INFINITY, S = 0.0f, logS = 0.0f;
+        if (live) {
+#pragma unroll
+            for (int v = 0; v < VP; ++v) cdf[v] = v < V ? z[v] : -INFINITY;
+#pragma unroll
+            for (int v = 0; v < VP; ++v) mx = fmaxf(mx, cdf[v]);
+            float c = 0.0f;
+#pragma unroll
+            for (int v = 0; v < VP; ++v) {
+                if (v < V) c = __fadd_rn(c, exp_spec(__fsub_rn(cdf[v], mx)));
+                cdf[v] = c;
+            }
+            S = c;
+            logS = logf(S);
+        }
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < K; ++k) {
+            float term = 0.0f;
+            int pi = 0;
+            if (live) {
+                float u;
+                if (a.uniforms) {
+                    u = __ldg(a.uniforms + ((size_t)b * K + k) * T + t);
+                } else {
+                    if ((k & 3) == 0)
+                        rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k >> 2), 0x50474153u), key);
+                    const uint32_t x = (k & 3) == 0 ? rnd.x : (k & 3) == 1 ? rnd.y : (k & 3) == 2 ? rnd.z : rnd.w;
+                    u = u32_to_uniform(x);
+                }
+                const float tau = __fmul_rn(u, S);
+                int cnt = 0;
+#pragma unroll
+                for (int v = 0; v < VP; ++v) cnt += (v < V && cdf[v] <= tau) ? 1 : 0;
+                pi = min(cnt, V - 1);
+                term = (z[pi] - mx) - logS;
+            }
+            if (t < T) {
+                samples_s[(size_t)k * Tp + t] = (uint8_t)pi;
+                if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi;
+            }
+            term = warp_sum(term);
+            if (lane == 0) warp_acc[warp * kFusedMaxK + k] += term;
+        }
+    }
+    __syncthreads();
+
+    PGASR_STAMP(dbg, 32);
+    // ---- P2: collapse (one warp per sample) and the match table of the transcript ---------------
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int j = threadIdx.x + q * kThreads;
+        const uint32_t c = (uint32_t)ref_r[q];
+        if (j < m && c < (uint32_t)V) atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+    }
+    for (int j = threadIdx.x + 2 * kThreads; j < m; j += kThreads) {     // (Lmax > 2 * threads: never with Lmax <= 511)
+        const uint32_t c = (uint32_t)ref[j];
+        if (c < (uint32_t)V) atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+    }
+    for (int k = warp; k < K; k += kWarps) {
+        const uint8_t* in = samples_s + (size_t)k * Tp;
+        uint8_t* o = hyp_s + (size_t)k * Tp;
+        int base = 0, carry = -1;
+        for (int t0 = 0; t0 < Tb; t0 += 32) {
+            const int t = t0 + lane;
+            const int x = t < Tb ? (int)in[t] : -2;
+            int p = __shfl_up_sync(kFull, x, 1);
+            if (lane == 0) p = carry;
+            const bool keep = t < Tb && x != p && x != a.blank;
+            const unsigned mask = __ballot_sync(kFull, keep);
+            if (keep) o[base + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)x;
+            base += __popc(mask);
+            carry = __shfl_sync(kFull, x, 31);
+        }
+        if (lane == 0) hlen_s[k] = base;
+    }
+    __syncthreads();
+
+    PGASR_STAMP(dbg, 33);
+    // ---- P3: edit distance, one thread per sample ------------------------------------------------
+    // (all K samples in the lanes of as few warps as possible: a Myers step is ~25 W dependent integer
+    // instructions, and lanes of one warp share them; one sample per warp was measured 3.6x slower)
+    if ((int)threadIdx.x < K) {
+        const int k = threadIdx.x;
+        dist_s[k] = myers_row<W, false>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, nullptr);
+    }
+    __syncthreads();
+
+    PGASR_STAMP(dbg, 34);
+    // ---- P4: rewards, baseline, advantages, loss term (warp 0) -----------------------------------
+    if (warp == 0) {
+        float sumR = 0.0f;
+        for (int k = lane; k < K; k += 32) {
+            float R = -(float)dist_s[k];
+            if (a.reward_mode == PGASR_REWARD_NEG_CER) R = __fdiv_rn(R, (float)m);
+            adv_s[k] = R;
+            sumR += R;
+        }
+        sumR = warp_sum(sumR);
+        float term = 0.0f, sumA = 0.0f;
+        for (int k = lane; k < K; k += 32) {
+            const float R = adv_s[k];
+            float base = 0.0f;
+            if (a.baseline_mode == PGASR_BASELINE_MEAN) base = sumR / (float)K;
+            else if (a.baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumR - R) / (float)(K - 1) : 0.0f;
+            else if (a.baseline_mode == PGASR_BASELINE_VALUE) base = a.baseline_value;
+            const float A = R - base;
+            float lp = 0.0f;
+            for (int w = 0; w < kWarps; ++w) lp += warp_acc[w * kFusedMaxK + k];
+            term += -A * lp;
+            sumA += A;
+            adv_s[k] = A;
+            const size_t o = (size_t)b * K + k;
+            if (a.rewards) a.rewards[o] = R;
+            if (a.logp) a.logp[o] = lp;
+            if (a.hyp_len) a.hyp_len[o] = hlen_s[k];
+            if (a.dist) a.dist[o] = dist_s[k];
+        }
+        term = warp_sum(term);
+        sumA = warp_sum(sumA);
+        if (lane == 0) {
+            a.loss_terms[b] = term;
+            misc_s[0] = sumA;
+        }
+    }
+    __syncthreads();
+
+    PGASR_STAMP(dbg, 35);
+    // ---- P5: REINFORCE gradient tile, in place of the logits tile ---------------------------------
+    const float coef = a.w_pg / ((float)a.B * (float)K);
+    const bool dense = a.baseline_mode != PGASR_BASELINE_MEAN;   // sum_k A_k == 0 under the per-utterance mean
+    const float dense_c = coef * misc_s[0];
+    float* dlog_u = a.dlogits + (size_t)b * T * V;
+    if constexpr (kStream) {
+        // one thread per frame: the K sample ids into registers, then for every class the advantage mass that fell
+        // on it; the row is added to (or, without a CTC term, stored as) dlogits directly
+        if (a.do_ctc) {
+            if (threadIdx.x == 0) {
+                const unsigned* flag = a.ctrl + 4 + b;
+                while (ld_acquire(flag) == 0u) __nanosleep(200);
+            }
+            __syncthreads();
+        }
+        PGASR_STAMP(dbg, 37);
+        for (int t = threadIdx.x; t < T; t += kThreads) {
+            float* out = dlog_u + (size_t)t * V;
+            if (t >= Tb) {
+                if (!a.do_ctc)
+                    for (int v = 0; v < V; ++v) out[v] = 0.0f;
+                continue;
+            }
+            float mx = 0.0f, sc = 0.0f;
+            const float* zr = lg + (size_t)t * V;
+            if (dense) {
+                mx = -INFINITY;
+                float ssum = 0.0f;
+                for (int v = 0; v < V; ++v) mx = fmaxf(mx, zr[v]);
+                for (int v = 0; v < V; ++v) ssum += __expf(zr[v] - mx);
+                sc = dense_c / ssum;
+            }
+            for (int v = 0; v < V; ++v) {
+                float g = dense ? __expf(zr[v] - mx) * sc : 0.0f;
+                for (int k = 0; k < K; ++k)              // same order of subtractions as the tile mode: k ascending
+                    if (samples_s[(size_t)k * Tp + t] == v) g -= coef * adv_s[k];
+                out[v] = a.do_ctc ? __ldcg(out + v) + g : g;
+            }
+        }
+        PGASR_STAMP(dbg, 38);
+    } else {
+    for (int t = threadIdx.x; t < T; t += kThreads) {
+        float* row = ztile + (size_t)t * V;
+        if (t < Tb) {
+            if (dense) {
+                float mx = -INFINITY, s = 0.0f;
+                for (int v = 0; v < V; ++v) mx = fmaxf(mx, row[v]);
+                for (int v = 0; v < V; ++v) s += __expf(row[v] - mx);
+                const float sc = dense_c / s;
+                for (int v = 0; v < V; ++v) row[v] = __expf(row[v] - mx) * sc;
+            } else {
+                for (int v = 0; v < V; ++v) row[v] = 0.0f;
+            }
+            for (int k = 0; k < K; ++k) row[samples_s[(size_t)k * Tp + t]] -= coef * adv_s[k];
+        } else {
+            for (int v = 0; v < V; ++v) row[v] = 0.0f;
+        }
+    }
+    __syncthreads();
+
+    PGASR_STAMP(dbg, 36);
+    // ---- P6: add the tile onto the CTC rows (or store it when there is no CTC term) ---------------
+    if (a.do_ctc) {
+        if (threadIdx.x == 0) {
+            const unsigned* flag = a.ctrl + 4 + b;
+            while (ld_acquire(flag) == 0u) __nanosleep(200);
+        }
+        __syncthreads();
+    }
+    PGASR_STAMP(dbg, 37);
+    if ((((size_t)T * V * 4) & 15) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dlog_u);
+        const float4* t4 = reinterpret_cast<const float4*>(ztile);
+        for (int i = threadIdx.x; i < T * V / 4; i += kThreads) {
+            float4 g = t4[i];
+            if (a.do_ctc) {
+                const float4 c = __ldcg(d4 + i);
+                g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w;
+            }
+            d4[i] = g;
+        }
+    } else {
+        for (int i = threadIdx.x; i < T * V; i += kThreads)
+            dlog_u[i] = a.do_ctc ? __ldcg(dlog_u + i) + ztile[i] : ztile[i];
+    }
+    PGASR_STAMP(dbg, 38);
+    }   // tile mode
+}
+
+#ifdef PGASR_TIMING
+static __device__ unsigned long long g_cta_ns[2048][3];          // per ticket: start, role end, exit (globaltimer ns)
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
+#endif
+
+template <int SPL, int kThreads, bool kGT, bool kStream>
+__global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned s_ticket, s_last;
+#ifdef PGASR_TIMING
+    const unsigned long long t_start = gtime();
+#endif
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ctrl, 1u);
+    __syncthreads();
+    const unsigned ticket = s_ticket;
+    const unsigned n_ctc = a.do_ctc ? (unsigned)a.B : 0u;
+    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT>(a, (int)ticket, smem_raw);
+    else fused_pg_role<SPL / 2, kThreads, kStream>(a, (int)(ticket - n_ctc), smem_raw);
+
+#ifdef PGASR_TIMING
+    if (threadIdx.x == 0 && ticket < 2048) { g_cta_ns[ticket][0] = t_start; g_cta_ns[ticket][1] = gtime(); }
+#endif
+    // ---- second ticket: the last CTA reduces the loss (fixed order) and re-arms the control block ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.ctrl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence();
+        const float* nl = a.nll_ws;
+        float pg = 0.0f, ct = 0.0f;
+        for (int b = threadIdx.x; b < a.B; b += 32) {
+            if (a.do_pg) pg += __ldcg(a.loss_terms + b);
+            if (a.do_ctc) ct += __ldcg(nl + b);
+            a.ctrl[4 + b] = 0u;
+        }
+        pg = warp_sum(pg);
+        ct = warp_sum(ct);
+        if (threadIdx.x == 0) {
+            float l = 0.0f;
+            if (a.do_pg) l += a.w_pg * pg / ((float)a.B * (float)a.K);
+            if (a.do_ctc) l += a.w_ctc * ct / (float)a.B;
+            a.loss[0] = l;
+            a.ctrl[0] = 0u;
+            a.ctrl[1] = 0u;
+        }
+    }
+#ifdef PGASR_TIMING
+    if (threadIdx.x == 0 && ticket < 2048) g_cta_ns[ticket][2] = gtime();
+#endif
+}
+
+template <int SPL, int kThreads, bool kGT, bool kStream>
+static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
+    static thread_local size_t smem_set = 0;               // the opt-in is sticky: raise it only when a larger tile comes
+    if (smem > smem_set) {
+        PGASR_CUDA_TRY(cudaFuncSetAttribute(pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const int grid = (a.do_ctc ? a.B : 0) + (a.do_pg ? a.B : 0);
+    pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream><<<grid, kThreads, smem, st>>>(a);
+    PGASR_LAUNCH_CHECK();
+    return PGASR_OK;
+}
+
+// one translation unit per SPL instantiates its three modes (0: tiles in shared memory, 1: the CTC role streams,
+// 2: both roles stream) so that the variants compile in parallel
+template <int SPL, int kThreads>
+int launch_fused_modes(int mode, FusedArgs& a, size_t smem, cudaStream_t st) {
+    switch (mode) {
+        case 0: return launch_fused<SPL, kThreads, false, false>(a, smem, st);
+        case 1: return launch_fused<SPL, kThreads, true, false>(a, smem, st);
+        default: return launch_fused<SPL, kThreads, true, true>(a, smem, st);
+    }
+}
+
+}  // namespace pgasr

@@ -1,0 +1,8 @@
+// pg_ctc_fused_kernel<4, 512, *, *>: 4 CTC states per lane (see fused_impl.cuh)
+#include "fused_impl.cuh"
+
+namespace pgasr {
+int launch_fused_spl4(int mode, FusedArgs& a, size_t smem, cudaStream_t st) {
+    return launch_fused_modes<4, 512>(mode, a, smem, st);
+}
+}  // namespace pgasr

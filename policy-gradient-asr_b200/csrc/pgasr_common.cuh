@@ -31,7 +31,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 // Optional phase timing (build with -DPGASR_TIMING; tools/phase_timing.py): clock64 stamps of CTA ticket 0.
 #ifdef PGASR_TIMING
-static __device__ long long g_dbg[64];   // one copy per translation unit; fused.cu's is the one read back
+static __device__ long long g_dbg[64];   // one copy per translation unit; fused_spl8.cu's is the one read back
 #define PGASR_STAMP(cond, slot) do { if (cond) ::pgasr::g_dbg[slot] = clock64(); } while (0)
 #define PGASR_ACCUM(cond, slot, v) do { if (cond) ::pgasr::g_dbg[slot] += (v); } while (0)
 #else

@@ -640,3 +640,14 @@ def test_step_empty_utterances_and_nonzero_blank(cuda):
     assert np.array_equal(out["rewards"].cpu().numpy(), R_ref)
     assert np.abs(out["nll"].cpu().numpy() / nll_ref - 1).max() < RTOL
     assert rel_err(out["dlogits"].cpu().numpy(), dl_ref) < RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V,K,L,reward,baseline", [(2, 1000, 30, 64, 120, "ed", "mean"), (2, 2000, 30, 16, 100, "cer", "loo"),
+                                                        (3, 1300, 12, 8, 250, "ed", "none"), (2, 2000, 30, 4, 400, "ed", "mean")])
+def test_step_long_utterances_single_launch(cuda, B, T, V, K, L, reward, baseline):
+    """Long T / large K: both roles stream (no [T][V] tile in shared memory), still one launch, same parity bar."""
+    from pgasr_b200 import _native
+    n0 = _native.lib().pgasr_launch_count()
+    step_case(cuda, B, T, V, K, L, seed=T + K, ragged=True, regime="random", reward=reward, baseline=baseline)
+    assert _native.lib().pgasr_launch_count() - n0 == 1
