@@ -35,9 +35,10 @@ def _need(t, dtype, name, ndim=None):
 def _opt_i32(t, name, n, device):
     if t is None:
         return None
-    if not isinstance(t, torch.Tensor):
-        t = torch.as_tensor(t)
-    t = t.to(device=device, dtype=torch.int32).contiguous()
+    if not (isinstance(t, torch.Tensor) and t.dtype == torch.int32 and t.device == device and t.is_contiguous()):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(t)
+        t = t.to(device=device, dtype=torch.int32).contiguous()
     if t.numel() != n:
         raise ValueError(f"{name} must have {n} entries, got {t.numel()}")
     return t
@@ -49,6 +50,8 @@ def as_targets(targets, device):
         targets = torch.as_tensor(targets)
     if targets.dim() != 2:
         raise ValueError("targets must be [B, Lmax]")
+    if targets.dtype == torch.int32 and targets.device == device and targets.is_contiguous():
+        return targets
     return targets.to(device=device, dtype=torch.int32).contiguous()
 
 
@@ -268,12 +271,13 @@ def pg_ctc_step(logits, targets, input_lengths=None, target_lengths=None, K=16, 
     if workspace is None or workspace.key != (B, T, V, K, Lmax):
         workspace = StepWorkspace(B, T, V, K, Lmax, dev)
     out = {"loss": torch.empty((1,), dtype=torch.float32, device=dev), "dlogits": torch.empty_like(logits)}
-    shapes = {"rewards": ((B, K), torch.float32), "logp": ((B, K), torch.float32),
-              "hyp_len": ((B, K), torch.int32), "dist": ((B, K), torch.int32),
-              "nll": ((B,), torch.float32), "samples": ((B, K, T), torch.uint8)}
     for name in want:
-        shp, dt = shapes[name]
-        out[name] = torch.empty(shp, dtype=dt, device=dev)
+        if name == "samples":
+            out[name] = torch.empty((B, K, T), dtype=torch.uint8, device=dev)
+        elif name == "nll":
+            out[name] = torch.empty((B,), dtype=torch.float32, device=dev)
+        else:
+            out[name] = torch.empty((B, K), dtype=torch.int32 if name in ("hyp_len", "dist") else torch.float32, device=dev)
     _native.call("pgasr_pg_ctc_step", _ptr(logits), _ptr(targets), _ptr(in_len), _ptr(tg_len), _ptr(uniforms),
                  int(seed) & (2**64 - 1), B, T, V, K, Lmax, int(blank), REWARD_MODES[reward],
                  BASELINE_MODES[baseline], float(baseline_value), float(pg_weight), float(ctc_weight),
