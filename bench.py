@@ -252,7 +252,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     step_bytes = B * algorithmic_bytes_per_utt(T, V, L, K)       # 120 540 B/utt at the headline shape
     achieved = step_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "pg_ctc_fused_kernel<8,512> (the whole step: 1 launch)",
+    roofline = {"bound": "hbm", "kernel": "pg_ctc_fused_kernel<8,512,tile,tile> (the whole step: 1 launch)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peak_src == "measured" else peak_src,
                 "traffic": traffic_from_profile(f"B={B},T={T},V={V},K={K},L={L}"),
