@@ -446,7 +446,8 @@ __device__ __forceinline__ double lds_f64_v(unsigned addr) {
 template <int SPL, bool kAlpha>
 struct CtcWalk {
     CtcLane<SPL> st;
-    double h0, h1;                // halo values for the frame about to be computed
+    double h0, h1;                // halo value for the frame about to be computed (h1: unused, kept zero)
+    double skip_prev;             // beta: skip factor of the PREVIOUS lane's last label state into this lane's state 1
     double pb_n, p_n[SPL / 2];    // probabilities of the frame about to be computed (loaded one frame ahead)
     unsigned pa_b, pa[SPL / 2];   // running shared-memory addresses of this lane's probabilities: the frame after
     int rstride;
@@ -480,16 +481,18 @@ __device__ __forceinline__ void ctc_walk_issue_group(CtcWalk<SPL, kAlpha>& w, un
 }
 
 
+// One value crosses each lane boundary per frame.  alpha: the neighbour's last state (it feeds both of this lane's
+// first two states).  beta: the lane's last (label) state needs the next lane's first TWO states, b(s+1) and
+// skip * b(s+2); the next lane knows that skip factor (skip_prev) and sends the sum, so it is one shuffle as well.
 template <int SPL, bool kAlpha>
 __device__ __forceinline__ void ctc_walk_halo(CtcWalk<SPL, kAlpha>& w) {
     if (kAlpha) {
         w.h0 = __shfl_up_sync(kFull, w.st.a[SPL - 1], 1);
     } else {
-        w.h0 = __shfl_down_sync(kFull, w.st.a[0], 1);
-        w.h1 = __shfl_down_sync(kFull, w.st.a[1], 1);
+        w.h0 = __shfl_down_sync(kFull, fma(w.skip_prev, w.st.a[1], w.st.a[0]), 1);
     }
     w.h0 = w.edge ? 0.0 : w.h0;
-    w.h1 = w.edge ? 0.0 : w.h1;
+    w.h1 = 0.0;
 }
 
 template <int SPL, bool kAlpha>
@@ -579,6 +582,11 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
     ctc_lane_init<SPL, kAlpha>(w.st, lab_u, L, V);
     w.edge = kAlpha ? lane == 0 : lane == 31;
     w.act = lane * SPL < S;
+    w.skip_prev = 0.0;
+    if (!kAlpha && lane > 0) {
+        const int li = (lane * SPL) / 2 - 1;              // last label of the previous lane; this lane's state 1 is label li + 1
+        if (li + 1 < L && lab_u[li + 1] != lab_u[li]) w.skip_prev = 1.0;
+    }
     const bool dbg = ring.dbg && lane == 0;
     PGASR_STAMP(dbg, kAlpha ? 10 : 14);
 

@@ -651,3 +651,21 @@ def test_step_long_utterances_single_launch(cuda, B, T, V, K, L, reward, baselin
     n0 = _native.lib().pgasr_launch_count()
     step_case(cuda, B, T, V, K, L, seed=T + K, ragged=True, regime="random", reward=reward, baseline=baseline)
     assert _native.lib().pgasr_launch_count() - n0 == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V,K,L", [(64, 500, 30, 16, 100), (8, 1000, 30, 4, 200), (3, 77, 9, 3, 12)])
+def test_step_does_not_depend_on_stale_workspace(cuda, B, T, V, K, L):
+    """Every lattice row a gradient worker reads must have been written in THIS launch: the workspace is poisoned
+    (all bits set = NaN) between steps, so a row read before the other direction stored it would surface as NaN or
+    as a difference from the clean run (the soak test alone cannot see it: identical steps leave identical rows)."""
+    from pgasr_b200 import functional as F
+    lg, tg, il, tl, _ = make_batch(B, T, V, K, L, seed=31, ragged=True)
+    lg, tg, il, tl = dev_t(lg, cuda), dev_t(tg, cuda), dev_t(il, cuda), dev_t(tl, cuda)
+    ref = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=5, want=("nll",))
+    ws = ref["workspace"]
+    for i in range(20):
+        ws.buf[65536:].fill_(0xFF)                       # the control block at the front stays armed
+        out = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=5, workspace=ws, want=("nll",))
+        assert bool(torch.isfinite(out["dlogits"]).all())
+        assert torch.equal(out["dlogits"], ref["dlogits"]) and torch.equal(out["nll"], ref["nll"])

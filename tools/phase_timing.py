@@ -31,6 +31,7 @@ for mode, (wp, wc) in {"both": (1.0, 1.0), "ctc": (0.0, 1.0), "pg": (1.0, 0.0)}.
     print(f"== {mode} (cycles)")
     if wc:
         print(f" ctc: zero-rows {d[1]-d[0]}  softmax-tile {d[2]-d[1]}  lattice+grad {d[3]-d[2]}  total {d[3]-d[0]}")
+        print(f" walker start after the tile barrier: alpha +{d[10]-d[2]}  beta +{d[14]-d[2]}   mid barrier passed at: alpha +{d[12]-d[2]}  beta +{d[16]-d[2]}")
         print(f" alpha walker: first-half {d[11]-d[10]}  mid-wait {d[12]-d[11]}  second-half {d[13]-d[12]}")
         print(f" beta  walker: first-half {d[15]-d[14]}  mid-wait {d[16]-d[15]}  second-half {d[17]-d[16]}")
         print(f" alpha worker0: waiting {d[20]}  busy {d[21]}   beta worker0: waiting {d[22]}  busy {d[23]}")
