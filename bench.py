@@ -182,6 +182,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if not os.path.exists(_native.LIB_PATH):             # the library normally travels with the snapshot; else build it here
+        if rank == 0:
+            import __graft_entry__
+            __graft_entry__.build()
+        if world > 1:
+            dist.barrier()
     _native.lib()
     assert _native.lib().pgasr_device_check() == 0, "not an sm_100 device"
 
