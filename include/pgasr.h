@@ -111,6 +111,8 @@ PGASR_API int pgasr_pg_grad(const uint8_t* samples, const float* adv, const floa
  * nll[b] = -log p(targets[b] | logits[b]); dlogits (+)= grad_scale * d nll[b] / d logits[b].
  * probs: softmax of logits if the caller already has it (pgasr_softmax_sample), else NULL and the
  * kernel computes it into its workspace.  No valid alignment: nll = +inf, zero gradient.
+ * With logits given, accumulate == 0 and V <= 32 this is the CTC role of the single-launch kernel below (walker and
+ * gradient-worker warps, any T); otherwise the classic one-CTA-per-utterance kernel.
  * Lmax <= 511.  workspace: pgasr_ctc_workspace_bytes(B,T,V,Lmax) bytes, 256-byte aligned.       */
 PGASR_API size_t pgasr_ctc_workspace_bytes(int B, int T, int V, int Lmax);
 PGASR_API int pgasr_ctc_loss_grad(const float* logits, const float* probs, const int32_t* targets,
@@ -134,7 +136,9 @@ PGASR_API int pgasr_nll_sum_backward(const int64_t* target, const float* grad_ou
  * Optional outputs (NULL to skip): rewards, logp, hyp_len, dist, nll, samples.
  * workspace: pgasr_pg_ctc_step_workspace_bytes(B,T,V,K,Lmax) bytes, 256-byte aligned, armed ONCE with
  * pgasr_pg_ctc_step_workspace_init before its first use (and again after a step that returned an error);
- * one workspace serves one stream at a time.  V <= 32, K <= 64.                                   */
+ * one workspace serves one stream at a time.  V <= 32, K <= 64.  One kernel launch for every shape whose sample
+ * buffers fit an SM (2 K T <= ~215 KB); targets / in_len / tgt_len and the small outputs may live in pinned host
+ * memory mapped into the device (they are read once per CTA / written once).                       */
 PGASR_API size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax);
 PGASR_API int pgasr_pg_ctc_step_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 PGASR_API int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, const int32_t* in_len,
