@@ -448,8 +448,9 @@ struct CtcWalk {
     CtcLane<SPL> st;
     double h0, h1;                // halo value for the frame about to be computed (h1: unused, kept zero)
     double skip_prev;             // beta: skip factor of the PREVIOUS lane's last label state into this lane's state 1
-    double pb_n, p_n[SPL / 2];    // probabilities of the frame about to be computed (loaded one frame ahead)
-    unsigned pa_b, pa[SPL / 2];   // running shared-memory addresses of this lane's probabilities: the frame after
+    double pb_n, p_n[SPL / 2];    // probabilities of the frame about to be computed   (both sets were loaded TWO frames
+    double pb_m, p_m[SPL / 2];    // probabilities of the frame after it                ahead of their use)
+    unsigned pa_b, pa[SPL / 2];   // running shared-memory addresses of this lane's probabilities: two frames on
     int rstride;
     bool edge;
     bool act;                     // this lane holds at least one state < S (lanes beyond never touch the lattice)
@@ -526,13 +527,19 @@ __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*
         }
         ++w.gstep;
     }
+    // The loads are volatile asm issued two frames before their values are multiplied in: measured on the bare frame
+    // loop (tools/walk_probe.cu) plain loads cost 127 cycles per frame wherever they are written (ptxas sinks them next
+    // to their consumers), volatile loads one frame ahead 94, two frames ahead 79; the arithmetic alone is 52.
     double p[SPL / 2];
     const double pb = w.pb_n;
 #pragma unroll
     for (int i = 0; i < SPL / 2; ++i) p[i] = w.p_n[i];
-    w.pb_n = kGT ? lds_f64_v(w.pa_b) : lds_f64(w.pa_b);   // next frame's values fly while this frame is computed
+    w.pb_n = w.pb_m;
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) w.p_n[i] = kGT ? lds_f64_v(w.pa[i]) : lds_f64(w.pa[i]);
+    for (int i = 0; i < SPL / 2; ++i) w.p_n[i] = w.p_m[i];
+    w.pb_m = lds_f64_v(w.pa_b);
+#pragma unroll
+    for (int i = 0; i < SPL / 2; ++i) w.p_m[i] = lds_f64_v(w.pa[i]);
     if (kGT) {
         w.pa_b = w.ring_base | ((w.pa_b + w.rstride) & w.ring_mask);
 #pragma unroll
@@ -615,18 +622,20 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
     // every tile load below takes its address from this opaque copy, so none of them (plain asm, free to be
     // scheduled) can be moved above this point, i.e. above the barrier that published the tile
     asm volatile("mov.u32 %0, %0;\n" : "+r"(row0) : : "memory");
-    w.pb_n = lds_f64_v(row0 + (unsigned)(blank * 8));
+    {
+        // frame 0 and frame 1 now, the running addresses point at frame 2
+        const unsigned row1 = kGT ? (w.ring_base | ((row0 + w.rstride) & w.ring_mask)) : row0 + w.rstride;
+        const unsigned row2 = kGT ? (w.ring_base | ((row1 + w.rstride) & w.ring_mask)) : row1 + w.rstride;
+        // (in ring mode row0 is ring_base + slot * row bytes: the column offsets below stay inside the row)
+        w.pb_n = lds_f64_v(row0 + (unsigned)(blank * 8));
+        w.pb_m = lds_f64_v(row1 + (unsigned)(blank * 8));
+        w.pa_b = row2 + (unsigned)(blank * 8);
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) w.p_n[i] = lds_f64_v(row0 + (unsigned)(w.st.loff[i] * 8));
-    if (kGT) {
-        w.pa_b = w.ring_base | ((row0 + (unsigned)(blank * 8) + w.rstride) & w.ring_mask);
-#pragma unroll
-        for (int i = 0; i < SPL / 2; ++i)
-            w.pa[i] = w.ring_base | ((row0 + (unsigned)(w.st.loff[i] * 8) + w.rstride) & w.ring_mask);
-    } else {
-        w.pa_b = row0 + (unsigned)(blank * 8) + w.rstride;
-#pragma unroll
-        for (int i = 0; i < SPL / 2; ++i) w.pa[i] = row0 + (unsigned)(w.st.loff[i] * 8) + w.rstride;
+        for (int i = 0; i < SPL / 2; ++i) {
+            w.p_n[i] = lds_f64_v(row0 + (unsigned)(w.st.loff[i] * 8));
+            w.p_m[i] = lds_f64_v(row1 + (unsigned)(w.st.loff[i] * 8));
+            w.pa[i] = row2 + (unsigned)(w.st.loff[i] * 8);
+        }
     }
     // virtual vector before the first frame: the recurrence turns it into the CTC start (alpha: states 0,1;
     // beta: states S-1,S-2) -- see DESIGN.md "CTC spec"

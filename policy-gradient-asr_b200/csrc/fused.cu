@@ -32,7 +32,7 @@ static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
     const int G = (threads / 32 - 2) / 2, per = (batch_of(spl) + G - 1) / G;
     const size_t pring = (size_t)kPRows * (RS <= 32 ? 32 : 64) * 8;
-    const size_t tile = gt ? 3 * pring /* two rings + alignment slack */ : (size_t)(T + 2) * RS * sizeof(double);
+    const size_t tile = gt ? 3 * pring /* two rings + alignment slack */ : (size_t)(T + 4) * RS * sizeof(double);
     return tile + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int);
 }
 

@@ -49,8 +49,8 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     const int T = a.T, V = a.V;
     const int RS = ctc_row_stride(V);
     // shared-memory carve-up (see fused_smem)
-    // [T][RS] between two guard rows: the walkers load the probabilities one frame ahead and run one row past
-    // either end (the guard values are loaded and never used)
+    // [T][RS] between two pairs of guard rows: the walkers load the probabilities two frames ahead and run two rows
+    // past either end (the guard values are loaded and never used)
     const int RSR = RS <= 32 ? 32 : 64;                                  // ring row stride (power of two)
     const size_t pring_bytes = (size_t)kPRows * RSR * 8;
     double* tile;
@@ -66,8 +66,8 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         pring_b = reinterpret_cast<double*>(smem_raw + pad + pring_bytes);
         p = smem_raw + pad + 2 * pring_bytes;
     } else {
-        tile = reinterpret_cast<double*>(smem_raw) + RS;
-        p = smem_raw + (size_t)(T + 2) * RS * 8;
+        tile = reinterpret_cast<double*>(smem_raw) + 2 * RS;
+        p = smem_raw + (size_t)(T + 4) * RS * 8;
     }
     unsigned char* const stage_base = p;
     GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
