@@ -10,6 +10,12 @@ __device__ __forceinline__ double lds_v(unsigned addr) {
     return v;
 }
 
+__device__ __forceinline__ double lds_v2(unsigned addr) {      // volatile, but no memory clobber
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 // 0: arithmetic only, 1: + halo shuffle, 2: + 5 shared loads of the next frame's probabilities (plain C++),
 // 3: loads two frames ahead (plain C++), 4: volatile-asm loads one frame ahead, 5: volatile-asm loads two frames ahead,
 // 6: as 2 without the shuffle
@@ -26,6 +32,8 @@ __global__ void probe(double* out, long long* cyc, int frames, const double* pta
     for (int i = 0; i < 5; ++i) pn[i] = pn2[i] = 0.2501 + 1e-4 * i;
     double h0 = 0.5;
     int row = 0, mxp = 0;
+    double2* latp = lat;
+    double bcp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t0 = clock64();
     for (int f = 0; f < frames; ++f) {
 #pragma unroll
@@ -35,7 +43,14 @@ __global__ void probe(double* out, long long* cyc, int frames, const double* pta
 #pragma unroll
             for (int i = 0; i < 5; ++i) pn[i] = tile[row * 32 + ((lane * 5 + i * 7) & 31)];
         }
-        if (MODE == 3 || MODE == 5 || MODE >= 7) {
+        if (MODE == 17 || MODE == 18) {
+            row = (row + 1) & 63;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                pn[i] = pn2[i];
+                pn2[i] = lds_v2(tbase + (unsigned)((row * 32 + ((lane * 5 + i * 7) & 31)) * 8));
+            }
+        } else if (MODE == 3 || MODE == 5 || MODE >= 7) {   // (modes 7+ build on mode 5)
             row = (row + 1) & 63;
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
@@ -57,6 +72,34 @@ __global__ void probe(double* out, long long* cyc, int frames, const double* pta
         }
         a[1] = fma(sk[0], h0, a[1] + a[0]);
         a[0] = a[0] + h0;
+        if (MODE == 16 || MODE == 18) {                   // store the PREVIOUS frame's sums from a copy, keep a copy of this frame's
+            double2* q = latp + lane;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) q[jj * 32] = make_double2(bcp[2 * jj], bcp[2 * jj + 1]);
+            latp += 128;
+            if ((f & 255) == 255) latp = lat;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bcp[j] = a[j];
+        }
+        if (MODE >= 12 && MODE <= 15) {                   // store variants on top of mode 5
+            double2* lp = lat + (size_t)(f & 255) * 128 + lane;
+            if (MODE == 12) {                             // 4 STG.128, no exponent
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) lp[jj * 32] = make_double2(a[2 * jj], a[2 * jj + 1]);
+            } else if (MODE == 13) {                      // one STG.128 only
+                lp[0] = make_double2(a[0], a[1]);
+            } else if (MODE == 14) {                      // 4 STS.128 to shared memory instead
+                double2* sp = reinterpret_cast<double2*>(tile) + ((f & 3) * 128) + lane;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) sp[jj * 32] = make_double2(a[2 * jj], a[2 * jj + 1]);
+            } else {                                      // running pointer instead of index arithmetic
+                double2* q = latp + lane;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) q[jj * 32] = make_double2(a[2 * jj], a[2 * jj + 1]);
+                latp += 128;
+                if ((f & 255) == 255) latp = lat;
+            }
+        }
         if (MODE == 7 || MODE == 9) {                     // lattice row: 4 x 16-byte stores per lane, one exponent per frame
             double2* lp = lat + (size_t)(f & 255) * 128 + lane;
 #pragma unroll
@@ -144,7 +187,12 @@ int main() {
     run<7>("mode 5 + lattice stores (4 STG.128 + exponent)", 1);
     run<8>("mode 5 + rescale test every 8 frames", 1);
     run<9>("mode 5 + stores + rescale", 1);
-    run<10>("mode 5 + pipelined rescale (measure, apply 4 frames later)", 1);
-    run<11>("mode 10 + stores, exponent once per 8 frames", 1);
+    run<12>("mode 5 + 4 STG.128 (no exponent store)", 1);
+    run<13>("mode 5 + 1 STG.128", 1);
+    run<14>("mode 5 + 4 STS.128 (shared memory)", 1);
+    run<15>("mode 5 + 4 STG.128 through a running pointer", 1);
+    run<16>("mode 5 + 4 STG.128 of the previous frame from copies", 1);
+    run<17>("loads volatile without memory clobber, no stores", 1);
+    run<18>("same + delayed stores from copies", 1);
     return 0;
 }
