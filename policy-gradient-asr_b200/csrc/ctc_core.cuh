@@ -431,6 +431,28 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
     return v;
 }
 
+// L2 residency hints for the half-lattice (written once, read once ~30 us later, then dead; the workspace is reused
+// every step): stores ask L2 to keep the lines (evict_last), the single read demotes them (evict_first).  Without
+// the hints ~11 MB of the 52 MB lattice were written back to DRAM per step before they were read (ncu).
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_lattice(double2* ptr, double x, double y, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;\n" ::"l"(ptr), "d"(x), "d"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double2 ld_lattice(const double2* ptr, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;\n" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
+
 // volatile flavour for the streaming ring: ordered after the cp.async waits (volatile asm keeps its order)
 __device__ __forceinline__ double lds_f64_v(unsigned addr) {
     double v;
@@ -454,6 +476,7 @@ struct CtcWalk {
     int rstride;
     bool edge;
     bool act;                     // this lane holds at least one state < S (lanes beyond never touch the lattice)
+    unsigned long long l2pol;     // L2 cache policy of the lattice stores
     // global-tile mode (long utterances): the probability rows stream from global memory through a 32-row ring
     unsigned ring_base, ring_mask;        // shared-memory address of the ring (aligned to its size), size - 1
     const double* tile_g;                 // row 0 of this utterance's fp64 tile in global memory (guard rows around it)
@@ -554,7 +577,7 @@ __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*
     if (kFirst) {
         if (w.act) {
 #pragma unroll
-            for (int jj = 0; jj < SPL / 2; ++jj) dst[jj * 32] = make_double2(w.st.a[2 * jj], w.st.a[2 * jj + 1]);
+            for (int jj = 0; jj < SPL / 2; ++jj) st_lattice(dst + jj * 32, w.st.a[2 * jj], w.st.a[2 * jj + 1], w.l2pol);
         }
     }
 #endif
@@ -589,6 +612,7 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
     ctc_lane_init<SPL, kAlpha>(w.st, lab_u, L, V);
     w.edge = kAlpha ? lane == 0 : lane == 31;
     w.act = lane * SPL < S;
+    w.l2pol = l2_policy_evict_last();
     w.skip_prev = 0.0;
     if (!kAlpha && lane > 0) {
         const int li = (lane * SPL) / 2 - 1;              // last label of the previous lane; this lane's state 1 is label li + 1
@@ -711,6 +735,7 @@ struct CtcWorker {
     double2 o[kPer][SPL / 2];
     int eo[kPer];
     double prow[kPer];            // global-tile mode: p_t(lane) of the frame, fetched with the lattice row
+    unsigned long long l2pol;     // L2 cache policy of the lattice loads (evict_first: the row is dead after this read)
 };
 
 template <int SPL, int G, bool kAlpha, bool kGT = false>
@@ -720,6 +745,7 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
                                                  int RS = 0) {
     const int lane = threadIdx.x & 31;
     const bool act = lane * SPL < S;                      // the other direction never stored the lanes beyond S
+    const unsigned long long pol = wk.l2pol;
 #pragma unroll
     for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kPer; ++r) {
         const int q = min(nb * kBatchOf<SPL> + min(g + r * G, kBatchOf<SPL> - 1), n2 - 1);   // clamped: a stale row is loaded, never used
@@ -732,7 +758,7 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
         wk.eo[r] = 0; (void)lp;
 #else
 #pragma unroll
-        for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = act ? __ldcg(lp + jj * 32) : make_double2(0.0, 0.0);
+        for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = act ? ld_lattice(lp + jj * 32, pol) : make_double2(0.0, 0.0);
         wk.eo[r] = __ldcg(exp_u + t);
         if (kGT) wk.prow[r] = __ldcg(tile + (size_t)t * RS + lane);
 #endif
@@ -899,6 +925,7 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
     nm.tA = nm.tB = nm.tWait = nm.tBusy = 0;
     const int nbatch = (n2 + kBatchOf<SPL> - 1) / kBatchOf<SPL>;
     CtcWorker<SPL, G, kAlpha> wk;
+    wk.l2pol = l2_policy_evict_first();
     int gb[kPer];
     const int S = 2 * L + 1;
     double prow[kPer];
