@@ -210,7 +210,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     uint8_t* hyp_s = smem_raw + off;                off += (size_t)K * Tp;            // [K][Tp]
     uint32_t* peq = reinterpret_cast<uint32_t*>(smem_raw + off); off += (size_t)(V + 1) * W * 4;
     off = (off + 15) & ~(size_t)15;
-    float* warp_acc = reinterpret_cast<float*>(smem_raw + off);  off += (size_t)kWarps * kFusedMaxK * 4;
+    double* warp_acc = reinterpret_cast<double*>(smem_raw + off); off += (size_t)kWarps * kFusedMaxK * 8;   // log-prob partial sums
     float* adv_s = reinterpret_cast<float*>(smem_raw + off);     off += kFusedMaxK * 4;
     int* hlen_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
     int* dist_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
@@ -238,7 +238,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
         const int j = threadIdx.x + q * kThreads;
         ref_r[q] = j < m ? ref[j] : -1;
     }
-    for (int i = threadIdx.x; i < kWarps * kFusedMaxK; i += kThreads) warp_acc[i] = 0.0f;
+    for (int i = threadIdx.x; i < kWarps * kFusedMaxK; i += kThreads) warp_acc[i] = 0.0;
     for (int i = threadIdx.x; i < (V + 1) * W; i += kThreads) peq[i] = 0u;
     cp_async_wait<0>();
     __syncthreads();
@@ -292,7 +292,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
                 if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi;
             }
             term = warp_sum(term);
-            if (lane == 0) warp_acc[warp * kFusedMaxK + k] += term;
+            if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)term;   // across passes and warps in fp64: log p ~ -1000
         }
     }
     __syncthreads();
@@ -341,37 +341,41 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     PGASR_STAMP(dbg, 34);
     // ---- P4: rewards, baseline, advantages, loss term (warp 0) -----------------------------------
     if (warp == 0) {
-        float sumR = 0.0f;
+        // rewards are fp32 by contract (bit exact with the oracle); baseline, advantage and the loss term are fp64:
+        // an fp32 rounding of A (1e-7 relative) times log p ~ -1000 would already show in the scalar loss
+        double sumR = 0.0;
         for (int k = lane; k < K; k += 32) {
             float R = -(float)dist_s[k];
             if (a.reward_mode == PGASR_REWARD_NEG_CER) R = __fdiv_rn(R, (float)m);
             adv_s[k] = R;
-            sumR += R;
+            sumR += (double)R;
         }
         sumR = warp_sum(sumR);
-        float term = 0.0f, sumA = 0.0f;
+        double term = 0.0;
+        float sumA = 0.0f;
         for (int k = lane; k < K; k += 32) {
             const float R = adv_s[k];
-            float base = 0.0f;
-            if (a.baseline_mode == PGASR_BASELINE_MEAN) base = sumR / (float)K;
-            else if (a.baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumR - R) / (float)(K - 1) : 0.0f;
-            else if (a.baseline_mode == PGASR_BASELINE_VALUE) base = a.baseline_value;
-            const float A = R - base;
-            float lp = 0.0f;
+            double base = 0.0;
+            if (a.baseline_mode == PGASR_BASELINE_MEAN) base = sumR / (double)K;
+            else if (a.baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumR - (double)R) / (double)(K - 1) : 0.0;
+            else if (a.baseline_mode == PGASR_BASELINE_VALUE) base = (double)a.baseline_value;
+            const double Ad = (double)R - base;
+            const float A = (float)Ad;
+            double lp = 0.0;
             for (int w = 0; w < kWarps; ++w) lp += warp_acc[w * kFusedMaxK + k];
-            term += -A * lp;
+            term += -Ad * lp;
             sumA += A;
             adv_s[k] = A;
             const size_t o = (size_t)b * K + k;
             if (a.rewards) a.rewards[o] = R;
-            if (a.logp) a.logp[o] = lp;
+            if (a.logp) a.logp[o] = (float)lp;
             if (a.hyp_len) a.hyp_len[o] = hlen_s[k];
             if (a.dist) a.dist[o] = dist_s[k];
         }
         term = warp_sum(term);
         sumA = warp_sum(sumA);
         if (lane == 0) {
-            a.loss_terms[b] = term;
+            a.loss_terms[b] = (float)term;
             misc_s[0] = sumA;
         }
     }

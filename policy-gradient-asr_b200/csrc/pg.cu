@@ -15,27 +15,28 @@ __global__ void pg_advantages_kernel(const int32_t* __restrict__ dist, const int
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
     const int m = tgt_len ? tgt_len[b] : Lmax;
-    float sumR = 0.0f;
+    // rewards are fp32 by contract; baseline, advantage and the loss term in fp64 (A times log p ~ -1000 cancels heavily)
+    double sumR = 0.0;
     for (int k = lane; k < K; k += 32) {
         float R = -(float)dist[(size_t)b * K + k];
         if (reward_mode == PGASR_REWARD_NEG_CER) R = __fdiv_rn(R, (float)m);
         rewards[(size_t)b * K + k] = R;
-        sumR += R;
+        sumR += (double)R;
     }
     sumR = warp_sum(sumR);
-    float term = 0.0f;
+    double term = 0.0;
     for (int k = lane; k < K; k += 32) {
         const float R = rewards[(size_t)b * K + k];
-        float base = 0.0f;
-        if (baseline_mode == PGASR_BASELINE_MEAN) base = sumR / (float)K;
-        else if (baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumR - R) / (float)(K - 1) : 0.0f;
-        else if (baseline_mode == PGASR_BASELINE_VALUE) base = baseline_value;
-        const float A = R - base;
-        adv[(size_t)b * K + k] = A;
-        term += -A * logp[(size_t)b * K + k];
+        double base = 0.0;
+        if (baseline_mode == PGASR_BASELINE_MEAN) base = sumR / (double)K;
+        else if (baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumR - (double)R) / (double)(K - 1) : 0.0;
+        else if (baseline_mode == PGASR_BASELINE_VALUE) base = (double)baseline_value;
+        const double Ad = (double)R - base;
+        adv[(size_t)b * K + k] = (float)Ad;
+        term += -Ad * (double)logp[(size_t)b * K + k];
     }
     term = warp_sum(term);
-    if (lane == 0 && loss_terms) loss_terms[b] = term;
+    if (lane == 0 && loss_terms) loss_terms[b] = (float)term;
 }
 
 // one thread per logit: dlogits[b,t,v] (+)= scale * (p * sumA - sum_k A_k [pi_k == v])

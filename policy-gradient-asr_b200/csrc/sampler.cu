@@ -14,13 +14,13 @@ softmax_sample_kernel(const float* __restrict__ logits, const int32_t* __restric
                       const float* __restrict__ uniforms, uint64_t seed, int T, int V, int K,
                       uint8_t* __restrict__ samples, float* __restrict__ logp,
                       float* __restrict__ probs) {
-    __shared__ float warp_acc[kSamplerThreads / kWarp][kSamplerMaxK];
+    __shared__ double warp_acc[kSamplerThreads / kWarp][kSamplerMaxK];   // log p ~ -1000: partial sums in fp64
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int Tb = in_len ? in_len[b] : T;
     Tb = min(max(Tb, 0), T);
     for (int i = threadIdx.x; i < (kSamplerThreads / kWarp) * kSamplerMaxK; i += blockDim.x)
-        (&warp_acc[0][0])[i] = 0.0f;
+        (&warp_acc[0][0])[i] = 0.0;
     __syncthreads();
 
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -85,14 +85,14 @@ softmax_sample_kernel(const float* __restrict__ logits, const int32_t* __restric
                 samples[((size_t)b * K + k) * T + t] = 0;
             }
             term = warp_sum(term);
-            if (lane == 0) warp_acc[warp][k] += term;
+            if (lane == 0) warp_acc[warp][k] += (double)term;
         }
     }
     __syncthreads();
     if (threadIdx.x < K) {
-        float s = 0.0f;
+        double s = 0.0;
         for (int w = 0; w < kSamplerThreads / kWarp; ++w) s += warp_acc[w][threadIdx.x];
-        logp[(size_t)b * K + threadIdx.x] = s;
+        logp[(size_t)b * K + threadIdx.x] = (float)s;
     }
 }
 

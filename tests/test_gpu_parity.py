@@ -669,3 +669,15 @@ def test_step_does_not_depend_on_stale_workspace(cuda, B, T, V, K, L):
         out = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=5, workspace=ws, want=("nll",))
         assert bool(torch.isfinite(out["dlogits"]).all())
         assert torch.equal(out["dlogits"], ref["dlogits"]) and torch.equal(out["nll"], ref["nll"])
+
+
+@pytest.mark.gpu
+def test_step_randomised_shapes_and_modes(cuda):
+    """tools/fuzz_step.py: random (B, T, V, K, L, reward, baseline, weights, regime, Philox or injected uniforms) across
+    the boundaries between the kernel's modes, every case against the C oracle with the usual bars."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_step.py"), "60", "5"], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "all 60 cases passed" in r.stdout

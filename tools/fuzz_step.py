@@ -1,0 +1,59 @@
+"""Randomised parity sweep of the whole step against the C oracle across the mode boundaries (states per lane 4/8/16/32,
+tile vs streaming roles, ragged lengths, every reward/baseline mode, Philox vs injected uniforms).
+    python tools/fuzz_step.py [cases] [seed]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from oracle import cport  # noqa: E402
+from pgasr_b200 import functional as F  # noqa: E402
+from tests.synth import make_batch  # noqa: E402
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+dev = torch.device("cuda:0")
+t = lambda a: torch.from_numpy(a).to(dev)
+worst = 0.0
+for case in range(n_cases):
+    L = int(rng.choice([1, 3, 20, 63, 64, 100, 127, 128, 200, 255, 256, 300, 400]))
+    T = int(min(2500, max(L + int(rng.integers(0, 60)), int(rng.choice([L + 5, 2 * L + 9, 60, 333, 500, 801, 1000, 1777])))))
+    V = int(rng.choice([2, 5, 17, 30, 31, 32]))
+    K = int(rng.choice([1, 2, 4, 7, 16, 33, 64]))
+    B = int(rng.choice([1, 2, 3, 5]))
+    if T * K * B * L > 4e8:
+        K = 2
+    reward = str(rng.choice(["ed", "cer"]))
+    baseline = str(rng.choice(["mean", "loo", "none", "value"]))
+    philox = bool(rng.integers(0, 2))
+    regime = str(rng.choice(["random", "peaky"]))
+    w_pg, w_ctc = [(1.0, 1.0), (0.4, 1.7), (1.0, 0.0), (0.0, 1.0)][int(rng.integers(0, 4))]
+    lg, tg, il, tl, uni = make_batch(B, T, V, K, L, seed=int(rng.integers(0, 1 << 30)), ragged=True, regime=regime)
+    kw = dict(reward_mode=F.REWARD_MODES[reward], baseline_mode=F.BASELINE_MODES[baseline], baseline_value=-1.5, w_pg=w_pg, w_ctc=w_ctc)
+    loss_ref, R_ref, nll_ref, dl_ref = cport.pg_ctc_step(lg, tg, il, tl, None if philox else uni, seed=77, K=K, **kw)
+    out = F.pg_ctc_step(t(lg), t(tg), t(il), t(tl), K=K, reward=reward, baseline=baseline, baseline_value=-1.5,
+                        pg_weight=w_pg, ctc_weight=w_ctc, uniforms=None if philox else t(uni), seed=77, want=("rewards", "nll"))
+    g = out["dlogits"].cpu().numpy()
+    err = float(np.abs(g - dl_ref).max() / max(np.abs(dl_ref).max(), 1e-30))
+    ok = err < 1e-4
+    if w_pg:
+        ok = ok and np.array_equal(out["rewards"].cpu().numpy(), R_ref)
+    if w_ctc:
+        nll = out["nll"].cpu().numpy()
+        fin = np.isfinite(nll_ref)
+        ok = ok and np.array_equal(np.isfinite(nll), fin) and (not fin.any() or np.abs(nll[fin] / nll_ref[fin] - 1).max() < 1e-4)
+    if np.isfinite(loss_ref):
+        ok = ok and abs(float(out["loss"]) - loss_ref) <= 1e-4 * abs(loss_ref) + 1e-5
+    worst = max(worst, err)
+    print(f"{'ok  ' if ok else 'FAIL'} B={B} T={T} V={V} K={K} L={L} {reward}/{baseline} philox={philox} {regime} w=({w_pg},{w_ctc}) grad err {err:.2e}",
+          flush=True)
+    if not ok:
+        print("   rewards equal:", bool(np.array_equal(out["rewards"].cpu().numpy(), R_ref)) if w_pg else None,
+              " loss", float(out["loss"]), "ref", loss_ref, " nll", out["nll"].cpu().numpy()[:3], nll_ref[:3])
+        if w_pg and not np.array_equal(out["rewards"].cpu().numpy(), R_ref):
+            d = np.nonzero(out["rewards"].cpu().numpy() != R_ref)
+            print("   reward diffs at", d, out["rewards"].cpu().numpy()[d][:5], R_ref[d][:5], "tgt_len", tl)
+        sys.exit(1)
+print(f"all {n_cases} cases passed, worst gradient error {worst:.2e}")
