@@ -145,28 +145,41 @@ __device__ __forceinline__ void ctc_step(CtcLane<SPL>& st, GradNorm& gn, int ste
 
     // ---- gradient row of frame t ---------------------------------------------------------------
     if (kGrad) {
+        // occupancies in 2^-30 fixed point, with the normalising power of two split between the two factors so that
+        // a(s) o(s) cannot underflow fp64 on its own (same scheme as the gradient workers of the fused kernel)
+        if (!gn.have) {                                   // first gradient frame: fix the normalisation
+            int emax = -1;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                const int ax = (__double2hiint(st.a[j]) >> 20) & 0x7ff, ox = (__double2hiint(o[j]) >> 20) & 0x7ff;
+                if (ax && ox) emax = max(emax, ax + ox);
+            }
+            emax = __reduce_max_sync(kFull, emax);
+            gn.dead = emax < 0;
+            const int ex0 = gn.dead ? 0 : 2046 - emax;
+            const double s1 = pow2i(ex0 >> 1), s2 = pow2i(ex0 - (ex0 >> 1));
+            double z = 0.0;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) z += (st.a[j] * s1) * (o[j] * s2);
+            const double Z0 = warp_sum(z);
+            gn.have = true;
+            gn.dead = gn.dead || !(Z0 > 0.0);
+            gn.invZ0 = gn.dead ? 0.0 : kCtcFix / Z0;
+            gn.E0 = st.E + eo - ex0;
+        }
+        const int ex = st.E + eo - gn.E0;
+        const int h1 = (ex >> 1) - 15;
+        const double s1 = gn.invZ0 * pow2i(h1), s2 = pow2i(ex - h1);
         double w[SPL];
         double zb = 0.0;
 #pragma unroll
         for (int j = 0; j < SPL; ++j) {
-            w[j] = st.a[j] * o[j];
+            w[j] = (st.a[j] * s1) * (o[j] * s2);
             if (!(j & 1)) zb += w[j];
         }
-        if (!gn.have) {                                   // first gradient frame: measure Z0 once
-            double zl = 0.0;
+        const int gb = __reduce_add_sync(kFull, __double2loint(zb + kCtcMagic));
 #pragma unroll
-            for (int j = 1; j < SPL; j += 2) zl += w[j];
-            const double Z0 = warp_sum(zb + zl);
-            gn.have = true;
-            gn.dead = !(Z0 > 0.0);
-            gn.invZ0 = gn.dead ? 0.0 : kCtcFix / Z0;
-            gn.E0 = st.E + eo;
-        }
-        const double c = gn.invZ0 * pow2i(st.E + eo - gn.E0);
-        const int gb = __reduce_add_sync(kFull, __double2loint(fma(zb, c, kCtcMagic)));
-#pragma unroll
-        for (int j = 1; j < SPL; j += 2)
-            atomicAdd(&racc[st.loff[j >> 1]], __double2loint(fma(w[j], c, kCtcMagic)));
+        for (int j = 1; j < SPL; j += 2) atomicAdd(&racc[st.loff[j >> 1]], __double2loint(w[j] + kCtcMagic));
         __syncwarp();
         float* out = dlog_u + (size_t)t * V;
         for (int v = lane; v < V; v += 32) {

@@ -681,3 +681,21 @@ def test_step_randomised_shapes_and_modes(cuda):
                        timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "all 60 cases passed" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V,L", [(4, 40, 7, 9), (2, 900, 12, 255), (2, 1100, 30, 400), (3, 2500, 30, 20), (2, 300, 40, 50)])
+def test_ctc_classic_kernel_path(cuda, B, T, V, L):
+    """The one-CTA-per-utterance kernel (taken for `accumulate`, for V > 32 and for probabilities-only input) keeps the
+    same bar as the walker/worker kernel, including T >> L where alpha * beta underflows fp64 unless the scaling is split."""
+    from pgasr_b200 import functional as F
+    logits, targets, in_len, tgt_len, _ = make_batch(B, T, V, 1, L, seed=T + V, ragged=True)
+    nll_ref, g_ref = cport.ctc_loss_grad(logits, targets, in_len, tgt_len)
+    base = torch.full((B, T, V), 0.25, dtype=torch.float32, device=cuda)
+    nll, g = F.ctc_loss_grad(dev_t(logits, cuda), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda),
+                             grad_scale=0.5, out=base)
+    assert g.data_ptr() == base.data_ptr()
+    nll, g = nll.cpu().numpy(), (g.cpu().numpy() - 0.25) / 0.5
+    fin = np.isfinite(nll_ref)
+    assert np.array_equal(np.isfinite(nll), fin) and np.abs(nll[fin] / nll_ref[fin] - 1).max() < RTOL
+    assert np.abs(g - g_ref).max() / np.abs(g_ref).max() < 2 * RTOL      # (the 0.25 offset costs a few fp32 ulps)
