@@ -699,3 +699,13 @@ def test_ctc_classic_kernel_path(cuda, B, T, V, L):
     fin = np.isfinite(nll_ref)
     assert np.array_equal(np.isfinite(nll), fin) and np.abs(nll[fin] / nll_ref[fin] - 1).max() < RTOL
     assert np.abs(g - g_ref).max() / np.abs(g_ref).max() < 2 * RTOL      # (the 0.25 offset costs a few fp32 ulps)
+
+
+@pytest.mark.gpu
+def test_step_hybrid_path_when_samples_do_not_fit(cuda):
+    """K = 64 at T = 1800: the sample buffers (2 K T bytes) exceed one SM, so the PG part runs as the stand-alone
+    kernels next to the single-launch CTC role; same parity bar, more than one launch."""
+    from pgasr_b200 import _native
+    n0 = _native.lib().pgasr_launch_count()
+    step_case(cuda, 2, 1800, 30, 64, 50, seed=9, ragged=True, regime="random", reward="cer", baseline="loo")
+    assert _native.lib().pgasr_launch_count() - n0 > 1
