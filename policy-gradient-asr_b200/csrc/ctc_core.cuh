@@ -359,8 +359,9 @@ inline int batch_of(int spl) { return spl >= 32 ? 4 : 7; }
 
 template <int SPL>
 struct GradRing {
-    double* slots;                // [2 * kBatch][SPL*32]
+    double* slots;                // [2 * kBatch][SPL*16]: the LABEL states of a frame ([SPL/4][32 lanes] double2)
     int* eslot;                   // [2 * kBatch] exponent of the published values
+    double* norm;                 // [2]: 2^30 / Z0, then (int) E0 and (int) dead -- written by the walker, see ctc_walk_publish_norm
     int bar_full;                 // named barrier ids: bar_full + k, bar_empty + k for buffer k in {0, 1}
     int bar_empty;
     const int* cls_off;           // [V + 1] CSR over classes: label positions li with lab[li] == v
@@ -394,7 +395,9 @@ __device__ __forceinline__ void ctc_build_class_lists(const int32_t* __restrict_
 
 template <int SPL>
 __host__ __device__ inline size_t grad_ring_bytes() {
-    return (size_t)2 * kBatchOf<SPL> * SPL * 32 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15);   // slots + exponents
+    // slots (allocated at twice the size in use: the spare half pads the staging area of the softmax phase) +
+    // exponents + the normalisation block
+    return (size_t)2 * kBatchOf<SPL> * SPL * 32 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15) + 16;
 }
 
 template <int SPL>
@@ -402,6 +405,7 @@ __device__ __forceinline__ GradRing<SPL> grad_ring_carve(unsigned char* p, int b
     GradRing<SPL> r;
     r.slots = reinterpret_cast<double*>(p);
     r.eslot = reinterpret_cast<int*>(p + (size_t)2 * kBatchOf<SPL> * SPL * 32 * 8);
+    r.norm = reinterpret_cast<double*>(p + (size_t)2 * kBatchOf<SPL> * SPL * 32 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15));
     r.bar_full = bar_base;
     r.bar_empty = bar_base + 2;
     r.dbg = false;
@@ -551,7 +555,11 @@ __device__ __forceinline__ void ctc_walk_rescale(CtcWalk<SPL, kAlpha>& w) {
 
 // kFirst: store the pre-emission sums to the lattice (dst = global), else the post-emission values to the ring
 // (dst = shared).  dst advances by `dstride` double2 per frame; edst (exponent per frame) by estride ints.
-template <int SPL, bool kAlpha, bool kFirst, bool kGT = false>
+// Only the LABEL states (odd j) are published: the blank column of the gradient follows from sum_s gamma_t(s) = 1
+// (in 2^-30 fixed point: 2^30 minus the label occupancies), so neither the lattice nor the ring carries the blank
+// states.  kMid: the direction's last first-half frame -- its blank states are stored too (second half of the
+// lattice row), because the other walker measures Z0 = sum_s alpha beta' over ALL states there, once.
+template <int SPL, bool kAlpha, bool kFirst, bool kGT = false, bool kMid = false>
 __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*& dst, ptrdiff_t dstride, int*& edst,
                                                int estride, bool lane0) {
     if (kGT) {
@@ -590,7 +598,12 @@ __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*
     if (kFirst) {
         if (w.act) {
 #pragma unroll
-            for (int jj = 0; jj < SPL / 2; ++jj) st_lattice(dst + jj * 32, w.st.a[2 * jj], w.st.a[2 * jj + 1], w.l2pol);
+            for (int jj = 0; jj < SPL / 4; ++jj) st_lattice(dst + jj * 32, w.st.a[4 * jj + 1], w.st.a[4 * jj + 3], w.l2pol);
+            if (kMid) {
+#pragma unroll
+                for (int jj = 0; jj < SPL / 4; ++jj)
+                    st_lattice(dst + (SPL / 4 + jj) * 32, w.st.a[4 * jj], w.st.a[4 * jj + 2], w.l2pol);
+            }
         }
     }
 #endif
@@ -599,11 +612,54 @@ __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*
     ctc_walk_halo<SPL, kAlpha>(w);
     if (!kFirst) {
 #pragma unroll
-        for (int jj = 0; jj < SPL / 2; ++jj) dst[jj * 32] = make_double2(w.st.a[2 * jj], w.st.a[2 * jj + 1]);
+        for (int jj = 0; jj < SPL / 4; ++jj) dst[jj * 32] = make_double2(w.st.a[4 * jj + 1], w.st.a[4 * jj + 3]);
     }
     if (lane0) *edst = w.st.E;
     dst += dstride;
     edst += estride;
+}
+
+// The walker's first second-half frame: Z0 = sum over ALL states of (own post-emission value) x (the other direction's
+// pre-emission sum), the one place the blank states of the other direction are needed (it stored them at its last
+// first-half frame, kMid).  The product a(s) o(s) can underflow fp64 on its own when alpha and beta peak far apart,
+// so the normalising power of two is split between the two factors (same scheme as the workers' occupancies).
+// Result -> shared memory: norm[0] = 2^30 / Z0 (0 when no alignment exists), then int E0, int dead.
+template <int SPL, bool kAlpha>
+__device__ __forceinline__ void ctc_walk_publish_norm(const CtcWalk<SPL, kAlpha>& w, const double* lat_row,
+                                                      const int* exp_p, double* norm) {
+    const int lane = threadIdx.x & 31;
+    const double2* lp = reinterpret_cast<const double2*>(lat_row) + lane;
+    double o[SPL];
+#pragma unroll
+    for (int jj = 0; jj < SPL / 4; ++jj) {
+        double2 lab = make_double2(0.0, 0.0), blk = make_double2(0.0, 0.0);
+        if (w.act) {
+            lab = __ldcg(lp + jj * 32);
+            blk = __ldcg(lp + (SPL / 4 + jj) * 32);
+        }
+        o[4 * jj] = blk.x; o[4 * jj + 1] = lab.x; o[4 * jj + 2] = blk.y; o[4 * jj + 3] = lab.y;
+    }
+    const int eo = __ldcg(exp_p);
+    int emax = -1;                                        // largest exponent-field sum of a product with both factors > 0
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int ax = (__double2hiint(w.st.a[j]) >> 20) & 0x7ff, ox = (__double2hiint(o[j]) >> 20) & 0x7ff;
+        if (ax && ox) emax = max(emax, ax + ox);
+    }
+    emax = __reduce_max_sync(kFull, emax);
+    bool dead = emax < 0;
+    const int ex0 = dead ? 0 : 2046 - emax;               // brings the largest product to about 2^0
+    const double s1 = pow2i(ex0 >> 1), s2 = pow2i(ex0 - (ex0 >> 1));
+    double z = 0.0;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) z += (w.st.a[j] * s1) * (o[j] * s2);
+    const double Z0 = warp_sum(z);
+    dead = dead || !(Z0 > 0.0);
+    if (lane == 0) {
+        norm[0] = dead ? 0.0 : kCtcFix / Z0;
+        reinterpret_cast<int*>(norm)[2] = w.st.E + eo - ex0;
+        reinterpret_cast<int*>(norm)[3] = dead ? 1 : 0;
+    }
 }
 
 // kGT: `tile` is row 0 of the utterance's tile in GLOBAL memory ([T] rows of RS doubles between two guard rows),
@@ -691,12 +747,13 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
         int* ep = exp_u + t0;
         const int estride = kAlpha ? 1 : -1;
         int step = 0;
-        for (; step + 4 <= n_first; step += 4) {
+        for (; step + 4 <= n_first - 1; step += 4) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) ctc_walk_frame<SPL, kAlpha, true, kGT>(w, lp, lstride, ep, estride, lane0);
             if (step & 4) ctc_walk_rescale<SPL, kAlpha>(w);
         }
-        for (; step < n_first; ++step) ctc_walk_frame<SPL, kAlpha, true, kGT>(w, lp, lstride, ep, estride, lane0);
+        for (; step < n_first - 1; ++step) ctc_walk_frame<SPL, kAlpha, true, kGT>(w, lp, lstride, ep, estride, lane0);
+        if (n_first > 0) ctc_walk_frame<SPL, kAlpha, true, kGT, true>(w, lp, lstride, ep, estride, lane0);   // + blank states
         ctc_walk_rescale<SPL, kAlpha>(w);
     }
     PGASR_STAMP(dbg, kAlpha ? 11 : 15);
@@ -707,14 +764,21 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
     for (int q = 0; q < n2; q += kBatchOf<SPL>) {
         const int buf = (q / kBatchOf<SPL>) & 1;
         if (q >= 2 * kBatchOf<SPL>) named_bar_sync(ring.bar_empty + buf, kGroup);
-        double2* sp = reinterpret_cast<double2*>(ring.slots + (size_t)(buf * kBatchOf<SPL>) * (SPL * 32)) + lane;
+        double2* sp = reinterpret_cast<double2*>(ring.slots + (size_t)(buf * kBatchOf<SPL>) * (SPL * 16)) + lane;
         int* ep = ring.eslot + buf * kBatchOf<SPL>;
         const int nfr = min(kBatchOf<SPL>, n2 - q);
-        if (nfr == kBatchOf<SPL>) {
+        if (q == 0) {
+            // first frame of the second half: measure Z0 against the other direction's full row and publish the
+            // normalisation for the workers (they read it after the first bar_full)
+            ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
+            const int tf = kAlpha ? n_first : Tb - 1 - n_first;
+            ctc_walk_publish_norm<SPL, kAlpha>(w, lat_u + (size_t)tf * (SPL * 32), exp_u + tf, ring.norm);
+            for (int u = 1; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
+        } else if (nfr == kBatchOf<SPL>) {
 #pragma unroll
-            for (int u = 0; u < kBatchOf<SPL>; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
+            for (int u = 0; u < kBatchOf<SPL>; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
         } else {
-            for (int u = 0; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 2) * 32, ep, 1, lane0);
+            for (int u = 0; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
         }
         named_bar_arrive(ring.bar_full + buf, kGroup);
         ctc_walk_rescale<SPL, kAlpha>(w);
@@ -745,7 +809,7 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
 template <int SPL, int G, bool kAlpha>
 struct CtcWorker {
     static constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;     // frames of a batch per worker (worker g: frames g, g+G, ..)
-    double2 o[kPer][SPL / 2];
+    double2 o[kPer][SPL / 4];     // the other direction's label states of the frame
     int eo[kPer];
     double prow[kPer];            // global-tile mode: p_t(lane) of the frame, fetched with the lattice row
     unsigned long long l2pol;     // L2 cache policy of the lattice loads (evict_first: the row is dead after this read)
@@ -767,11 +831,11 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
         const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lane;
 #ifdef EXP_NO_LATTICE
 #pragma unroll
-        for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = make_double2(1.0 + lane, 0.5);
+        for (int jj = 0; jj < SPL / 4; ++jj) wk.o[r][jj] = make_double2(1.0 + lane, 0.5);
         wk.eo[r] = 0; (void)lp;
 #else
 #pragma unroll
-        for (int jj = 0; jj < SPL / 2; ++jj) wk.o[r][jj] = act ? ld_lattice(lp + jj * 32, pol) : make_double2(0.0, 0.0);
+        for (int jj = 0; jj < SPL / 4; ++jj) wk.o[r][jj] = act ? ld_lattice(lp + jj * 32, pol) : make_double2(0.0, 0.0);
         wk.eo[r] = __ldcg(exp_u + t);
         if (kGT) wk.prow[r] = __ldcg(tile + (size_t)t * RS + lane);
 #endif
@@ -797,59 +861,34 @@ __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlph
         gb[r] = 0;
         if (g + r * G < kBatchOf<SPL> && q < n2) {
             const int slot = q % (2 * kBatchOf<SPL>);
-            const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 32)) + lane;
+            const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 16)) + lane;
             // Occupancy of state s in 2^-30 fixed point = a(s) o(s) c with c = invZ0 2^(E + eo - E0).  The product
             // a(s) o(s) alone can underflow fp64 although both factors and the final value are in range (alpha and
             // beta peak far apart when T >> L with diffuse posteriors), so the power of two is split between the
             // two factors before they are multiplied: (a 2^h1) (o invZ0 2^h2), h1 + h2 = E + eo - E0.
-            double2 av[SPL / 2];
+            // Only the label states are handled; the blank column is 2^30 minus their sum (sum_s gamma_t(s) = 1).
+            double2 av[SPL / 4];
 #pragma unroll
-            for (int jj = 0; jj < SPL / 2; ++jj) av[jj] = sp[jj * 32];
+            for (int jj = 0; jj < SPL / 4; ++jj) av[jj] = sp[jj * 32];
             const int E = ring.eslot[slot];
-            if (!nm.have) {                               // this worker's first frame: fix the normalisation
-                int emax = -1;                            // largest exponent-field sum of a product with both factors > 0
-#pragma unroll
-                for (int jj = 0; jj < SPL / 2; ++jj) {
-                    const int ax = (__double2hiint(av[jj].x) >> 20) & 0x7ff, ox = (__double2hiint(wk.o[r][jj].x) >> 20) & 0x7ff;
-                    const int ay = (__double2hiint(av[jj].y) >> 20) & 0x7ff, oy = (__double2hiint(wk.o[r][jj].y) >> 20) & 0x7ff;
-                    if (ax && ox) emax = max(emax, ax + ox);
-                    if (ay && oy) emax = max(emax, ay + oy);
-                }
-                emax = __reduce_max_sync(kFull, emax);
-                nm.dead = emax < 0;
-                const int ex0 = nm.dead ? 0 : 2046 - emax;            // brings the largest product to about 2^0
-                const double s1 = pow2i(ex0 >> 1), s2 = pow2i(ex0 - (ex0 >> 1));
-                double z = 0.0;
-#pragma unroll
-                for (int jj = 0; jj < SPL / 2; ++jj)
-                    z += (av[jj].x * s1) * (wk.o[r][jj].x * s2) + (av[jj].y * s1) * (wk.o[r][jj].y * s2);
-                const double Z0 = warp_sum(z);
-                nm.dead = nm.dead || !(Z0 > 0.0);
-                nm.invZ0 = nm.dead ? 0.0 : kCtcFix / Z0;
-                nm.E0 = E + wk.eo[r] - ex0;
-                nm.have = true;
-            }
             const int ex = E + wk.eo[r] - nm.E0;
             const int h1 = (ex >> 1) - 15;                // invZ0 <= 2^30 rides on the smaller half
             const double s1 = nm.invZ0 * pow2i(h1), s2 = pow2i(ex - h1);
-            double wv[SPL];
-            double zb = 0.0;
+            int wi[SPL / 2];
+            int ls = 0;
 #pragma unroll
-            for (int jj = 0; jj < SPL / 2; ++jj) {
-                wv[2 * jj] = (av[jj].x * s1) * (wk.o[r][jj].x * s2);
-                wv[2 * jj + 1] = (av[jj].y * s1) * (wk.o[r][jj].y * s2);
-                zb += wv[2 * jj];
+            for (int jj = 0; jj < SPL / 4; ++jj) {
+                wi[2 * jj] = __double2loint((av[jj].x * s1) * (wk.o[r][jj].x * s2) + kCtcMagic);
+                wi[2 * jj + 1] = __double2loint((av[jj].y * s1) * (wk.o[r][jj].y * s2) + kCtcMagic);
+                ls += wi[2 * jj] + wi[2 * jj + 1];
             }
-            gb[r] = __reduce_add_sync(kFull, __double2loint(zb + kCtcMagic));
+            gb[r] = (1 << 30) - __reduce_add_sync(kFull, ls);
             if constexpr (SPL >= 8) {
                 int4* gr = reinterpret_cast<int4*>(gam + r * kGam) + lane * (SPL / 8);
 #pragma unroll
-                for (int i = 0; i < SPL / 8; ++i)
-                    gr[i] = make_int4(__double2loint(wv[8 * i + 1] + kCtcMagic), __double2loint(wv[8 * i + 3] + kCtcMagic),
-                                      __double2loint(wv[8 * i + 5] + kCtcMagic), __double2loint(wv[8 * i + 7] + kCtcMagic));
+                for (int i = 0; i < SPL / 8; ++i) gr[i] = make_int4(wi[4 * i], wi[4 * i + 1], wi[4 * i + 2], wi[4 * i + 3]);
             } else {
-                reinterpret_cast<int2*>(gam + r * kGam)[lane] =
-                    make_int2(__double2loint(wv[1] + kCtcMagic), __double2loint(wv[3] + kCtcMagic));
+                reinterpret_cast<int2*>(gam + r * kGam)[lane] = make_int2(wi[0], wi[1]);
             }
         }
     }
@@ -953,6 +992,12 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const
         const long long w1 = clock64();
         nm.tWait += w1 - w0;
 #endif
+        if (nb == 0) {                                    // the walker measured Z0 on its first second-half frame
+            nm.invZ0 = ring.norm[0];
+            nm.E0 = reinterpret_cast<const int*>(ring.norm)[2];
+            nm.dead = reinterpret_cast<const int*>(ring.norm)[3] != 0;
+            nm.have = true;
+        }
 #ifndef EXP_NO_WORKER
         ctc_worker_phase_a<SPL, G, kAlpha>(wk, nm, nb, g, n2, ring, gam, gb);
 #ifdef PGASR_TIMING
