@@ -353,9 +353,14 @@ namespace pgasr {
 
 // frames per hand-off batch (two batches in flight per direction); 32 states per lane make a frame 8 KB, so the
 // rings of that variant hold fewer frames
+// (up to 8 states per lane: 14 frames, so each of the 7 workers owns TWO frames of a batch and runs them side by
+// side -- a worker frame is ~170 dependent instructions at ~7 cycles each, measured; one frame at a time left the
+// workers, not the walkers, as the bound of the second half)
 template <int SPL>
-constexpr int kBatchOf = SPL >= 32 ? 4 : 7;
-inline int batch_of(int spl) { return spl >= 32 ? 4 : 7; }
+constexpr int kBatchOf = SPL >= 32 ? 4 : SPL >= 16 ? 7 : 14;
+inline int batch_of(int spl) { return spl >= 32 ? 4 : spl >= 16 ? 7 : 14; }
+template <int SPL>
+constexpr int kWalkUnroll = kBatchOf<SPL> % 7 == 0 ? 7 : kBatchOf<SPL>;   // frames per unrolled group of the walker
 
 template <int SPL>
 struct GradRing {
@@ -395,17 +400,16 @@ __device__ __forceinline__ void ctc_build_class_lists(const int32_t* __restrict_
 
 template <int SPL>
 __host__ __device__ inline size_t grad_ring_bytes() {
-    // slots (allocated at twice the size in use: the spare half pads the staging area of the softmax phase) +
-    // exponents + the normalisation block
-    return (size_t)2 * kBatchOf<SPL> * SPL * 32 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15) + 16;
+    // slots + exponents + the normalisation block
+    return (size_t)2 * kBatchOf<SPL> * SPL * 16 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15) + 16;
 }
 
 template <int SPL>
 __device__ __forceinline__ GradRing<SPL> grad_ring_carve(unsigned char* p, int bar_base) {   // p 16-byte aligned
     GradRing<SPL> r;
     r.slots = reinterpret_cast<double*>(p);
-    r.eslot = reinterpret_cast<int*>(p + (size_t)2 * kBatchOf<SPL> * SPL * 32 * 8);
-    r.norm = reinterpret_cast<double*>(p + (size_t)2 * kBatchOf<SPL> * SPL * 32 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15));
+    r.eslot = reinterpret_cast<int*>(p + (size_t)2 * kBatchOf<SPL> * SPL * 16 * 8);
+    r.norm = reinterpret_cast<double*>(p + (size_t)2 * kBatchOf<SPL> * SPL * 16 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15));
     r.bar_full = bar_base;
     r.bar_empty = bar_base + 2;
     r.dbg = false;
@@ -775,8 +779,10 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
             ctc_walk_publish_norm<SPL, kAlpha>(w, lat_u + (size_t)tf * (SPL * 32), exp_u + tf, ring.norm);
             for (int u = 1; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
         } else if (nfr == kBatchOf<SPL>) {
+            for (int u0 = 0; u0 < kBatchOf<SPL>; u0 += kWalkUnroll<SPL>) {
 #pragma unroll
-            for (int u = 0; u < kBatchOf<SPL>; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
+                for (int u = 0; u < kWalkUnroll<SPL>; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
+            }
         } else {
             for (int u = 0; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
         }
@@ -847,48 +853,92 @@ struct WorkerNorm { double invZ0; int E0; bool dead, have; long long tA, tB, tWa
 constexpr int kClsRegs = 12;      // label positions of this lane's class held in registers
 
 // phase A: occupancies of every owned frame of batch nb; label states go to gam[frame][label index] and the
-// blank total to gb[] (2^-30 fixed point)
+// blank total to gb[] (2^-30 fixed point).  When every worker owns the same number of frames per batch (kUncond)
+// the frames are computed unconditionally, in ONE basic block, so that their dependent chains interleave; a frame
+// beyond the end of the utterance then reads a stale ring slot and its results are never stored.
 template <int SPL, int G, bool kAlpha>
 __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlpha>& wk, WorkerNorm& nm, int nb, int g,
                                                    int n2, const GradRing<SPL>& ring, int* gam,
                                                    int (&gb)[(kBatchOf<SPL> + G - 1) / G]) {
     constexpr int kPer = CtcWorker<SPL, G, kAlpha>::kPer;
     constexpr int kGam = 16 * SPL;                        // ints per frame: SPL/2 label occupancies per lane
+    constexpr bool kUncond = kBatchOf<SPL> % G == 0;
     const int lane = threadIdx.x & 31;
+    // Occupancy of state s in 2^-30 fixed point = a(s) o(s) c with c = invZ0 2^(E + eo - E0).  The product
+    // a(s) o(s) alone can underflow fp64 although both factors and the final value are in range (alpha and
+    // beta peak far apart when T >> L with diffuse posteriors), so the power of two is split between the
+    // two factors before they are multiplied: (a 2^h1) (o invZ0 2^h2), h1 + h2 = E + eo - E0.
+    // Only the label states are handled; the blank column is 2^30 minus their sum (sum_s gamma_t(s) = 1).
+    if constexpr (kUncond) {
+        // stage by stage over the frames (loads, products, reductions, stores): the shared-memory stores of one
+        // frame would otherwise fence the loads of the next (the compiler cannot tell the ring from gam)
+        double2 av[kPer][SPL / 4];
+        int E[kPer], wi[kPer][SPL / 2], ls[kPer];
 #pragma unroll
-    for (int r = 0; r < kPer; ++r) {
-        const int q = nb * kBatchOf<SPL> + g + r * G;
-        gb[r] = 0;
-        if (g + r * G < kBatchOf<SPL> && q < n2) {
-            const int slot = q % (2 * kBatchOf<SPL>);
+        for (int r = 0; r < kPer; ++r) {
+            const int slot = (nb & 1) * kBatchOf<SPL> + g + r * G;
             const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 16)) + lane;
-            // Occupancy of state s in 2^-30 fixed point = a(s) o(s) c with c = invZ0 2^(E + eo - E0).  The product
-            // a(s) o(s) alone can underflow fp64 although both factors and the final value are in range (alpha and
-            // beta peak far apart when T >> L with diffuse posteriors), so the power of two is split between the
-            // two factors before they are multiplied: (a 2^h1) (o invZ0 2^h2), h1 + h2 = E + eo - E0.
-            // Only the label states are handled; the blank column is 2^30 minus their sum (sum_s gamma_t(s) = 1).
-            double2 av[SPL / 4];
 #pragma unroll
-            for (int jj = 0; jj < SPL / 4; ++jj) av[jj] = sp[jj * 32];
-            const int E = ring.eslot[slot];
-            const int ex = E + wk.eo[r] - nm.E0;
+            for (int jj = 0; jj < SPL / 4; ++jj) av[r][jj] = sp[jj * 32];
+            E[r] = ring.eslot[slot];
+        }
+#pragma unroll
+        for (int r = 0; r < kPer; ++r) {
+            const int ex = E[r] + wk.eo[r] - nm.E0;
             const int h1 = (ex >> 1) - 15;                // invZ0 <= 2^30 rides on the smaller half
             const double s1 = nm.invZ0 * pow2i(h1), s2 = pow2i(ex - h1);
-            int wi[SPL / 2];
-            int ls = 0;
+            ls[r] = 0;
 #pragma unroll
             for (int jj = 0; jj < SPL / 4; ++jj) {
-                wi[2 * jj] = __double2loint((av[jj].x * s1) * (wk.o[r][jj].x * s2) + kCtcMagic);
-                wi[2 * jj + 1] = __double2loint((av[jj].y * s1) * (wk.o[r][jj].y * s2) + kCtcMagic);
-                ls += wi[2 * jj] + wi[2 * jj + 1];
+                wi[r][2 * jj] = __double2loint((av[r][jj].x * s1) * (wk.o[r][jj].x * s2) + kCtcMagic);
+                wi[r][2 * jj + 1] = __double2loint((av[r][jj].y * s1) * (wk.o[r][jj].y * s2) + kCtcMagic);
+                ls[r] += wi[r][2 * jj] + wi[r][2 * jj + 1];
             }
-            gb[r] = (1 << 30) - __reduce_add_sync(kFull, ls);
+        }
+#pragma unroll
+        for (int r = 0; r < kPer; ++r) gb[r] = (1 << 30) - __reduce_add_sync(kFull, ls[r]);
+#pragma unroll
+        for (int r = 0; r < kPer; ++r) {
             if constexpr (SPL >= 8) {
                 int4* gr = reinterpret_cast<int4*>(gam + r * kGam) + lane * (SPL / 8);
 #pragma unroll
-                for (int i = 0; i < SPL / 8; ++i) gr[i] = make_int4(wi[4 * i], wi[4 * i + 1], wi[4 * i + 2], wi[4 * i + 3]);
+                for (int i = 0; i < SPL / 8; ++i) gr[i] = make_int4(wi[r][4 * i], wi[r][4 * i + 1], wi[r][4 * i + 2], wi[r][4 * i + 3]);
             } else {
-                reinterpret_cast<int2*>(gam + r * kGam)[lane] = make_int2(wi[0], wi[1]);
+                reinterpret_cast<int2*>(gam + r * kGam)[lane] = make_int2(wi[r][0], wi[r][1]);
+            }
+        }
+        (void)n2;
+    } else {
+#pragma unroll
+        for (int r = 0; r < kPer; ++r) {
+            const int qi = g + r * G;                     // frame of the batch
+            gb[r] = 0;
+            if (qi < kBatchOf<SPL> && nb * kBatchOf<SPL> + qi < n2) {
+                const int slot = (nb & 1) * kBatchOf<SPL> + qi;
+                const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 16)) + lane;
+                double2 av[SPL / 4];
+#pragma unroll
+                for (int jj = 0; jj < SPL / 4; ++jj) av[jj] = sp[jj * 32];
+                const int E = ring.eslot[slot];
+                const int ex = E + wk.eo[r] - nm.E0;
+                const int h1 = (ex >> 1) - 15;
+                const double s1 = nm.invZ0 * pow2i(h1), s2 = pow2i(ex - h1);
+                int wi[SPL / 2];
+                int ls = 0;
+#pragma unroll
+                for (int jj = 0; jj < SPL / 4; ++jj) {
+                    wi[2 * jj] = __double2loint((av[jj].x * s1) * (wk.o[r][jj].x * s2) + kCtcMagic);
+                    wi[2 * jj + 1] = __double2loint((av[jj].y * s1) * (wk.o[r][jj].y * s2) + kCtcMagic);
+                    ls += wi[2 * jj] + wi[2 * jj + 1];
+                }
+                gb[r] = (1 << 30) - __reduce_add_sync(kFull, ls);
+                if constexpr (SPL >= 8) {
+                    int4* gr = reinterpret_cast<int4*>(gam + r * kGam) + lane * (SPL / 8);
+#pragma unroll
+                    for (int i = 0; i < SPL / 8; ++i) gr[i] = make_int4(wi[4 * i], wi[4 * i + 1], wi[4 * i + 2], wi[4 * i + 3]);
+                } else {
+                    reinterpret_cast<int2*>(gam + r * kGam)[lane] = make_int2(wi[0], wi[1]);
+                }
             }
         }
     }
@@ -907,37 +957,60 @@ __device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlph
                                                    const int (&cpos)[kClsRegs]) {
     constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;
     constexpr int kGam = 16 * SPL;
+    constexpr bool kUncond = kBatchOf<SPL> % G == 0;
     const int lane = threadIdx.x & 31;
+    if (V <= 32) {
+        // the frames of this worker side by side: gathers, then the rare tail, then the rows
+        int occ[kPer];
 #pragma unroll
-    for (int r = 0; r < kPer; ++r) {
-        const int q = nb * kBatchOf<SPL> + g + r * G;
-        if (g + r * G < kBatchOf<SPL> && q < n2) {
-            const int step = n_first + q;
-            const int t = kAlpha ? step : Tb - 1 - step;
-            const double* row = tile + (size_t)t * RS;
-            float* out = dlog_u + (size_t)t * V;
+        for (int r = 0; r < kPer; ++r) {
             const int* gr = gam + r * kGam;
-            if (V <= 32) {
-                int occ = 0;
+            int o1 = 0, o2 = 0;
 #ifndef EXP_NO_PHASEB
-                int o2 = 0;
 #pragma unroll
-                for (int i = 0; i < kClsRegs; i += 2) {
-                    if (i < cmax) {                            // warp uniform: no class of this transcript is longer
-                        occ += gr[cpos[i]];
-                        o2 += gr[cpos[i + 1]];
-                    }
+            for (int i = 0; i < kClsRegs; i += 2) {
+                if (i < cmax) {                            // warp uniform: no class of this transcript is longer
+                    o1 += gr[cpos[i]];
+                    o2 += gr[cpos[i + 1]];
                 }
-                occ += o2;
-                for (int i = kClsRegs; i < cmax; ++i)
-                    occ += i < ccnt ? gr[ring.cls_pos[ring.cls_off[lane] + i]] : 0;
+            }
 #endif
-                occ = lane == blank ? gb[r] : occ;
-                const double pv = kGT ? prow[r] : row[min(lane, RS - 1)];
+            occ[r] = o1 + o2;
+        }
+#ifndef EXP_NO_PHASEB
+        if (cmax > kClsRegs) {
+#pragma unroll
+            for (int r = 0; r < kPer; ++r)
+                for (int i = kClsRegs; i < cmax; ++i)
+                    occ[r] += i < ccnt ? gam[r * kGam + ring.cls_pos[ring.cls_off[lane] + i]] : 0;
+        }
+#endif
+#pragma unroll
+        for (int r = 0; r < kPer; ++r) {
+            const int qi = g + r * G;
+            const int q = nb * kBatchOf<SPL> + qi;
+            const bool valid = qi < kBatchOf<SPL> && q < n2;
+            if (kUncond || valid) {
+                const int step = n_first + (kUncond ? min(q, n2 - 1) : q);
+                const int t = kAlpha ? step : Tb - 1 - step;
+                const int oc = lane == blank ? gb[r] : occ[r];
+                const double pv = kGT ? prow[r] : tile[(size_t)t * RS + min(lane, RS - 1)];
                 const int pfix = __double2loint(fma(pv, kCtcFix, kCtcMagic));
-                const float gval = nm.dead ? 0.0f : grad_scale * ((float)(pfix - occ) * kCtcUnfix);
-                if (lane < V) out[lane] = gval;
-            } else {
+                const float gval = nm.dead ? 0.0f : grad_scale * ((float)(pfix - oc) * kCtcUnfix);
+                if (lane < V && valid) dlog_u[(size_t)t * V + lane] = gval;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kPer; ++r) {
+            const int qi = g + r * G;
+            const int q = nb * kBatchOf<SPL> + qi;
+            if (qi < kBatchOf<SPL> && q < n2) {
+                const int step = n_first + q;
+                const int t = kAlpha ? step : Tb - 1 - step;
+                const double* row = tile + (size_t)t * RS;
+                float* out = dlog_u + (size_t)t * V;
+                const int* gr = gam + r * kGam;
                 for (int v = lane; v < V; v += 32) {
                     int occ = 0;
                     for (int i = ring.cls_off[v]; i < ring.cls_off[v + 1]; ++i) occ += gr[ring.cls_pos[i]];

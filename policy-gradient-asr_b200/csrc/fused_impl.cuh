@@ -329,12 +329,20 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     __syncthreads();
 
     PGASR_STAMP(dbg, 33);
-    // ---- P3: edit distance, one thread per sample ------------------------------------------------
-    // (all K samples in the lanes of as few warps as possible: a Myers step is ~25 W dependent integer
-    // instructions, and lanes of one warp share them; one sample per warp was measured 3.6x slower)
-    if ((int)threadIdx.x < K) {
-        const int k = threadIdx.x;
-        dist_s[k] = myers_row<W, false>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, nullptr);
+    // ---- P3: edit distance, P lanes per sample ---------------------------------------------------
+    // (all K samples in the lanes of as few warps as possible: a Myers step is a chain of dependent integer
+    // instructions, and lanes of one warp share them; one sample per warp was measured 3.6x slower.  The words of a
+    // sample are spread over P lanes that run one symbol apart, see myers_row_split)
+    {
+        constexpr int P = W >= 4 ? 4 : 2;                 // lanes per sample (myers_row_split)
+        if (warp * 32 < K * P) {                          // whole warps: the lanes shuffle with a full mask
+            const int k = (int)threadIdx.x / P, p = (int)threadIdx.x % P;
+            const int kc = min(k, K - 1);
+            const int n = k < K ? hlen_s[kc] : 0;
+            const int nmax = __reduce_max_sync(kFull, n);
+            const int d = myers_row_split<W, P>(hyp_s + (size_t)kc * Tp, n, peq, V, m, p, nmax);
+            if (k < K && p == 0) dist_s[k] = d;
+        }
     }
     __syncthreads();
 
