@@ -34,6 +34,27 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 
 constexpr int kFusedMaxK = 64;
 
+// Number of entries of a non-decreasing 32-entry register array that are <= tau: a binary search written as a tree
+// of selects (26 FSEL + 5 FSETP instead of 32 compare-and-add pairs).  Same count as the linear scan of the sampler
+// spec because the CDF is non-decreasing (sums of non-negative terms, round to nearest).
+__device__ __forceinline__ int cdf_count32(const float (&c)[32], float tau) {
+    const bool b4 = c[15] <= tau;
+    const float p3 = b4 ? c[23] : c[7];
+    const bool b3 = p3 <= tau;
+    const float q0 = b3 ? c[11] : c[3], q1 = b3 ? c[27] : c[19];
+    const bool b2 = (b4 ? q1 : q0) <= tau;
+    const float r0 = b2 ? c[5] : c[1], r1 = b2 ? c[13] : c[9], r2 = b2 ? c[21] : c[17], r3 = b2 ? c[29] : c[25];
+    const float s0 = b3 ? r1 : r0, s1 = b3 ? r3 : r2;
+    const bool b1 = (b4 ? s1 : s0) <= tau;
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = b1 ? c[4 * i + 2] : c[4 * i];
+    const float u0 = b2 ? t[1] : t[0], u1 = b2 ? t[3] : t[2], u2 = b2 ? t[5] : t[4], u3 = b2 ? t[7] : t[6];
+    const float v0 = b3 ? u1 : u0, v1 = b3 ? u3 : u2;
+    const bool b0 = (b4 ? v1 : v0) <= tau;
+    return (b4 ? 16 : 0) + (b3 ? 8 : 0) + (b2 ? 4 : 0) + (b1 ? 2 : 0) + (b0 ? 1 : 0);
+}
+
 // ------------------------------------------------------------------------------------------------ CTC role
 // warp 0: alpha recurrence, warp 1: beta recurrence; every other warp is a gradient worker, even warps on the
 // alpha side, odd warps on the beta side (G = (warps - 2) / 2 per direction).
@@ -97,7 +118,8 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         // softmax tile.  The raw logits are staged through the (not yet used) ring region with cp.async, then one
         // thread per frame makes three passes over its row -- max, exp + sum, normalise -- visiting the classes in
         // a per-thread rotated order so that neither the staged reads (row stride V floats) nor the fp64 tile
-        // writes (row stride RS doubles) collide on a shared-memory bank.
+        // writes (row stride RS doubles) collide on a shared-memory bank.  (One warp per frame with a lane per
+        // class was measured at twice the time, 17.9k against 9k cycles: 5 shuffles + a redux per frame.)
         const float* lg = a.logits + (size_t)b * T * V;
         {
             float* stage = reinterpret_cast<float*>(stage_base);
@@ -117,6 +139,11 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                     for (int i = threadIdx.x; i < n * V; i += kThreads) cp_async4(stage + i, src + i);
                 }
                 cp_async_commit();
+                if (c0 == 0) {
+                    // class lists of the transcript, built by warp 0 while the logits are in flight
+                    __syncthreads();                           // the transcript is in shared memory
+                    if (warp == 0) ctc_build_class_lists(lab_s, L, V, cls_off, cls_pos, cls_scr);
+                }
                 cp_async_wait<0>();
                 __syncthreads();
                 for (int t = threadIdx.x; t < n; t += kThreads) {
@@ -152,11 +179,9 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                 __syncthreads();
             }
         }
-        const int32_t* lab_u = lab_s;                      // (published by the barriers of the tile loop above)
-        if (warp == 0) ctc_build_class_lists(lab_u, L, V, cls_off, cls_pos, cls_scr);
-        ring_a.cls_off = ring_b.cls_off = cls_off;
+        const int32_t* lab_u = lab_s;                      // (published by the barriers of the tile loop above,
+        ring_a.cls_off = ring_b.cls_off = cls_off;         //  like the class lists)
         ring_a.cls_pos = ring_b.cls_pos = cls_pos;
-        __syncthreads();
         PGASR_STAMP(b == 0 && threadIdx.x == 0, 2);
         double* lat_u = a.lattice + (size_t)b * T * (SPL * 32);
         int* exp_u = a.lat_exp + (size_t)b * T;
@@ -281,10 +306,9 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
                     u = u32_to_uniform(x);
                 }
                 const float tau = __fmul_rn(u, S);
-                int cnt = 0;
-#pragma unroll
-                for (int v = 0; v < VP; ++v) cnt += (v < V && cdf[v] <= tau) ? 1 : 0;
-                pi = min(cnt, V - 1);
+                // (entries V..31 of cdf[] repeat S, so the count over all 32 entries differs from the spec's count
+                // over V entries only when tau == S, where both clamp to V - 1)
+                pi = min(cdf_count32(cdf, tau), V - 1);
                 term = (z[pi] - mx) - logS;
             }
             if (t < T) {
@@ -333,8 +357,8 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     // (all K samples in the lanes of as few warps as possible: a Myers step is a chain of dependent integer
     // instructions, and lanes of one warp share them; one sample per warp was measured 3.6x slower.  The words of a
     // sample are spread over P lanes that run one symbol apart, see myers_row_split)
-    {
-        constexpr int P = W >= 4 ? 4 : 2;                 // lanes per sample (myers_row_split)
+    if constexpr (W >= 4) {
+        constexpr int P = 4;                              // lanes per sample (myers_row_split)
         if (warp * 32 < K * P) {                          // whole warps: the lanes shuffle with a full mask
             const int k = (int)threadIdx.x / P, p = (int)threadIdx.x % P;
             const int kc = min(k, K - 1);
@@ -342,6 +366,11 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
             const int nmax = __reduce_max_sync(kFull, n);
             const int d = myers_row_split<W, P>(hyp_s + (size_t)kc * Tp, n, peq, V, m, p, nmax);
             if (k < K && p == 0) dist_s[k] = d;
+        }
+    } else {                                              // two words: one thread per sample is as fast (measured)
+        if ((int)threadIdx.x < K) {
+            const int k = threadIdx.x;
+            dist_s[k] = myers_row<W, false>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, nullptr);
         }
     }
     __syncthreads();
@@ -463,13 +492,27 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     if ((((size_t)T * V * 4) & 15) == 0) {
         float4* d4 = reinterpret_cast<float4*>(dlog_u);
         const float4* t4 = reinterpret_cast<const float4*>(ztile);
-        for (int i = threadIdx.x; i < T * V / 4; i += kThreads) {
-            float4 g = t4[i];
-            if (a.do_ctc) {
-                const float4 c = __ldcg(d4 + i);
-                g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w;
+        const int n4 = T * V / 4;
+        if (a.do_ctc) {
+            // eight L2 reads in flight per thread (one at a time, every pass waited out the full L2 latency)
+            for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * kThreads) {
+                float4 c[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * kThreads;
+                    c[u] = i < n4 ? __ldcg(d4 + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * kThreads;
+                    if (i < n4) {
+                        const float4 g = t4[i];
+                        d4[i] = make_float4(g.x + c[u].x, g.y + c[u].y, g.z + c[u].z, g.w + c[u].w);
+                    }
+                }
             }
-            d4[i] = g;
+        } else {
+            for (int i = threadIdx.x; i < n4; i += kThreads) d4[i] = t4[i];
         }
     } else {
         for (int i = threadIdx.x; i < T * V; i += kThreads)
@@ -506,9 +549,13 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     if (threadIdx.x == 0 && ticket < 2048) { g_cta_ns[ticket][0] = t_start; g_cta_ns[ticket][1] = gtime(); }
 #endif
     // ---- second ticket: the last CTA reduces the loss (fixed order) and re-arms the control block ----
-    __threadfence();
+    // (what the last CTA reads -- loss_terms[b], nll_ws[b] -- was written by thread 0 of the owning CTA, so only that
+    // thread's writes have to be ordered before the ticket; the rows of dlogits are published by the kernel boundary)
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(a.ctrl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(a.ctrl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
     __syncthreads();
     if (s_last && threadIdx.x < 32) {
         __threadfence();
