@@ -19,7 +19,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__host__ __device__ inline int ctc_row_stride(int V) { return (V + 2) & ~1; }   // doubles per probability row
+__host__ __device__ inline int ctc_row_stride(int V) { return (V + 2) & ~1; }   // doubles per probability row (classic kernel)
+// floats per probability row of the walker / worker kernel: a multiple of 4 (16-byte cp.async pieces) with at least
+// one zero slot after the V classes (what label states beyond the transcript read)
+__host__ __device__ inline int ctc_row_stride_f32(int V) { return (V + 4) & ~3; }
 
 constexpr double kCtcMagic = 6755399441055744.0;       // 2^52 + 2^51: low word of (x + magic) = round(x)
 constexpr double kCtcFix = 1073741824.0;               // occupancies and probabilities in 2^-30 fixed point
@@ -480,6 +483,14 @@ __device__ __forceinline__ double lds_f64_v(unsigned addr) {
     asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
     return v;
 }
+// The probability tile of the walker / worker kernel is fp32 (the softmax is computed in fp32, so nothing is lost):
+// a lane's 4-byte read of "its" class within a 128-byte row never collides on a bank with the other lanes' reads
+// (8-byte reads of a 256-byte row were 2-3 wavefronts each), and the tile takes half the shared memory.
+__device__ __forceinline__ float lds_f32_v(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 
 // Recurrence warp of one direction over the whole utterance (tile mode).  G: workers of this direction.
 // Lattice / ring layout per frame: [SPL/2][32 lanes] double2, so each lane moves 16 bytes per access and a warp
@@ -492,7 +503,8 @@ struct CtcWalk {
     double h0, h1;                // halo value for the frame about to be computed (h1: unused, kept zero)
     double skip_prev;             // beta: skip factor of the PREVIOUS lane's last label state into this lane's state 1
     double pb_n, p_n[SPL / 2];    // probabilities of the frame about to be computed   (both sets were loaded TWO frames
-    double pb_m, p_m[SPL / 2];    // probabilities of the frame after it                ahead of their use)
+    float pb_m, p_m[SPL / 2];     // probabilities of the frame after it                ahead of their use; widened to
+                                  //                                                    fp64 one frame after the load)
     unsigned pa_b, pa[SPL / 2];   // running shared-memory addresses of this lane's probabilities: two frames on
     int rstride;
     bool edge;
@@ -500,7 +512,7 @@ struct CtcWalk {
     unsigned long long l2pol;     // L2 cache policy of the lattice stores
     // global-tile mode (long utterances): the probability rows stream from global memory through a 32-row ring
     unsigned ring_base, ring_mask;        // shared-memory address of the ring (aligned to its size), size - 1
-    const double* tile_g;                 // row 0 of this utterance's fp64 tile in global memory (guard rows around it)
+    const float* tile_g;                  // row 0 of this utterance's fp32 tile in global memory (guard rows around it)
     int gstep, row_next, row_dir, row_lo, row_hi, RS, RSR;
 };
 
@@ -512,13 +524,13 @@ template <int SPL, bool kAlpha>
 __device__ __forceinline__ void ctc_walk_issue_group(CtcWalk<SPL, kAlpha>& w, unsigned ring_generic_lo) {
     (void)ring_generic_lo;
     const int lane = threadIdx.x & 31;
-    const int per_row = w.RS / 2;                         // 16-byte pieces per row
+    const int per_row = w.RS / 4;                         // 16-byte pieces per row
     for (int i = lane; i < kPGroup * per_row; i += 32) {
         const int r = i / per_row, c = i - r * per_row;
         int row = w.row_next + w.row_dir * r;
         row = min(max(row, w.row_lo), w.row_hi);          // guard rows: loaded, never used
-        const unsigned dst = w.ring_base + (unsigned)(((row & (kPRows - 1)) * w.RSR + 2 * c) * 8);
-        const double* src = w.tile_g + (ptrdiff_t)row * w.RS + 2 * c;
+        const unsigned dst = w.ring_base + (unsigned)(((row & (kPRows - 1)) * w.RSR + 4 * c) * 4);
+        const float* src = w.tile_g + (ptrdiff_t)row * w.RS + 4 * c;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
     }
     cp_async_commit();
@@ -582,12 +594,12 @@ __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*
     const double pb = w.pb_n;
 #pragma unroll
     for (int i = 0; i < SPL / 2; ++i) p[i] = w.p_n[i];
-    w.pb_n = w.pb_m;
+    w.pb_n = (double)w.pb_m;
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) w.p_n[i] = w.p_m[i];
-    w.pb_m = lds_f64_v(w.pa_b);
+    for (int i = 0; i < SPL / 2; ++i) w.p_n[i] = (double)w.p_m[i];
+    w.pb_m = lds_f32_v(w.pa_b);
 #pragma unroll
-    for (int i = 0; i < SPL / 2; ++i) w.p_m[i] = lds_f64_v(w.pa[i]);
+    for (int i = 0; i < SPL / 2; ++i) w.p_m[i] = lds_f32_v(w.pa[i]);
     if (kGT) {
         w.pa_b = w.ring_base | ((w.pa_b + w.rstride) & w.ring_mask);
 #pragma unroll
@@ -669,10 +681,10 @@ __device__ __forceinline__ void ctc_walk_publish_norm(const CtcWalk<SPL, kAlpha>
 // kGT: `tile` is row 0 of the utterance's tile in GLOBAL memory ([T] rows of RS doubles between two guard rows),
 // `pring` the 32-row shared-memory ring of this walker (aligned to its size, row stride RSR doubles).
 template <int SPL, int G, bool kAlpha, bool kGT = false, typename Barrier>
-__device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t* __restrict__ lab_u, int Tb, int L,
+__device__ __forceinline__ void ctc_walk_tile(const float* tile, const int32_t* __restrict__ lab_u, int Tb, int L,
                                               int V, int RS, int blank, float* __restrict__ nll_out,
                                               double* __restrict__ lat_u, int* __restrict__ exp_u,
-                                              GradRing<SPL> ring, Barrier mid_barrier, double* pring = nullptr,
+                                              GradRing<SPL> ring, Barrier mid_barrier, float* pring = nullptr,
                                               int RSR = 0, int T = 0) {
     constexpr int kGroup = 32 * (1 + G);                  // this warp + its workers
     const int lane = threadIdx.x & 31;
@@ -699,8 +711,8 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
     if (kGT) {
         w.tile_g = tile; w.RS = RS; w.RSR = RSR;
         w.ring_base = (unsigned)__cvta_generic_to_shared(pring);
-        w.ring_mask = (unsigned)(kPRows * RSR * 8 - 1);
-        w.rstride = kAlpha ? RSR * 8 : -RSR * 8;
+        w.ring_mask = (unsigned)(kPRows * RSR * 4 - 1);
+        w.rstride = kAlpha ? RSR * 4 : -RSR * 4;
         w.row_dir = kAlpha ? 1 : -1;
         w.row_lo = -1; w.row_hi = T;
         w.row_next = t0;
@@ -711,10 +723,10 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
         ctc_walk_issue_group<SPL, kAlpha>(w, 0u);
         cp_async_wait<1>();
         __syncwarp();
-        row0 = w.ring_base + (unsigned)((t0 & (kPRows - 1)) * RSR * 8);
+        row0 = w.ring_base + (unsigned)((t0 & (kPRows - 1)) * RSR * 4);
     } else {
-        w.rstride = kAlpha ? RS * 8 : -RS * 8;
-        row0 = (unsigned)__cvta_generic_to_shared(tile) + (unsigned)(t0 * RS * 8);
+        w.rstride = kAlpha ? RS * 4 : -RS * 4;
+        row0 = (unsigned)__cvta_generic_to_shared(tile) + (unsigned)(t0 * RS * 4);
     }
     // every tile load below takes its address from this opaque copy, so none of them (plain asm, free to be
     // scheduled) can be moved above this point, i.e. above the barrier that published the tile
@@ -724,14 +736,14 @@ __device__ __forceinline__ void ctc_walk_tile(const double* tile, const int32_t*
         const unsigned row1 = kGT ? (w.ring_base | ((row0 + w.rstride) & w.ring_mask)) : row0 + w.rstride;
         const unsigned row2 = kGT ? (w.ring_base | ((row1 + w.rstride) & w.ring_mask)) : row1 + w.rstride;
         // (in ring mode row0 is ring_base + slot * row bytes: the column offsets below stay inside the row)
-        w.pb_n = lds_f64_v(row0 + (unsigned)(blank * 8));
-        w.pb_m = lds_f64_v(row1 + (unsigned)(blank * 8));
-        w.pa_b = row2 + (unsigned)(blank * 8);
+        w.pb_n = (double)lds_f32_v(row0 + (unsigned)(blank * 4));
+        w.pb_m = lds_f32_v(row1 + (unsigned)(blank * 4));
+        w.pa_b = row2 + (unsigned)(blank * 4);
 #pragma unroll
         for (int i = 0; i < SPL / 2; ++i) {
-            w.p_n[i] = lds_f64_v(row0 + (unsigned)(w.st.loff[i] * 8));
-            w.p_m[i] = lds_f64_v(row1 + (unsigned)(w.st.loff[i] * 8));
-            w.pa[i] = row2 + (unsigned)(w.st.loff[i] * 8);
+            w.p_n[i] = (double)lds_f32_v(row0 + (unsigned)(w.st.loff[i] * 4));
+            w.p_m[i] = lds_f32_v(row1 + (unsigned)(w.st.loff[i] * 4));
+            w.pa[i] = row2 + (unsigned)(w.st.loff[i] * 4);
         }
     }
     // virtual vector before the first frame: the recurrence turns it into the CTC start (alpha: states 0,1;
@@ -824,7 +836,7 @@ struct CtcWorker {
 template <int SPL, int G, bool kAlpha, bool kGT = false>
 __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, int nb, int g, int n_first, int n2,
                                                  int Tb, int S, const double* __restrict__ lat_u,
-                                                 const int* __restrict__ exp_u, const double* tile = nullptr,
+                                                 const int* __restrict__ exp_u, const float* tile = nullptr,
                                                  int RS = 0) {
     const int lane = threadIdx.x & 31;
     const bool act = lane * SPL < S;                      // the other direction never stored the lanes beyond S
@@ -843,7 +855,7 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
 #pragma unroll
         for (int jj = 0; jj < SPL / 4; ++jj) wk.o[r][jj] = act ? ld_lattice(lp + jj * 32, pol) : make_double2(0.0, 0.0);
         wk.eo[r] = __ldcg(exp_u + t);
-        if (kGT) wk.prow[r] = __ldcg(tile + (size_t)t * RS + lane);
+        if (kGT) wk.prow[r] = (double)__ldcg(tile + (size_t)t * RS + min(lane, RS - 1));
 #endif
     }
 }
@@ -951,7 +963,7 @@ __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlph
 template <int SPL, int G, bool kAlpha, bool kGT = false>
 __device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlpha>& wk, const double (&prow)[(kBatchOf<SPL> + G - 1) / G],
                                                    const WorkerNorm& nm, int nb, int g, int n_first, int n2, int Tb,
-                                                   const double* tile, int V, int RS, int blank, float grad_scale,
+                                                   const float* tile, int V, int RS, int blank, float grad_scale,
                                                    float* __restrict__ dlog_u, const GradRing<SPL>& ring,
                                                    const int* gam, const int (&gb)[(kBatchOf<SPL> + G - 1) / G], int ccnt, int cmax,
                                                    const int (&cpos)[kClsRegs]) {
@@ -994,7 +1006,7 @@ __device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlph
                 const int step = n_first + (kUncond ? min(q, n2 - 1) : q);
                 const int t = kAlpha ? step : Tb - 1 - step;
                 const int oc = lane == blank ? gb[r] : occ[r];
-                const double pv = kGT ? prow[r] : tile[(size_t)t * RS + min(lane, RS - 1)];
+                const double pv = kGT ? prow[r] : (double)tile[(size_t)t * RS + min(lane, RS - 1)];
                 const int pfix = __double2loint(fma(pv, kCtcFix, kCtcMagic));
                 const float gval = nm.dead ? 0.0f : grad_scale * ((float)(pfix - oc) * kCtcUnfix);
                 if (lane < V && valid) dlog_u[(size_t)t * V + lane] = gval;
@@ -1008,14 +1020,14 @@ __device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlph
             if (qi < kBatchOf<SPL> && q < n2) {
                 const int step = n_first + q;
                 const int t = kAlpha ? step : Tb - 1 - step;
-                const double* row = tile + (size_t)t * RS;
+                const float* row = tile + (size_t)t * RS;
                 float* out = dlog_u + (size_t)t * V;
                 const int* gr = gam + r * kGam;
                 for (int v = lane; v < V; v += 32) {
                     int occ = 0;
                     for (int i = ring.cls_off[v]; i < ring.cls_off[v + 1]; ++i) occ += gr[ring.cls_pos[i]];
                     if (v == blank) occ = gb[r];
-                    const int pfix = __double2loint(fma(row[v], kCtcFix, kCtcMagic));
+                    const int pfix = __double2loint(fma((double)row[v], kCtcFix, kCtcMagic));
                     const float gval = grad_scale * ((float)(pfix - occ) * kCtcUnfix);
                     out[v] = nm.dead ? 0.0f : gval;
                 }
@@ -1026,7 +1038,7 @@ __device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlph
 }
 
 template <int SPL, int G, bool kAlpha, bool kGT = false, typename Barrier>
-__device__ __forceinline__ void ctc_grad_worker(int g, const double* tile, const int32_t* __restrict__ lab_u, int Tb,
+__device__ __forceinline__ void ctc_grad_worker(int g, const float* tile, const int32_t* __restrict__ lab_u, int Tb,
                                                 int L, int V, int RS, int blank, float grad_scale,
                                                 float* __restrict__ dlog_u, const double* __restrict__ lat_u,
                                                 const int* __restrict__ exp_u, GradRing<SPL> ring, int* gam,

@@ -1,5 +1,8 @@
 // Host side of the single-launch kernel: what fits where (fused_plan), workspace layout, dispatch to the per-SPL
 // translation units (fused_spl4/8/16/32.cu, which instantiate fused_impl.cuh).
+#include <mutex>
+#include <unordered_map>
+
 #include "ctc_core.cuh"
 #include "fused_args.cuh"
 
@@ -13,26 +16,33 @@ int launch_fused_spl32(int mode, FusedArgs& a, size_t smem, cudaStream_t st);
 
 constexpr size_t kFusedSmemLimit = 220 * 1024;
 
+static unsigned workspace_parity(const void* ws) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, unsigned> seq;
+    std::lock_guard<std::mutex> lk(mu);
+    return seq[ws]++ & 1u;
+}
+
 struct FusedWs { size_t ctrl, lat, exps, terms, nll, tile, total; };
 
 static FusedWs fused_ws(int B, int T, int V, int spl, bool gt) {
     FusedWs w;
-    w.ctrl = align_up((size_t)(4 + B) * sizeof(unsigned), 256);
+    w.ctrl = align_up((size_t)2 * (4 + B) * sizeof(unsigned), 256);   // two control blocks, used alternately
     w.lat = align_up((size_t)B * T * spl * 32 * sizeof(double), 256);
     w.exps = align_up((size_t)B * T * sizeof(int), 256);
     w.terms = align_up((size_t)B * sizeof(float), 256);
     w.nll = align_up((size_t)B * sizeof(float), 256);
-    w.tile = gt ? align_up((size_t)B * (T + 2) * ctc_row_stride(V) * sizeof(double), 256) : 0;
+    w.tile = gt ? align_up((size_t)B * (T + 2) * ctc_row_stride_f32(V) * sizeof(float), 256) : 0;
     w.total = w.ctrl + w.lat + w.exps + w.terms + w.nll + w.tile;
     return w;
 }
 
 static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
-    const int RS = ctc_row_stride(V);
+    const int RS = ctc_row_stride_f32(V);
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
     const int G = (threads / 32 - 2) / 2, per = (batch_of(spl) + G - 1) / G;
-    const size_t pring = (size_t)kPRows * (RS <= 32 ? 32 : 64) * 8;
-    const size_t tile = gt ? 3 * pring /* two rings + alignment slack */ : (size_t)(T + 4) * RS * sizeof(double);
+    const size_t pring = (size_t)kPRows * (RS <= 32 ? 32 : 64) * 4;
+    const size_t tile = gt ? 3 * pring /* two rings + alignment slack */ : (((size_t)(T + 4) * RS * sizeof(float) + 15) & ~(size_t)15);
     return tile + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int);
 }
 
@@ -52,18 +62,19 @@ static FusedPlan fused_plan(int T, int V, int K, int Lmax) {
     pl.threads = pl.spl >= 32 ? 256 : 512;             // 32 states per lane need the 255-register budget
     pl.ctc_ok = pl.gt = pl.pg_ok = pl.stream = false;
     if (pl.spl == 0 || V > 32 || K > kFusedMaxK) return pl;
-    // each role keeps its [T][..] tile in shared memory when it fits one SM, else it streams
-    if (ctc_role_smem(T, V, pl.spl, pl.threads, false) <= kFusedSmemLimit) {
+    // each role keeps its [T][..] tile in shared memory when it fits one SM, else it streams; the streaming PG role
+    // is only instantiated next to the streaming CTC role, so a PG role that has to stream makes the CTC role stream
+    const bool ctc_tile = ctc_role_smem(T, V, pl.spl, pl.threads, false) <= kFusedSmemLimit;
+    const bool ctc_gt = ctc_role_smem(T, V, pl.spl, pl.threads, true) <= kFusedSmemLimit;
+    const bool pg_tile = pg_role_smem(T, V, K, pl.spl, pl.threads, false) <= kFusedSmemLimit;
+    const bool pg_stream = pg_role_smem(T, V, K, pl.spl, pl.threads, true) <= kFusedSmemLimit;
+    if (ctc_tile && (pg_tile || !(ctc_gt && pg_stream))) {
         pl.ctc_ok = true;
-    } else if (ctc_role_smem(T, V, pl.spl, pl.threads, true) <= kFusedSmemLimit) {
+        pl.pg_ok = pg_tile;
+    } else if (ctc_gt) {
         pl.ctc_ok = pl.gt = true;
-    }
-    if (pl.ctc_ok) {
-        if (pg_role_smem(T, V, K, pl.spl, pl.threads, false) <= kFusedSmemLimit) {
-            pl.pg_ok = true;
-        } else if (pl.gt && pg_role_smem(T, V, K, pl.spl, pl.threads, true) <= kFusedSmemLimit) {
-            pl.pg_ok = pl.stream = true;                   // (streaming PG is only instantiated next to the streaming CTC role)
-        }
+        if (pg_tile) pl.pg_ok = true;
+        else if (pg_stream) pl.pg_ok = pl.stream = true;
     }
     return pl;
 }
@@ -87,12 +98,17 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
     if (!pl.ctc_ok || (a.do_pg && !pl.pg_ok)) return PGASR_ERR_UNSUPPORTED;
     const FusedWs w = fused_ws(a.B, a.T, a.V, pl.spl, pl.gt);
     char* p = reinterpret_cast<char*>(workspace);
-    a.ctrl = reinterpret_cast<unsigned*>(p);             p += w.ctrl;
+    // Consecutive launches on one workspace alternate between its two control blocks: under programmatic dependent
+    // launch the CTAs of step n + 1 take their role tickets while step n is still running on its own block.  (Step
+    // n + 2 is launched only after every CTA of step n + 1 has passed its grid-dependency wait, i.e. after step n
+    // completed and re-armed the block.)  The parity lives on the host, per workspace.
+    a.ctrl = reinterpret_cast<unsigned*>(p) + (size_t)workspace_parity(workspace) * (4 + a.B);
+    p += w.ctrl;
     a.lattice = reinterpret_cast<double*>(p);            p += w.lat;
     a.lat_exp = reinterpret_cast<int*>(p);               p += w.exps;
     a.loss_terms = reinterpret_cast<float*>(p);          p += w.terms;
     a.nll_ws = reinterpret_cast<float*>(p);              p += w.nll;
-    a.tile_g = pl.gt ? reinterpret_cast<double*>(p) : nullptr;
+    a.tile_g = pl.gt ? reinterpret_cast<float*>(p) : nullptr;
     size_t smem = a.do_ctc ? ctc_role_smem(a.T, a.V, pl.spl, pl.threads, pl.gt) : 0;
     const bool stream = a.do_pg && pl.stream;
     if (a.do_pg) smem = smem > pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream) ? smem : pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream);

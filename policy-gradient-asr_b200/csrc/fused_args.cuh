@@ -14,7 +14,7 @@ struct FusedArgs {
     float* rewards; float* logp; int32_t* hyp_len; int32_t* dist; float* nll; uint8_t* samples;   // optional
     unsigned* ctrl;          // [0] role ticket, [1] done ticket, [4 + b] CTC-done flag of utterance b
     double* lattice; int* lat_exp; float* loss_terms; float* nll_ws;
-    double* tile_g;          // global-tile mode: [B][T + 2][RS] fp64 softmax rows (guard row before and after)
+    float* tile_g;           // global-tile mode: [B][T + 2][RS] fp32 softmax rows (guard row before and after)
 };
 
 // bit 0: the CTC role fits (tile in shared memory or streamed from the workspace), bit 1: the PG role fits too

@@ -6,7 +6,7 @@
 // Grid = 2B CTAs that pick their role from an atomic ticket (tickets < B: CTC role of utterance `ticket`;
 // the rest: PG role of utterance `ticket - B`), so the long-pole CTC CTAs are always resident before any PG CTA
 // waits on them.  Both roles of an utterance run at the same time on different SMs:
-//   CTC role: softmax of the utterance into an fp64 shared-memory tile, then warp 0 / warp 1 walk alpha / beta
+//   CTC role: softmax of the utterance into an fp32 shared-memory tile, then warp 0 / warp 1 walk alpha / beta
 //             (ctc_core.cuh) and write the CTC gradient rows; finally a release flag.
 //   PG role:  logits tile -> shared memory (cp.async), one thread per frame: softmax CDF + K inverse-CDF draws
 //             (Philox or injected uniforms), one warp per sample: ballot/popc collapse, one thread per sample:
@@ -16,6 +16,8 @@
 // The last CTA to finish (second ticket) reduces the loss in a fixed order and re-arms the control block.
 // dlogits is written once by the CTC role and updated once by the PG role; every sum is order independent or
 // fixed-order, so the step is bit-reproducible run to run.
+#include <cstdlib>
+
 #include "ctc_core.cuh"
 #include "fused_args.cuh"
 #include "myers_core.cuh"
@@ -58,7 +60,7 @@ __device__ __forceinline__ int cdf_count32(const float (&c)[32], float tau) {
 // ------------------------------------------------------------------------------------------------ CTC role
 // warp 0: alpha recurrence, warp 1: beta recurrence; every other warp is a gradient worker, even warps on the
 // alpha side, odd warps on the beta side (G = (warps - 2) / 2 per direction).
-// kGT (long utterances): the fp64 softmax tile does not fit in shared memory; it is written to the global
+// kGT (long utterances): the fp32 softmax tile does not fit in shared memory; it is written to the global
 // workspace instead, the walkers stream it back through 32-row cp.async rings and the workers fetch their
 // p_t(lane) with the lattice row.  Shared memory then no longer depends on T.
 template <int SPL, int kThreads, bool kGT>
@@ -68,27 +70,27 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     constexpr int kMidThreads = 32 * (2 + 2 * G);
     const int warp = threadIdx.x >> 5;
     const int T = a.T, V = a.V;
-    const int RS = ctc_row_stride(V);
+    const int RS = ctc_row_stride_f32(V);
     // shared-memory carve-up (see fused_smem)
     // [T][RS] between two pairs of guard rows: the walkers load the probabilities two frames ahead and run two rows
     // past either end (the guard values are loaded and never used)
     const int RSR = RS <= 32 ? 32 : 64;                                  // ring row stride (power of two)
-    const size_t pring_bytes = (size_t)kPRows * RSR * 8;
-    double* tile;
-    double* pring_a = nullptr;
-    double* pring_b = nullptr;
+    const size_t pring_bytes = (size_t)kPRows * RSR * 4;
+    float* tile;
+    float* pring_a = nullptr;
+    float* pring_b = nullptr;
     unsigned char* p;
     if (kGT) {
         tile = a.tile_g + ((size_t)b * (T + 2) + 1) * RS;
         // the dynamic shared memory window is 1 KB aligned at least; align the rings to their size by address
         const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw);
         const unsigned pad = (unsigned)((pring_bytes - (base & (pring_bytes - 1))) & (pring_bytes - 1));
-        pring_a = reinterpret_cast<double*>(smem_raw + pad);
-        pring_b = reinterpret_cast<double*>(smem_raw + pad + pring_bytes);
+        pring_a = reinterpret_cast<float*>(smem_raw + pad);
+        pring_b = reinterpret_cast<float*>(smem_raw + pad + pring_bytes);
         p = smem_raw + pad + 2 * pring_bytes;
     } else {
-        tile = reinterpret_cast<double*>(smem_raw) + 2 * RS;
-        p = smem_raw + (size_t)(T + 4) * RS * 8;
+        tile = reinterpret_cast<float*>(smem_raw) + 2 * RS;
+        p = smem_raw + (((size_t)(T + 4) * RS * 4 + 15) & ~(size_t)15);
     }
     unsigned char* const stage_base = p;
     GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
@@ -117,8 +119,8 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         PGASR_STAMP(b == 0 && threadIdx.x == 0, 1);
         // softmax tile.  The raw logits are staged through the (not yet used) ring region with cp.async, then one
         // thread per frame makes three passes over its row -- max, exp + sum, normalise -- visiting the classes in
-        // a per-thread rotated order so that neither the staged reads (row stride V floats) nor the fp64 tile
-        // writes (row stride RS doubles) collide on a shared-memory bank.  (One warp per frame with a lane per
+        // a per-thread rotated order so that neither the staged reads (row stride V floats) nor the fp32 tile
+        // writes (row stride RS floats) collide on a shared-memory bank.  (One warp per frame with a lane per
         // class was measured at twice the time, 17.9k against 9k cycles: 5 shuffles + a redux per frame.)
         const float* lg = a.logits + (size_t)b * T * V;
         {
@@ -150,7 +152,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                     // the row lives in registers in rotated order (slot k holds class (k + t) & 31): the order does
                     // not matter for the max and the sum, every load / exp / store is independent of the others
                     const float* zr = stage + (size_t)t * V;
-                    double* orow = tile + (size_t)(c0 + t) * RS;
+                    float* orow = tile + (size_t)(c0 + t) * RS;
                     float x[32];
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
@@ -171,9 +173,9 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const int idx = (k + t) & 31;
-                        if (idx < RS) orow[idx] = (double)(x[k] * inv);
+                        if (idx < RS) orow[idx] = x[k] * inv;
                     }
-                    for (int idx = 32; idx < RS; ++idx) orow[idx] = 0.0;
+                    for (int idx = 32; idx < RS; ++idx) orow[idx] = 0.0f;
                 }
                 if (kGT) __threadfence_block();            // the rows go to global memory: order them before the barrier
                 __syncthreads();
@@ -540,6 +542,11 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
 #endif
     if (threadIdx.x == 0) s_ticket = atomicAdd(a.ctrl, 1u);
     __syncthreads();
+    // Programmatic dependent launch: everything above (CTA start, role ticket on this step's own control block)
+    // overlaps the tail of the previous kernel in the stream; nothing below may touch global memory before that kernel
+    // has completed and flushed.  The next launch may start as soon as every CTA of this grid got here.
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const unsigned ticket = s_ticket;
     const unsigned n_ctc = a.do_ctc ? (unsigned)a.B : 0u;
     if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT>(a, (int)ticket, smem_raw);
@@ -591,8 +598,19 @@ static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
         smem_set = smem;
     }
     const int grid = (a.do_ctc ? a.B : 0) + (a.do_pg ? a.B : 0);
-    pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream><<<grid, kThreads, smem, st>>>(a);
-    PGASR_LAUNCH_CHECK();
+    static const bool no_pdl = getenv("PGASR_NO_PDL") != nullptr;     // (A/B measurements)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    PGASR_CUDA_TRY(cudaLaunchKernelEx(&cfg, pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream>, a));
+    ++g_launches;
     return PGASR_OK;
 }
 

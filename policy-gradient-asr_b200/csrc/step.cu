@@ -101,8 +101,8 @@ extern "C" size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, 
 
 extern "C" int pgasr_pg_ctc_step_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
     if (!workspace) return PGASR_ERR_INVALID_ARG;
-    // only the control block at the front has to start at zero; the kernel re-arms it after every step
-    const size_t n = workspace_bytes < 65536 ? workspace_bytes : 65536;
+    // only the two control blocks at the front have to start at zero; the kernel re-arms its block after every step
+    const size_t n = workspace_bytes < 131072 ? workspace_bytes : 131072;
     PGASR_CUDA_TRY(cudaMemsetAsync(workspace, 0, n, pgasr::as_stream(stream)));
     return PGASR_OK;
 }
