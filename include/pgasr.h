@@ -4,7 +4,8 @@
  * The upstream project is pure Python: its "plugin interface" for this path is a handful of Python
  * functions and one nn.Module slot.  This header is what those bind to.  Every
  * entry point is extern "C", takes plain device pointers and sizes, allocates nothing, keeps no
- * global state, enqueues its work on the caller's stream (a cudaStream_t passed as void*; NULL = the
+ * global state (one exception: the parity of a step workspace, see pgasr_pg_ctc_step), enqueues its work on the
+ * caller's stream (a cudaStream_t passed as void*; NULL = the
  * legacy default stream) and returns a pgasr_status.  All pointers are device pointers borrowed until
  * the stream work completes, unless a parameter says "host".  There is no CPU fallback: without a
  * sm_100 device every compute call returns PGASR_ERR_NO_DEVICE / a CUDA error.
@@ -136,7 +137,11 @@ PGASR_API int pgasr_nll_sum_backward(const int64_t* target, const float* grad_ou
  * Optional outputs (NULL to skip): rewards, logp, hyp_len, dist, nll, samples.
  * workspace: pgasr_pg_ctc_step_workspace_bytes(B,T,V,K,Lmax) bytes, 256-byte aligned, armed ONCE with
  * pgasr_pg_ctc_step_workspace_init before its first use (and again after a step that returned an error);
- * one workspace serves one stream at a time.  V <= 32, K <= 64.  One kernel launch for every shape whose sample
+ * one workspace serves one stream at a time.  The step kernel is launched with programmatic stream serialisation:
+ * back-to-back steps on one stream overlap the launch of step n+1 with the tail of step n (the CTAs of n+1 wait on
+ * the grid dependency before they touch any input or output); for that the workspace holds two control blocks that
+ * consecutive calls use alternately -- the library remembers, per workspace pointer, which one is next (host side).
+ * V <= 32, K <= 64.  One kernel launch for every shape whose sample
  * buffers fit an SM (2 K T <= ~215 KB); targets / in_len / tgt_len and the small outputs may live in pinned host
  * memory mapped into the device (they are read once per CTA / written once).                       */
 PGASR_API size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax);
