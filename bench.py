@@ -105,7 +105,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -332,14 +332,33 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.result(),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; see main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
+    # stdout must carry exactly one JSON line: libraries that print there (NCCL's version banner under torchrun) are
+    # sent to stderr by pointing fd 1 at fd 2 for the lifetime of the run; the JSON line is written to the saved fd
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
