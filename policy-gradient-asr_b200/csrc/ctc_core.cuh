@@ -471,6 +471,17 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
 __device__ __forceinline__ void st_lattice(double2* ptr, double x, double y, unsigned long long pol) {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;\n" ::"l"(ptr), "d"(x), "d"(y), "l"(pol) : "memory");
 }
+// 32-byte flavours (sm_100: STG/LDG.256): a lane's four label values of a frame in one access.  Lattice rows with
+// 8 or more states per lane are laid out [SPL/8][32 lanes][2 double2] so that they apply; SPL 4 keeps [32 lanes] double2.
+__device__ __forceinline__ void st_lattice4(double2* ptr, double x, double y, double z, double w, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(ptr), "d"(x), "d"(y), "d"(z), "d"(w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void ld_lattice4(const double2* ptr, unsigned long long pol, double2& lo, double2& hi) {
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;\n"
+                 : "=d"(lo.x), "=d"(lo.y), "=d"(hi.x), "=d"(hi.y) : "l"(ptr), "l"(pol));
+}
+template <int SPL>
+__device__ __forceinline__ int lat_lane_off(int lane) { return SPL >= 8 ? 2 * lane : lane; }   // in double2 units
 __device__ __forceinline__ double2 ld_lattice(const double2* ptr, unsigned long long pol) {
     double2 v;
     asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;\n" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol));
@@ -613,12 +624,19 @@ __device__ __forceinline__ void ctc_walk_frame(CtcWalk<SPL, kAlpha>& w, double2*
 #ifndef EXP_NO_LATSTORE
     if (kFirst) {
         if (w.act) {
+            if constexpr (SPL >= 8) {
 #pragma unroll
-            for (int jj = 0; jj < SPL / 4; ++jj) st_lattice(dst + jj * 32, w.st.a[4 * jj + 1], w.st.a[4 * jj + 3], w.l2pol);
-            if (kMid) {
+                for (int j2 = 0; j2 < SPL / 8; ++j2)
+                    st_lattice4(dst + j2 * 64, w.st.a[8 * j2 + 1], w.st.a[8 * j2 + 3], w.st.a[8 * j2 + 5], w.st.a[8 * j2 + 7], w.l2pol);
+                if (kMid) {
 #pragma unroll
-                for (int jj = 0; jj < SPL / 4; ++jj)
-                    st_lattice(dst + (SPL / 4 + jj) * 32, w.st.a[4 * jj], w.st.a[4 * jj + 2], w.l2pol);
+                    for (int j2 = 0; j2 < SPL / 8; ++j2)
+                        st_lattice4(dst + (SPL / 4) * 32 + j2 * 64, w.st.a[8 * j2], w.st.a[8 * j2 + 2], w.st.a[8 * j2 + 4],
+                                    w.st.a[8 * j2 + 6], w.l2pol);
+                }
+            } else {
+                st_lattice(dst, w.st.a[1], w.st.a[3], w.l2pol);
+                if (kMid) st_lattice(dst + 32, w.st.a[0], w.st.a[2], w.l2pol);
             }
         }
     }
@@ -644,14 +662,15 @@ template <int SPL, bool kAlpha>
 __device__ __forceinline__ void ctc_walk_publish_norm(const CtcWalk<SPL, kAlpha>& w, const double* lat_row,
                                                       const int* exp_p, double* norm) {
     const int lane = threadIdx.x & 31;
-    const double2* lp = reinterpret_cast<const double2*>(lat_row) + lane;
+    const double2* lp = reinterpret_cast<const double2*>(lat_row) + lat_lane_off<SPL>(lane);
     double o[SPL];
 #pragma unroll
     for (int jj = 0; jj < SPL / 4; ++jj) {
         double2 lab = make_double2(0.0, 0.0), blk = make_double2(0.0, 0.0);
         if (w.act) {
-            lab = __ldcg(lp + jj * 32);
-            blk = __ldcg(lp + (SPL / 4 + jj) * 32);
+            const int off = SPL >= 8 ? (jj >> 1) * 64 + (jj & 1) : jj * 32;   // (see st_lattice4)
+            lab = __ldcg(lp + off);
+            blk = __ldcg(lp + (SPL / 4) * 32 + off);
         }
         o[4 * jj] = blk.x; o[4 * jj + 1] = lab.x; o[4 * jj + 2] = blk.y; o[4 * jj + 3] = lab.y;
     }
@@ -758,7 +777,7 @@ __device__ __forceinline__ void ctc_walk_tile(const float* tile, const int32_t* 
 
     // ---- first half: pre-emission sums go to the lattice for the other direction -----------------
     {
-        double2* lp = reinterpret_cast<double2*>(lat_u + (size_t)t0 * (SPL * 32)) + lane;
+        double2* lp = reinterpret_cast<double2*>(lat_u + (size_t)t0 * (SPL * 32)) + lat_lane_off<SPL>(lane);
         const ptrdiff_t lstride = kAlpha ? (SPL / 2) * 32 : -(SPL / 2) * 32;
         int* ep = exp_u + t0;
         const int estride = kAlpha ? 1 : -1;
@@ -846,14 +865,21 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
         const int q = min(nb * kBatchOf<SPL> + min(g + r * G, kBatchOf<SPL> - 1), n2 - 1);   // clamped: a stale row is loaded, never used
         const int step = n_first + q;
         const int t = kAlpha ? step : Tb - 1 - step;
-        const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lane;
+        const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lat_lane_off<SPL>(lane);
 #ifdef EXP_NO_LATTICE
 #pragma unroll
         for (int jj = 0; jj < SPL / 4; ++jj) wk.o[r][jj] = make_double2(1.0 + lane, 0.5);
         wk.eo[r] = 0; (void)lp;
 #else
+        if constexpr (SPL >= 8) {
 #pragma unroll
-        for (int jj = 0; jj < SPL / 4; ++jj) wk.o[r][jj] = act ? ld_lattice(lp + jj * 32, pol) : make_double2(0.0, 0.0);
+            for (int j2 = 0; j2 < SPL / 8; ++j2) {
+                wk.o[r][2 * j2] = wk.o[r][2 * j2 + 1] = make_double2(0.0, 0.0);
+                if (act) ld_lattice4(lp + j2 * 64, pol, wk.o[r][2 * j2], wk.o[r][2 * j2 + 1]);
+            }
+        } else {
+            wk.o[r][0] = act ? ld_lattice(lp, pol) : make_double2(0.0, 0.0);
+        }
         wk.eo[r] = __ldcg(exp_u + t);
         if (kGT) wk.prow[r] = (double)__ldcg(tile + (size_t)t * RS + min(lane, RS - 1));
 #endif

@@ -709,3 +709,32 @@ def test_step_hybrid_path_when_samples_do_not_fit(cuda):
     n0 = _native.lib().pgasr_launch_count()
     step_case(cuda, 2, 1800, 30, 64, 50, seed=9, ragged=True, regime="random", reward="cer", baseline="loo")
     assert _native.lib().pgasr_launch_count() - n0 > 1
+
+
+@pytest.mark.gpu
+def test_step_back_to_back_distinct_batches(cuda):
+    """Programmatic dependent launch: steps on DIFFERENT batches enqueued back to back on one workspace (no host sync in
+    between, so the CTAs of step n+1 are placed while step n runs) must each give exactly what the same step gives
+    alone on a fresh workspace."""
+    from pgasr_b200 import functional as F
+    B, T, V, K, L = 64, 500, 30, 16, 100
+    batches = []
+    for s in range(5):
+        lg, tg, il, tl, _ = make_batch(B, T, V, K, L, seed=100 + s, ragged=(s % 2 == 1))
+        batches.append(tuple(dev_t(x, cuda) for x in (lg, tg, il, tl)))
+    refs = []
+    for s, (lg, tg, il, tl) in enumerate(batches):
+        out = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=s, want=("rewards", "nll"))
+        torch.cuda.synchronize()
+        refs.append({k: out[k].clone() for k in ("loss", "dlogits", "rewards", "nll")})
+    ws = None
+    outs = []
+    for rep in range(6):
+        for s, (lg, tg, il, tl) in enumerate(batches):
+            out = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=s, workspace=ws, want=("rewards", "nll"))
+            ws = out["workspace"]
+            outs.append((s, out))
+    torch.cuda.synchronize()
+    for s, out in outs:
+        for k in ("loss", "dlogits", "rewards", "nll"):
+            assert torch.equal(out[k], refs[s][k]), (s, k)
