@@ -36,6 +36,40 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 
 constexpr int kFusedMaxK = 64;
 
+// Second ticket (thread 0 of a CTA, once): the CTA that draws the last one reduces the loss at the end of the kernel
+// and re-arms the control block.  It is drawn as EARLY as the protocol allows -- by a CTC CTA right after it released
+// its flag, by a PG CTA right after it acquired that flag and before its read-modify-write of dlogits -- so that the
+// fence in front of it does not have to wait for 60 KB of freshly issued stores (that cost ~1 us at the end of the
+// kernel).  Everything the last CTA reads (loss_terms[b], nll_ws[b]) was written by thread 0 of the owning CTA before
+// this point; nobody reads a flag after its CTA drew this ticket, so re-arming the flags is safe.
+__device__ __forceinline__ void draw_done_ticket(const FusedArgs& a, unsigned* s_last) {
+    __threadfence();
+    *s_last = atomicAdd(a.ctrl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+}
+
+// One warp of the CTA that drew the last ticket: the loss in a fixed order, then the control block re-armed.
+__device__ __forceinline__ void loss_reduce_and_rearm(const FusedArgs& a) {
+    const int lane = threadIdx.x & 31;
+    __threadfence();
+    const float* nl = a.nll_ws;
+    float pg = 0.0f, ct = 0.0f;
+    for (int b = lane; b < a.B; b += 32) {
+        if (a.do_pg) pg += __ldcg(a.loss_terms + b);
+        if (a.do_ctc) ct += __ldcg(nl + b);
+        a.ctrl[4 + b] = 0u;
+    }
+    pg = warp_sum(pg);
+    ct = warp_sum(ct);
+    if (lane == 0) {
+        float l = 0.0f;
+        if (a.do_pg) l += a.w_pg * pg / ((float)a.B * (float)a.K);
+        if (a.do_ctc) l += a.w_ctc * ct / (float)a.B;
+        a.loss[0] = l;
+        a.ctrl[0] = 0u;
+        a.ctrl[1] = 0u;
+    }
+}
+
 // Number of entries of a non-decreasing 32-entry register array that are <= tau: a binary search written as a tree
 // of selects (26 FSEL + 5 FSETP instead of 32 compare-and-add pairs).  Same count as the linear scan of the sampler
 // spec because the CDF is non-decreasing (sums of non-negative terms, round to nearest).
@@ -64,7 +98,7 @@ __device__ __forceinline__ int cdf_count32(const float (&c)[32], float tau) {
 // workspace instead, the walkers stream it back through 32-row cp.async rings and the workers fetch their
 // p_t(lane) with the lattice row.  Shared memory then no longer depends on T.
 template <int SPL, int kThreads, bool kGT>
-__device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw) {
+__device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last) {
     constexpr int G = (kThreads / 32 - 2) / 2;             // gradient workers per direction
     constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;      // frames of a batch per worker
     constexpr int kMidThreads = 32 * (2 + 2 * G);
@@ -210,8 +244,9 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     __syncthreads();
     PGASR_STAMP(b == 0 && threadIdx.x == 0, 3);
     if (threadIdx.x == 0) {
-        if (a.nll) a.nll[b] = *nll_u;                      // the caller's copy (possibly host memory); the loss reads nll_ws
         st_release(a.ctrl + 4 + b, 1u);
+        draw_done_ticket(a, s_last);
+        if (a.nll) a.nll[b] = *nll_u;                      // the caller's copy (possibly host memory); the loss reads nll_ws
     }
 }
 
@@ -219,7 +254,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
 // kStream (long utterances): no [T][V] tile in shared memory -- a thread reads its frame's logits straight from
 // global memory, and the gradient rows are formed in registers and added to dlogits row by row.
 template <int W, int kThreads, bool kStream>
-__device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw) {
+__device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last) {
     constexpr int kWarps = kThreads / 32;
     constexpr int VP = 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -429,13 +464,14 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     if constexpr (kStream) {
         // one thread per frame: the K sample ids into registers, then for every class the advantage mass that fell
         // on it; the row is added to (or, without a CTC term, stored as) dlogits directly
-        if (a.do_ctc) {
-            if (threadIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            if (a.do_ctc) {
                 const unsigned* flag = a.ctrl + 4 + b;
-                while (ld_acquire(flag) == 0u) __nanosleep(200);
+                while (ld_acquire(flag) == 0u) __nanosleep(40);
             }
-            __syncthreads();
+            draw_done_ticket(a, s_last);
         }
+        __syncthreads();
         PGASR_STAMP(dbg, 37);
         for (int t = threadIdx.x; t < T; t += kThreads) {
             float* out = dlog_u + (size_t)t * V;
@@ -483,30 +519,37 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
 
     PGASR_STAMP(dbg, 36);
     // ---- P6: add the tile onto the CTC rows (or store it when there is no CTC term) ---------------
-    if (a.do_ctc) {
-        if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
+        if (a.do_ctc) {
             const unsigned* flag = a.ctrl + 4 + b;
-            while (ld_acquire(flag) == 0u) __nanosleep(200);
+            while (ld_acquire(flag) == 0u) __nanosleep(40);
         }
-        __syncthreads();
+        draw_done_ticket(a, s_last);
     }
+    __syncthreads();
     PGASR_STAMP(dbg, 37);
     if ((((size_t)T * V * 4) & 15) == 0) {
         float4* d4 = reinterpret_cast<float4*>(dlog_u);
         const float4* t4 = reinterpret_cast<const float4*>(ztile);
         const int n4 = T * V / 4;
-        if (a.do_ctc) {
+        // In the CTA that drew the last ticket the last warp reduces the loss (three dependent L2 round trips) while
+        // the other warps share the pass among themselves, instead of after it.
+        const bool last = *s_last != 0u;
+        const int nt = last ? kThreads - 32 : kThreads;
+        if (last && warp == kWarps - 1) {
+            loss_reduce_and_rearm(a);
+        } else if (a.do_ctc) {
             // eight L2 reads in flight per thread (one at a time, every pass waited out the full L2 latency)
-            for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * kThreads) {
+            for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * nt) {
                 float4 c[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int i = i0 + u * kThreads;
+                    const int i = i0 + u * nt;
                     c[u] = i < n4 ? __ldcg(d4 + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int i = i0 + u * kThreads;
+                    const int i = i0 + u * nt;
                     if (i < n4) {
                         const float4 g = t4[i];
                         d4[i] = make_float4(g.x + c[u].x, g.y + c[u].y, g.z + c[u].z, g.w + c[u].w);
@@ -514,9 +557,10 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
                 }
             }
         } else {
-            for (int i = threadIdx.x; i < n4; i += kThreads) d4[i] = t4[i];
+            for (int i = threadIdx.x; i < n4; i += nt) d4[i] = t4[i];
         }
     } else {
+        if (*s_last != 0u && warp == kWarps - 1) loss_reduce_and_rearm(a);    // (then it joins the pass)
         for (int i = threadIdx.x; i < T * V; i += kThreads)
             dlog_u[i] = a.do_ctc ? __ldcg(dlog_u + i) + ztile[i] : ztile[i];
     }
@@ -549,41 +593,17 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const unsigned ticket = s_ticket;
     const unsigned n_ctc = a.do_ctc ? (unsigned)a.B : 0u;
-    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT>(a, (int)ticket, smem_raw);
-    else fused_pg_role<SPL / 2, kThreads, kStream>(a, (int)(ticket - n_ctc), smem_raw);
+    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT>(a, (int)ticket, smem_raw, &s_last);
+    else fused_pg_role<SPL / 2, kThreads, kStream>(a, (int)(ticket - n_ctc), smem_raw, &s_last);
 
 #ifdef PGASR_TIMING
     if (threadIdx.x == 0 && ticket < 2048) { g_cta_ns[ticket][0] = t_start; g_cta_ns[ticket][1] = gtime(); }
 #endif
-    // ---- second ticket: the last CTA reduces the loss (fixed order) and re-arms the control block ----
-    // (what the last CTA reads -- loss_terms[b], nll_ws[b] -- was written by thread 0 of the owning CTA, so only that
-    // thread's writes have to be ordered before the ticket; the rows of dlogits are published by the kernel boundary)
+    // ---- the CTA that drew the last second ticket (draw_done_ticket, inside the roles) reduces the loss in a fixed
+    // order and re-arms the control block; the rows of dlogits are published by the kernel boundary ----
+    // (a PG CTA with its tile in shared memory has done that already, next to its read-modify-write pass)
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(a.ctrl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x < 32) {
-        __threadfence();
-        const float* nl = a.nll_ws;
-        float pg = 0.0f, ct = 0.0f;
-        for (int b = threadIdx.x; b < a.B; b += 32) {
-            if (a.do_pg) pg += __ldcg(a.loss_terms + b);
-            if (a.do_ctc) ct += __ldcg(nl + b);
-            a.ctrl[4 + b] = 0u;
-        }
-        pg = warp_sum(pg);
-        ct = warp_sum(ct);
-        if (threadIdx.x == 0) {
-            float l = 0.0f;
-            if (a.do_pg) l += a.w_pg * pg / ((float)a.B * (float)a.K);
-            if (a.do_ctc) l += a.w_ctc * ct / (float)a.B;
-            a.loss[0] = l;
-            a.ctrl[0] = 0u;
-            a.ctrl[1] = 0u;
-        }
-    }
+    if (s_last && threadIdx.x < 32 && (ticket < n_ctc || kStream)) loss_reduce_and_rearm(a);
 #ifdef PGASR_TIMING
     if (threadIdx.x == 0 && ticket < 2048) g_cta_ns[ticket][2] = gtime();
 #endif
