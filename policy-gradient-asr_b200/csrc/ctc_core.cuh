@@ -850,11 +850,26 @@ struct CtcWorker {
     int eo[kPer];
     double prow[kPer];            // global-tile mode: p_t(lane) of the frame, fetched with the lattice row
     unsigned long long l2pol;     // L2 cache policy of the lattice loads (evict_first: the row is dead after this read)
+    int tF[kPer], qF[kPer];       // frame and second-half index of the NEXT fetch of each owned frame (they advance by
+                                  // a batch per fetch: no per-batch index arithmetic)
+    const double2* lat2;          // the utterance's lattice as double2, this lane's offset folded in
 };
 
+template <int SPL, int G, bool kAlpha>
+__device__ __forceinline__ void ctc_worker_fetch_init(CtcWorker<SPL, G, kAlpha>& wk, int g, int n_first, int Tb,
+                                                      const double* __restrict__ lat_u) {
+    const int lane = threadIdx.x & 31;
+    wk.lat2 = reinterpret_cast<const double2*>(lat_u) + lat_lane_off<SPL>(lane);
+#pragma unroll
+    for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kPer; ++r) {
+        const int q = g + r * G;
+        wk.qF[r] = q < kBatchOf<SPL> ? q : (1 << 28);     // (a frame this worker never owns: always out of range)
+        wk.tF[r] = kAlpha ? n_first + q : Tb - 1 - n_first - q;
+    }
+}
+
 template <int SPL, int G, bool kAlpha, bool kGT = false>
-__device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, int nb, int g, int n_first, int n2,
-                                                 int Tb, int S, const double* __restrict__ lat_u,
+__device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, int n2, int S,
                                                  const int* __restrict__ exp_u, const float* tile = nullptr,
                                                  int RS = 0) {
     const int lane = threadIdx.x & 31;
@@ -862,10 +877,9 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
     const unsigned long long pol = wk.l2pol;
 #pragma unroll
     for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kPer; ++r) {
-        const int q = min(nb * kBatchOf<SPL> + min(g + r * G, kBatchOf<SPL> - 1), n2 - 1);   // clamped: a stale row is loaded, never used
-        const int step = n_first + q;
-        const int t = kAlpha ? step : Tb - 1 - step;
-        const double2* lp = reinterpret_cast<const double2*>(lat_u + (size_t)t * (SPL * 32)) + lat_lane_off<SPL>(lane);
+        const int t = wk.tF[r];
+        const bool valid = wk.qF[r] < n2;                 // (beyond the utterance: nothing is loaded, zeros are used)
+        const double2* lp = wk.lat2 + (size_t)t * (SPL * 16);
 #ifdef EXP_NO_LATTICE
 #pragma unroll
         for (int jj = 0; jj < SPL / 4; ++jj) wk.o[r][jj] = make_double2(1.0 + lane, 0.5);
@@ -875,14 +889,16 @@ __device__ __forceinline__ void ctc_worker_fetch(CtcWorker<SPL, G, kAlpha>& wk, 
 #pragma unroll
             for (int j2 = 0; j2 < SPL / 8; ++j2) {
                 wk.o[r][2 * j2] = wk.o[r][2 * j2 + 1] = make_double2(0.0, 0.0);
-                if (act) ld_lattice4(lp + j2 * 64, pol, wk.o[r][2 * j2], wk.o[r][2 * j2 + 1]);
+                if (act && valid) ld_lattice4(lp + j2 * 64, pol, wk.o[r][2 * j2], wk.o[r][2 * j2 + 1]);
             }
         } else {
-            wk.o[r][0] = act ? ld_lattice(lp, pol) : make_double2(0.0, 0.0);
+            wk.o[r][0] = (act && valid) ? ld_lattice(lp, pol) : make_double2(0.0, 0.0);
         }
-        wk.eo[r] = __ldcg(exp_u + t);
-        if (kGT) wk.prow[r] = (double)__ldcg(tile + (size_t)t * RS + min(lane, RS - 1));
+        wk.eo[r] = valid ? __ldcg(exp_u + t) : 0;
+        if (kGT) wk.prow[r] = valid ? (double)__ldcg(tile + (size_t)t * RS + min(lane, RS - 1)) : 0.0;
 #endif
+        wk.qF[r] += kBatchOf<SPL>;
+        wk.tF[r] += kAlpha ? kBatchOf<SPL> : -kBatchOf<SPL>;
     }
 }
 
@@ -1092,7 +1108,8 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const float* tile, const 
     int gb[kPer];
     const int S = 2 * L + 1;
     double prow[kPer];
-    if (nbatch > 0) ctc_worker_fetch<SPL, G, kAlpha, kGT>(wk, 0, g, n_first, n2, Tb, S, lat_u, exp_u, tile, RS);
+    ctc_worker_fetch_init<SPL, G, kAlpha>(wk, g, n_first, Tb, lat_u);
+    if (nbatch > 0) ctc_worker_fetch<SPL, G, kAlpha, kGT>(wk, n2, S, exp_u, tile, RS);
     for (int nb = 0; nb < nbatch; ++nb) {
         const int buf = nb & 1;
 #ifdef PGASR_TIMING
@@ -1119,7 +1136,7 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const float* tile, const 
 #pragma unroll
             for (int r = 0; r < kPer; ++r) prow[r] = wk.prow[r];
         }
-        if (nb + 1 < nbatch) ctc_worker_fetch<SPL, G, kAlpha, kGT>(wk, nb + 1, g, n_first, n2, Tb, S, lat_u, exp_u, tile, RS);
+        if (nb + 1 < nbatch) ctc_worker_fetch<SPL, G, kAlpha, kGT>(wk, n2, S, exp_u, tile, RS);
         ctc_worker_phase_b<SPL, G, kAlpha, kGT>(wk, prow, nm, nb, g, n_first, n2, Tb, tile, V, RS, blank, grad_scale,
                                                 dlog_u, ring, gam, gb, ccnt, cmax, cpos);
 #ifdef PGASR_TIMING
