@@ -852,6 +852,7 @@ struct CtcWorker {
     unsigned long long l2pol;     // L2 cache policy of the lattice loads (evict_first: the row is dead after this read)
     int tF[kPer], qF[kPer];       // frame and second-half index of the NEXT fetch of each owned frame (they advance by
                                   // a batch per fetch: no per-batch index arithmetic)
+    int tB[kPer], qB[kPer];       // the same for the NEXT phase B (it runs one fetch behind)
     const double2* lat2;          // the utterance's lattice as double2, this lane's offset folded in
 };
 
@@ -863,8 +864,8 @@ __device__ __forceinline__ void ctc_worker_fetch_init(CtcWorker<SPL, G, kAlpha>&
 #pragma unroll
     for (int r = 0; r < CtcWorker<SPL, G, kAlpha>::kPer; ++r) {
         const int q = g + r * G;
-        wk.qF[r] = q < kBatchOf<SPL> ? q : (1 << 28);     // (a frame this worker never owns: always out of range)
-        wk.tF[r] = kAlpha ? n_first + q : Tb - 1 - n_first - q;
+        wk.qF[r] = wk.qB[r] = q < kBatchOf<SPL> ? q : (1 << 28);     // (a frame this worker never owns: always out of range)
+        wk.tF[r] = wk.tB[r] = kAlpha ? n_first + q : Tb - 1 - n_first - q;
     }
 }
 
@@ -1003,7 +1004,7 @@ __device__ __forceinline__ void ctc_worker_phase_a(const CtcWorker<SPL, G, kAlph
 // count point at label slot 16*SPL-1, whose state 32*SPL-1 lies beyond S for every transcript (always 0), so the
 // gather is branch free; cmax (warp uniform) bounds the rare tail of classes with more than kClsRegs labels.
 template <int SPL, int G, bool kAlpha, bool kGT = false>
-__device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlpha>& wk, const double (&prow)[(kBatchOf<SPL> + G - 1) / G],
+__device__ __forceinline__ void ctc_worker_phase_b(CtcWorker<SPL, G, kAlpha>& wk, const double (&prow)[(kBatchOf<SPL> + G - 1) / G],
                                                    const WorkerNorm& nm, int nb, int g, int n_first, int n2, int Tb,
                                                    const float* tile, int V, int RS, int blank, float grad_scale,
                                                    float* __restrict__ dlog_u, const GradRing<SPL>& ring,
@@ -1039,16 +1040,14 @@ __device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlph
                     occ[r] += i < ccnt ? gam[r * kGam + ring.cls_pos[ring.cls_off[lane] + i]] : 0;
         }
 #endif
+        const int lane_c = min(lane, RS - 1);
 #pragma unroll
         for (int r = 0; r < kPer; ++r) {
-            const int qi = g + r * G;
-            const int q = nb * kBatchOf<SPL> + qi;
-            const bool valid = qi < kBatchOf<SPL> && q < n2;
+            const bool valid = wk.qB[r] < n2;
+            const int t = wk.tB[r];
             if (kUncond || valid) {
-                const int step = n_first + (kUncond ? min(q, n2 - 1) : q);
-                const int t = kAlpha ? step : Tb - 1 - step;
                 const int oc = lane == blank ? gb[r] : occ[r];
-                const double pv = kGT ? prow[r] : (double)tile[(size_t)t * RS + min(lane, RS - 1)];
+                const double pv = kGT ? prow[r] : (valid ? (double)tile[t * RS + lane_c] : 0.0);
                 const int pfix = __double2loint(fma(pv, kCtcFix, kCtcMagic));
                 const float gval = nm.dead ? 0.0f : grad_scale * ((float)(pfix - oc) * kCtcUnfix);
                 if (lane < V && valid) dlog_u[(size_t)t * V + lane] = gval;
@@ -1057,11 +1056,8 @@ __device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlph
     } else {
 #pragma unroll
         for (int r = 0; r < kPer; ++r) {
-            const int qi = g + r * G;
-            const int q = nb * kBatchOf<SPL> + qi;
-            if (qi < kBatchOf<SPL> && q < n2) {
-                const int step = n_first + q;
-                const int t = kAlpha ? step : Tb - 1 - step;
+            if (wk.qB[r] < n2) {
+                const int t = wk.tB[r];
                 const float* row = tile + (size_t)t * RS;
                 float* out = dlog_u + (size_t)t * V;
                 const int* gr = gam + r * kGam;
@@ -1076,6 +1072,12 @@ __device__ __forceinline__ void ctc_worker_phase_b(const CtcWorker<SPL, G, kAlph
             }
         }
     }
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+        wk.qB[r] += kBatchOf<SPL>;
+        wk.tB[r] += kAlpha ? kBatchOf<SPL> : -kBatchOf<SPL>;
+    }
+    (void)nb; (void)g; (void)n_first; (void)Tb;
     __syncwarp();
 }
 
