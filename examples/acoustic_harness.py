@@ -45,6 +45,78 @@ class AcousticModel(nn.Module):
         return self.head(out)
 
 
+def run(D, global_batch=256, T=500, V=30, K=16, L=100, steps=20, warmup=3):
+    """One data-parallel training job on the process group of `D` (bench.Dist: world, rank, local, dev).  Returns the
+    per-step time (max over ranks) and its breakdown: the loss step alone, the step without the gradient all-reduce
+    (DDP no_sync) and the all-reduce of a gradient-sized flat buffer alone."""
+    world, rank, dev = D.world, D.rank, D.dev
+    lo, hi = pgasr_b200.distributed.shard_range(global_batch, rank, world)
+    B = hi - lo
+    torch.manual_seed(1234 + rank)
+    model = AcousticModel(V).to(dev)
+    n_params = sum(p.numel() for p in model.parameters())
+    if world > 1:
+        model = nn.parallel.DistributedDataParallel(model, device_ids=[D.local])
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)                   # model.py:207
+    crit = pgasr_b200.PolicyGradCTCLoss(K=K, reward="cer", baseline="mean", seed=rank)
+    feats = torch.randn(B, 120, T, device=dev)
+    flen = torch.full((B,), T, dtype=torch.int32, device=dev)
+    trans = torch.randint(1, V, (B, L), dtype=torch.int32, device=dev)
+    tlen = torch.full((B,), L, dtype=torch.int32, device=dev)
+
+    def step(sync=True):
+        opt.zero_grad(set_to_none=True)
+        if world > 1 and not sync:
+            with model.no_sync():
+                loss = crit(model(feats, flen), trans, flen, tlen)
+                loss.backward()
+        else:
+            loss = crit(model(feats, flen), trans, flen, tlen)
+            loss.backward()
+        opt.step()
+        return loss
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return D.max_over_ranks(e0.elapsed_time(e1) / n), out
+
+    for _ in range(warmup):
+        step()
+    ms, loss = timed(step, steps)
+    ms_nosync, _ = timed(lambda: step(sync=False), max(steps // 2, 3)) if world > 1 else (ms, None)
+    # the gradient all-reduce alone: one flat fp32 buffer of the model's size (what DDP's buckets add up to)
+    ar_ms = 0.0
+    if world > 1:
+        flat = torch.zeros(n_params, device=dev)
+        for _ in range(3):
+            dist.all_reduce(flat)
+        ar_ms, _ = timed(lambda: dist.all_reduce(flat), 20)
+        loss = pgasr_b200.distributed.allreduce_mean(loss)
+    # the loss step alone, on this rank's logits
+    with torch.no_grad():
+        logits = model(feats, flen).detach()
+    for _ in range(3):
+        crit(logits.requires_grad_(True), trans, flen, tlen)
+    n0 = pgasr_b200._native.lib().pgasr_launch_count()
+    loss_ms, _ = timed(lambda: crit(logits.requires_grad_(True), trans, flen, tlen), 20)
+    per_step = (pgasr_b200._native.lib().pgasr_launch_count() - n0) / 20
+    return {"what": "full PG training step: acoustic model fwd/bwd + fused PG+CTC loss + optimizer",
+            "n_gpus": world, "global_batch": global_batch, "B_per_gpu": B, "T": T, "V": V, "K": K, "L": L,
+            "ms_per_step": float(ms), "utt_per_s": global_batch / float(ms) * 1e3,
+            "ms_per_step_without_allreduce": float(ms_nosync), "allreduce_exposed_ms": float(ms - ms_nosync),
+            "allreduce_alone_ms": float(ar_ms), "allreduce_bytes": 4 * n_params,
+            "loss_step_ms": float(loss_ms), "loss_launches_per_step": per_step, "loss": float(loss),
+            "mean_reward": float(crit.last["rewards"].mean())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--global-batch", type=int, default=256)
@@ -55,68 +127,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lo, hi = pgasr_b200.distributed.shard_range(args.global_batch, rank, world)
-    B = hi - lo
-    torch.manual_seed(1234 + rank)
-    model = AcousticModel(args.V).to(dev)
-    if world > 1:
-        model = nn.parallel.DistributedDataParallel(model, device_ids=[local])
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4)                   # model.py:207
-    crit = pgasr_b200.PolicyGradCTCLoss(K=args.K, reward="cer", baseline="mean", seed=rank)
-    feats = torch.randn(B, 120, args.T, device=dev)
-    flen = torch.full((B,), args.T, dtype=torch.int32, device=dev)
-    trans = torch.randint(1, args.V, (B, args.L), dtype=torch.int32, device=dev)
-    tlen = torch.full((B,), args.L, dtype=torch.int32, device=dev)
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        logits = model(feats, flen)
-        loss = crit(logits, trans, flen, tlen)
-        loss.backward()
-        opt.step()
-        return loss
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        loss = pgasr_b200.distributed.allreduce_mean(loss)
-    # the loss step alone, on this rank's logits
-    with torch.no_grad():
-        logits = model(feats, flen).detach()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(3):
-        crit(logits.requires_grad_(True), trans, flen, tlen)
-    k0.record()
-    for _ in range(20):
-        crit(logits.requires_grad_(True), trans, flen, tlen)
-    k1.record()
-    torch.cuda.synchronize()
-    if rank == 0:
-        print(json.dumps({"what": "full PG training step: acoustic model fwd/bwd + fused PG+CTC loss + optimizer",
-                          "n_gpus": world, "global_batch": args.global_batch, "B_per_gpu": B, "T": args.T, "V": args.V,
-                          "K": args.K, "L": args.L, "ms_per_step": float(ms), "utt_per_s": args.global_batch / float(ms) * 1e3,
-                          "loss_step_ms": k0.elapsed_time(k1) / 20, "loss": float(loss),
-                          "mean_reward": float(crit.last["rewards"].mean())}))
-    if world > 1:
-        dist.destroy_process_group()
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    D = bench.Dist()
+    res = run(D, args.global_batch, args.T, args.V, args.K, args.L, args.steps, args.warmup)
+    if D.rank == 0:
+        print(json.dumps(res))
+    D.close()
 
 
 if __name__ == "__main__":

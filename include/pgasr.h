@@ -57,8 +57,10 @@ typedef enum {
     PGASR_ERR_CUDA = -5           /* a CUDA call failed; pgasr_last_cuda_error() has the code */
 } pgasr_status;
 
-/* reward_mode: R = -ED  |  R = -ED/len(ref)  (the CER ratio of metrics.py:24-25) */
-enum { PGASR_REWARD_NEG_ED = 0, PGASR_REWARD_NEG_CER = 1 };
+/* reward_mode: R = -ED  |  R = -ED/len(ref)  (the CER ratio of metrics.py:24-25)  |  per-position rewards
+ * r_i = -(ED(ref, hyp[:i+1]) - ED(ref, hyp[:i])) (policy_grad.py:10-15) credited to the frames that can still
+ * influence them: reward-to-go G_t = sum over the symbols emitted at frames >= t (DESIGN.md "reward-to-go spec") */
+enum { PGASR_REWARD_NEG_ED = 0, PGASR_REWARD_NEG_CER = 1, PGASR_REWARD_ED_TO_GO = 2, PGASR_REWARD_MAX = 2 };
 /* baseline_mode: none | mean over the utterance's K samples | leave-one-out mean | external scalar */
 enum { PGASR_BASELINE_NONE = 0, PGASR_BASELINE_MEAN = 1, PGASR_BASELINE_LOO = 2, PGASR_BASELINE_VALUE = 3 };
 
@@ -123,8 +125,10 @@ PGASR_API int pgasr_ctc_loss_grad(const float* logits, const float* probs, const
 
 /* ---- a5: customNLLLoss (loss.py:13-17) ---------------------------------------------------------
  * inp [L,B,V] log-probs, target [B,L] int64.  loss = sum_i mean_b(-inp[i,b,target[b,i]]),
- * ignoring entries equal to ignore_index when ignore_index >= 0.
+ * ignoring entries equal to ignore_index (any value, e.g. torch's -100; PGASR_NO_IGNORE for none).  A target
+ * outside [0,V) that is not ignored makes the loss NaN (torch raises there); nothing is read out of bounds.
  * backward: grad_inp = grad_out * d loss / d inp (dense write, zero elsewhere).                 */
+#define PGASR_NO_IGNORE (-2147483647 - 1)
 PGASR_API int pgasr_nll_sum_forward(const float* inp, const int64_t* target, int L, int B, int V,
                           int ignore_index, float* loss, void* stream);
 PGASR_API int pgasr_nll_sum_backward(const int64_t* target, const float* grad_out, int L, int B, int V,
@@ -145,6 +149,7 @@ PGASR_API int pgasr_nll_sum_backward(const int64_t* target, const float* grad_ou
  * buffers fit an SM (2 K T <= ~215 KB); targets / in_len / tgt_len and the small outputs may live in pinned host
  * memory mapped into the device (they are read once per CTA / written once).                       */
 PGASR_API size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax);
+/* (init also forgets which control block the workspace pointer used last, so a freed and recycled pointer is safe) */
 PGASR_API int pgasr_pg_ctc_step_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 PGASR_API int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, const int32_t* in_len,
                       const int32_t* tgt_len, const float* uniforms, uint64_t seed,
@@ -154,6 +159,25 @@ PGASR_API int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, con
                       float* loss, float* dlogits, float* rewards, float* logp, int32_t* hyp_len,
                       int32_t* dist, float* nll, uint8_t* samples,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- n steps with one call (micro-batches of one optimiser step; a bench loop) ---------------------------
+ * steps: HOST array of n_steps records of DEVICE pointers, same meaning as the arguments of pgasr_pg_ctc_step
+ * (optional ones may be NULL); step i samples with Philox(seed_base + steps[i].seed).  The steps run back to back on
+ * `stream`, all on the one workspace; per step the host does one kernel launch and nothing else.
+ * to_go [B,K,T] int16 and r_pos [B,K,T] int8 (optional, reward_mode PGASR_REWARD_ED_TO_GO only): the reward-to-go of
+ * every frame and the per-position reward of every collapsed symbol (zero beyond hyp_len).                    */
+typedef struct pgasr_step_io {
+    const float* logits; const int32_t* targets; const int32_t* in_len; const int32_t* tgt_len;
+    const float* uniforms; uint64_t seed;
+    float* loss; float* dlogits;
+    float* rewards; float* logp; int32_t* hyp_len; int32_t* dist; float* nll; uint8_t* samples;
+    int16_t* to_go; int8_t* r_pos;
+} pgasr_step_io;
+PGASR_API int pgasr_pg_ctc_step_multi(const pgasr_step_io* steps, int n_steps, uint64_t seed_base,
+                            int B, int T, int V, int K, int Lmax, int blank,
+                            int reward_mode, int baseline_mode, float baseline_value,
+                            float w_pg, float w_ctc,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- CTC prefix beam search (upstream CTCdecoder.py:41-116, CTCDecoder.decode) -----------------------
  * probs [N,T,V] fp64 post-softmax (upstream takes the post-softmax array and works in Python floats), frames

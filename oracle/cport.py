@@ -55,6 +55,10 @@ def lib():
         L.orc_pg_loss_grad.argtypes = [f32p, i32p, u8p, f64p, i32p, i32p, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, f32p, f64p, f64p]
         L.orc_pg_loss_grad.restype = C.c_double
+        L.orc_pg_togo_loss_grad.argtypes = [f32p, i32p, u8p, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_double, f32p, C.POINTER(C.c_int16),
+                                            C.POINTER(C.c_int8), f64p]
+        L.orc_pg_togo_loss_grad.restype = C.c_double
         L.orc_ctc_loss_grad.argtypes = [f32p, i32p, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, f64p, f64p]
         L.orc_ctc_loss_grad.restype = None
@@ -189,6 +193,29 @@ def pg_loss_grad(logits, samples, logp, dist, in_len=None, tgt_len=None, Lmax=No
                                   int(baseline_mode), float(baseline_value),
                                   _p(rewards, C.c_float), _p(adv, C.c_double), _p(grad, C.c_double))
     return loss, rewards, adv, grad
+
+
+def pg_togo_loss_grad(logits, samples, targets, in_len=None, tgt_len=None, blank=0, baseline_mode=1,
+                      baseline_value=0.0, want_grad=True):
+    """per-position rewards (policy_grad.py:10-15) credited as reward-to-go.
+    -> loss, rewards [B,K] (= len(ref) - ED), to_go [B,K,T] int16, r_pos [B,K,T] int8, grad [B,T,V] fp64."""
+    logits = _f32(logits)
+    B, T, V = logits.shape
+    samples = np.ascontiguousarray(samples, np.uint8)
+    K = samples.shape[1]
+    targets = _i32(targets)
+    Lmax = targets.shape[1]
+    in_len, tgt_len = _i32(in_len), _i32(tgt_len)
+    rewards = np.zeros((B, K), np.float32)
+    to_go = np.zeros((B, K, T), np.int16)
+    r_pos = np.zeros((B, K, T), np.int8)
+    grad = np.zeros((B, T, V), np.float64) if want_grad else None
+    loss = lib().orc_pg_togo_loss_grad(_p(logits, C.c_float), _p(in_len, C.c_int32), _p(samples, C.c_uint8),
+                                       _p(targets, C.c_int32), _p(tgt_len, C.c_int32), B, T, V, K, Lmax,
+                                       int(blank), int(baseline_mode), float(baseline_value),
+                                       _p(rewards, C.c_float), _p(to_go, C.c_int16), _p(r_pos, C.c_int8),
+                                       _p(grad, C.c_double))
+    return loss, rewards, to_go, r_pos, grad
 
 
 def ctc_loss_grad(logits, targets, in_len=None, tgt_len=None, blank=0, want_grad=True):

@@ -15,6 +15,8 @@
  *   orc_nll_sum             loss.py:13-17         PINNED
  * Where the reference has NO code the oracle implements the written spec in DESIGN.md
  * ("parity unpinned" -- no upstream code, tests or vectors exist for these):
+ *   orc_pg_togo_loss_grad   DESIGN.md "reward-to-go spec": r_i is the PINNED last column of orc_edit_distance
+ *                           (policy_grad.py:10-15), the credit assignment over frames is this repo's spec (fp64)
  *   orc_softmax_sample      DESIGN.md "sampler spec"  (bit-exact contract with the CUDA kernel)
  *   orc_pg_loss_grad        DESIGN.md "policy gradient spec" (fp64)
  *   orc_ctc_loss_grad       DESIGN.md "CTC spec" (fp64 log-space alpha-beta; cross-checked
@@ -377,6 +379,85 @@ ORC_API double orc_pg_loss_grad(const float* logits, const int32_t* in_len,
 }
 
 /* ------------------------------------------------------------------------------------
+ * 8f.1  per-position rewards and reward-to-go (DESIGN.md "reward-to-go spec").
+ * Upstream's policy_grad.reward (policy_grad.py:10-15) scores position i of the COLLAPSED hypothesis with
+ *   r_i = -(c[i+1] - c[i]),  c[i] = ED(y*, yhat[:i])  (c[0] = len(y*); the t == 1 branch is r_0 + r_1),
+ * i.e. with the increments of the last column of the edit-distance table (orc_edit_distance's last_col,
+ * pinned by the reward_positions golden vectors).  A frame t of the sampled path can only influence the symbols
+ * emitted at frames >= t, so the return credited to the action at frame t is the reward-to-go
+ *   G_t = sum_{i >= pos(t)} r_i = c[pos(t)] - c[n],   pos(t) = number of symbols emitted at frames < t,
+ * where frame t emits iff (t == 0 or pi_t != pi_{t-1}) and pi_t != blank (orc_collapse), n = len(yhat).
+ *   baseline (per frame, over the K samples of the utterance): 0 none | 1 mean_k G_kt | 2 leave-one-out | 3 value
+ *   A_kt = G_kt - b_kt;  L_pg = -(1/(B K)) sum_{b,k,t<T_b} A_kt log p_t(pi_kt)
+ *   g[b,t,v] = (1/(B K)) ( p_tv sum_k A_kt - sum_k A_kt [pi_kt = v] )
+ * rewards[b,k] = G_0 = len(y*) - ED (fp32, exact);  to_go [B,K,T] int16 (0 for t >= T_b);  r_pos [B,K,T] int8
+ * (0 for i >= n).  Integers are part of the bit-exact contract, the rest is fp64.
+ * ------------------------------------------------------------------------------------ */
+ORC_API double orc_pg_togo_loss_grad(const float* logits, const int32_t* in_len, const uint8_t* samples,
+                                     const int32_t* targets, const int32_t* tgt_len,
+                                     int B, int T, int V, int K, int Lmax, int blank,
+                                     int baseline_mode, double baseline_value,
+                                     float* rewards, int16_t* to_go, int8_t* r_pos, double* grad) {
+    double loss = 0.0;
+    double inv = 1.0 / ((double)B * K);
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : loss)
+    for (int b = 0; b < B; ++b) {
+        int Tb = in_len ? in_len[b] : T;
+        int m = tgt_len ? tgt_len[b] : Lmax;
+        int32_t* path = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T + 1));
+        int32_t* hyp = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T + 1));
+        int32_t* col = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T + 1));
+        int32_t* G = (int32_t*)malloc(sizeof(int32_t) * (size_t)K * (size_t)(T + 1));
+        for (int k = 0; k < K; ++k) {
+            const uint8_t* s = samples + ((size_t)b * K + k) * T;
+            for (int t = 0; t < Tb; ++t) path[t] = s[t];
+            int n = orc_collapse(path, Tb, blank, hyp);
+            orc_edit_distance(targets + (size_t)b * Lmax, m, hyp, n, col);
+            int8_t* rp = r_pos ? r_pos + ((size_t)b * K + k) * T : NULL;
+            if (rp) for (int i = 0; i < T; ++i) rp[i] = i < n ? (int8_t)(-(col[i + 1] - col[i])) : 0;
+            int pos = 0;
+            for (int t = 0; t < T; ++t) {
+                int g = t < Tb ? col[pos] - col[n] : 0;
+                G[(size_t)k * T + t] = g;
+                if (to_go) to_go[((size_t)b * K + k) * T + t] = (int16_t)g;
+                if (t < Tb) {
+                    int keep = (t == 0 || path[t] != path[t - 1]) && path[t] != blank;
+                    pos += keep;
+                }
+            }
+            rewards[(size_t)b * K + k] = (float)(col[0] - col[n]);
+        }
+        for (int t = 0; t < T; ++t) {
+            double* g = grad ? grad + ((size_t)b * T + t) * V : NULL;
+            if (g) for (int v = 0; v < V; ++v) g[v] = 0.0;
+            if (t >= Tb) continue;
+            const float* z = logits + ((size_t)b * T + t) * V;
+            double mx = z[0];
+            for (int v = 1; v < V; ++v) if (z[v] > mx) mx = z[v];
+            double den = 0.0;
+            for (int v = 0; v < V; ++v) den += exp((double)z[v] - mx);
+            double lz = mx + log(den);
+            double sumG = 0.0, sumA = 0.0;
+            for (int k = 0; k < K; ++k) sumG += (double)G[(size_t)k * T + t];
+            for (int k = 0; k < K; ++k) {
+                double Gk = (double)G[(size_t)k * T + t], base = 0.0;
+                if (baseline_mode == 1) base = sumG / K;
+                else if (baseline_mode == 2) base = K > 1 ? (sumG - Gk) / (K - 1) : 0.0;
+                else if (baseline_mode == 3) base = baseline_value;
+                double A = Gk - base;
+                int pi = samples[((size_t)b * K + k) * T + t];
+                loss += -A * ((double)z[pi] - lz);
+                sumA += A;
+                if (g) g[pi] -= inv * A;
+            }
+            if (g) for (int v = 0; v < V; ++v) g[v] += inv * sumA * exp((double)z[v] - lz);
+        }
+        free(path); free(hyp); free(col); free(G);
+    }
+    return loss * inv;
+}
+
+/* ------------------------------------------------------------------------------------
  * a8  CTC alpha-beta in fp64 log space (DESIGN.md "CTC spec"; Graves et al. 2006).
  *   extended labels l' = (blank, l1, blank, ..., lL, blank), S = 2L+1, blank id given
  *   alpha_t(s) = lse(alpha_{t-1}(s), alpha_{t-1}(s-1), [alpha_{t-1}(s-2) if l'_s != blank and
@@ -493,8 +574,13 @@ ORC_API double orc_pg_ctc_step(const float* logits, const int32_t* targets,
     double* gctc = (double*)malloc(nBTV * sizeof(double));
     orc_softmax_sample(logits, in_len, uniforms, seed, B, T, V, K, samples, logp);
     orc_collapse_score(samples, in_len, targets, tgt_len, B, T, K, Lmax, blank, hyps, hyp_len, dist);
-    double lpg = orc_pg_loss_grad(logits, in_len, samples, logp, dist, tgt_len, B, T, V, K, Lmax,
-                                  reward_mode, baseline_mode, baseline_value, rewards, adv, gpg);
+    double lpg;
+    if (reward_mode == 2)
+        lpg = orc_pg_togo_loss_grad(logits, in_len, samples, targets, tgt_len, B, T, V, K, Lmax, blank,
+                                    baseline_mode, baseline_value, rewards, NULL, NULL, gpg);
+    else
+        lpg = orc_pg_loss_grad(logits, in_len, samples, logp, dist, tgt_len, B, T, V, K, Lmax,
+                               reward_mode, baseline_mode, baseline_value, rewards, adv, gpg);
     orc_ctc_loss_grad(logits, targets, in_len, tgt_len, B, T, V, Lmax, blank, nll, gctc);
     double lctc = 0.0;
     for (int b = 0; b < B; ++b) lctc += nll[b];

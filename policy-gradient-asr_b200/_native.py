@@ -31,6 +31,7 @@ SIGNATURES = {
     "pgasr_pg_ctc_step_workspace_init": (_i, [_vp, _sz, _vp]),
     "pgasr_pg_ctc_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pgasr_pg_ctc_step_multi": (_i, [_vp, _i, _u64, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
     "pgasr_ctc_beam_search_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "pgasr_ctc_beam_search": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pgasr_host_create": (_i, [_i, _i, _i, _i, _i, _i, _vp]),
@@ -40,6 +41,13 @@ SIGNATURES = {
     "pgasr_host_pin": (_i, [_vp, _sz]),
     "pgasr_host_unpin": (_i, [_vp]),
 }
+
+
+class StepIO(C.Structure):
+    """struct pgasr_step_io (include/pgasr.h): the device pointers of one step of pgasr_pg_ctc_step_multi."""
+    _fields_ = [("logits", _vp), ("targets", _vp), ("in_len", _vp), ("tgt_len", _vp), ("uniforms", _vp),
+                ("seed", _u64), ("loss", _vp), ("dlogits", _vp), ("rewards", _vp), ("logp", _vp),
+                ("hyp_len", _vp), ("dist", _vp), ("nll", _vp), ("samples", _vp), ("to_go", _vp), ("r_pos", _vp)]
 
 
 class PgasrError(RuntimeError):

@@ -146,7 +146,7 @@ extern "C" int pgasr_ctc_loss_grad(const float* logits, const float* probs, cons
         a.do_pg = 0; a.do_ctc = 1;
         a.loss = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + fused_bytes - 256);
         a.dlogits = dlogits; a.rewards = nullptr; a.logp = nullptr; a.hyp_len = nullptr; a.dist = nullptr;
-        a.nll = nll; a.samples = nullptr;
+        a.nll = nll; a.samples = nullptr; a.to_go = nullptr; a.r_pos = nullptr;
         PGASR_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)2 * (4 + B) * sizeof(unsigned), st));   // arm both control blocks
         return fused_step(a, workspace, st);
     }

@@ -72,7 +72,11 @@ __device__ __forceinline__ void ctc_lane_init(CtcLane<SPL>& st, const int32_t* _
 #pragma unroll
     for (int i = 0; i < SPL / 2; ++i) {
         const int li = (lane * SPL) / 2 + i;              // label index of odd state lane*SPL + 2i + 1
-        const int c = li < L ? lab_u[li] : -1;
+        int c = li < L ? lab_u[li] : -1;
+        // a label id outside [0,V) reads the zero slot like a state beyond the transcript: its emission probability is
+        // 0 in every frame, so the utterance has no valid alignment (nll = +inf, zero gradient) instead of a read of
+        // the neighbouring row
+        if (c >= V) c = -2;
         st.loff[i] = c >= 0 ? c : V;
         bool legal;
         if (kAlpha) legal = c >= 0 && li >= 1 && lab_u[li - 1] != c;

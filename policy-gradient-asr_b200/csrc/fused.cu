@@ -16,11 +16,17 @@ int launch_fused_spl32(int mode, FusedArgs& a, size_t smem, cudaStream_t st);
 
 constexpr size_t kFusedSmemLimit = 220 * 1024;
 
+// The only host-side state of the library: which of a workspace's two control blocks its next step uses.  The entry
+// is dropped by pgasr_pg_ctc_step_workspace_init (which zeroes both blocks), so a recycled pointer starts afresh.
+static std::mutex g_parity_mu;
+static std::unordered_map<const void*, unsigned> g_parity;
 static unsigned workspace_parity(const void* ws) {
-    static std::mutex mu;
-    static std::unordered_map<const void*, unsigned> seq;
-    std::lock_guard<std::mutex> lk(mu);
-    return seq[ws]++ & 1u;
+    std::lock_guard<std::mutex> lk(g_parity_mu);
+    return g_parity[ws]++ & 1u;
+}
+void fused_workspace_reset(const void* ws) {
+    std::lock_guard<std::mutex> lk(g_parity_mu);
+    g_parity.erase(ws);
 }
 
 struct FusedWs { size_t ctrl, lat, exps, terms, nll, tile, total; };

@@ -12,6 +12,7 @@ struct FusedArgs {
     int do_pg, do_ctc;
     float* loss; float* dlogits;
     float* rewards; float* logp; int32_t* hyp_len; int32_t* dist; float* nll; uint8_t* samples;   // optional
+    int16_t* to_go; int8_t* r_pos;                                                                // optional (reward-to-go)
     unsigned* ctrl;          // [0] role ticket, [1] done ticket, [4 + b] CTC-done flag of utterance b
     double* lattice; int* lat_exp; float* loss_terms; float* nll_ws;
     float* tile_g;           // global-tile mode: [B][T + 2][RS] fp32 softmax rows (guard row before and after)
@@ -25,5 +26,6 @@ size_t fused_workspace_bytes(int B, int T, int V, int K, int Lmax);
 // (armed once: the kernel re-arms it when it finishes)
 int fused_step(FusedArgs& a, void* workspace, cudaStream_t st);
 size_t align256(size_t x);
+void fused_workspace_reset(const void* workspace);      // forget the control-block parity kept for this pointer
 
 }  // namespace pgasr

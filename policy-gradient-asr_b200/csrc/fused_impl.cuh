@@ -611,11 +611,14 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
 
 template <int SPL, int kThreads, bool kGT, bool kStream>
 static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
-    static thread_local size_t smem_set = 0;               // the opt-in is sticky: raise it only when a larger tile comes
-    if (smem > smem_set) {
+    // the opt-in is sticky PER DEVICE: raise it only when a larger tile comes on the device the launch goes to
+    static thread_local size_t smem_set[64] = {0};
+    int dev = 0;
+    PGASR_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
         PGASR_CUDA_TRY(cudaFuncSetAttribute(pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        if (dev >= 0 && dev < 64) smem_set[dev] = smem;
     }
     const int grid = (a.do_ctc ? a.B : 0) + (a.do_pg ? a.B : 0);
     static const bool no_pdl = getenv("PGASR_NO_PDL") != nullptr;     // (A/B measurements)

@@ -78,8 +78,10 @@ __global__ void nll_sum_forward_kernel(const float* __restrict__ inp, const int6
         float s = 0.0f, cnt = 0.0f;
         for (int b = lane; b < B; b += 32) {
             const long long c = target[(size_t)b * L + i];
-            if (ignore_index >= 0 && c == ignore_index) continue;
-            s += -inp[((size_t)i * B + b) * V + c];
+            if (c == (long long)ignore_index) continue;
+            // a class id outside [0,V) that is not the ignore value: torch raises there; here the loss turns NaN
+            // (loud, and no out-of-bounds read)
+            s += (c >= 0 && c < V) ? -inp[((size_t)i * B + b) * V + c] : __int_as_float(0x7fc00000);
             cnt += 1.0f;
         }
         s = warp_sum(s);
@@ -105,7 +107,7 @@ __global__ void nll_sum_backward_kernel(const int64_t* __restrict__ target, cons
         float cnt = 0.0f;
         for (int b = lane; b < B; b += 32) {
             const long long c = target[(size_t)b * L + i];
-            if (!(ignore_index >= 0 && c == ignore_index)) cnt += 1.0f;
+            if (c != (long long)ignore_index) cnt += 1.0f;
         }
         cnt = warp_sum(cnt);
         if (lane == 0) s_cnt = cnt;
@@ -115,7 +117,7 @@ __global__ void nll_sum_backward_kernel(const int64_t* __restrict__ target, cons
     for (int e = threadIdx.x; e < B * V; e += blockDim.x) {
         const int b = e / V, v = e - b * V;
         const long long c = target[(size_t)b * L + i];
-        const bool live = !(ignore_index >= 0 && c == ignore_index);
+        const bool live = c != (long long)ignore_index;
         grad_inp[((size_t)i * B + b) * V + v] = (live && v == c) ? w : 0.0f;
     }
 }

@@ -18,6 +18,14 @@ struct StepWorkspace {
     void* ctc; size_t ctc_bytes; size_t total;
 };
 
+// The one predicate carve(), pgasr_pg_ctc_step_workspace_bytes and the step share: the single-launch kernel takes
+// the shape AND the batch fits its control block (4 + B words per block, two blocks inside the 128 KB that
+// pgasr_pg_ctc_step_workspace_init clears).  Larger batches chain the stand-alone kernels.
+constexpr int kFusedMaxB = 16380;
+static int step_fused_capability(int B, int T, int V, int K, int Lmax) {
+    return B <= kFusedMaxB ? fused_capability(T, V, K, Lmax) : 0;
+}
+
 static StepWorkspace carve(void* base, int B, int T, int V, int K, int Lmax) {
     StepWorkspace w;
     char* p = reinterpret_cast<char*>(base);
@@ -35,7 +43,7 @@ static StepWorkspace carve(void* base, int B, int T, int V, int K, int Lmax) {
     w.nll = reinterpret_cast<float*>(take((size_t)B * 4));
     w.probs = reinterpret_cast<float*>(take((size_t)B * T * V * 4));
     // the classic CTC kernel is only chained when the single-launch kernel cannot take the shape
-    w.ctc_bytes = (fused_capability(T, V, K, Lmax) & 1) ? 256 : pgasr_ctc_workspace_bytes(B, T, V, Lmax);
+    w.ctc_bytes = (step_fused_capability(B, T, V, K, Lmax) & 1) ? 256 : pgasr_ctc_workspace_bytes(B, T, V, Lmax);
     w.ctc = take(w.ctc_bytes);
     w.total = off;
     return w;
@@ -93,7 +101,8 @@ extern "C" int pgasr_device_check(void) {
 // layout: [fused-kernel workspace (control block first)][scratch of the stand-alone kernels]
 extern "C" size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax) {
     if (B < 0 || T <= 0 || V <= 0 || K <= 0 || Lmax <= 0) return 0;
-    const size_t fused = pgasr::align256(pgasr::fused_workspace_bytes(B, T, V, K, Lmax));
+    const size_t fused = pgasr::step_fused_capability(B, T, V, K, Lmax)
+                             ? pgasr::align256(pgasr::fused_workspace_bytes(B, T, V, K, Lmax)) : 0;
     const pgasr::StepWorkspace w = pgasr::carve(nullptr, B, T, V, K, Lmax);
     if (w.ctc_bytes == 0) return 0;
     return fused + w.total;
@@ -101,62 +110,78 @@ extern "C" size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, 
 
 extern "C" int pgasr_pg_ctc_step_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
     if (!workspace) return PGASR_ERR_INVALID_ARG;
-    // only the two control blocks at the front have to start at zero; the kernel re-arms its block after every step
-    const size_t n = workspace_bytes < 131072 ? workspace_bytes : 131072;
+    // only the two control blocks at the front have to start at zero (2 * (4 + kFusedMaxB) words = 128 KB at most);
+    // the kernel re-arms its block after every step.  The host-side record of which block the next step uses is
+    // dropped with it, so a recycled pointer starts from block 0 again.
+    const size_t ctrl = (size_t)2 * (4 + pgasr::kFusedMaxB) * sizeof(unsigned);
+    const size_t n = workspace_bytes < ctrl ? workspace_bytes : ctrl;
     PGASR_CUDA_TRY(cudaMemsetAsync(workspace, 0, n, pgasr::as_stream(stream)));
+    pgasr::fused_workspace_reset(workspace);
     return PGASR_OK;
 }
 
-extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, const int32_t* in_len,
-                                 const int32_t* tgt_len, const float* uniforms, uint64_t seed, int B, int T,
-                                 int V, int K, int Lmax, int blank, int reward_mode, int baseline_mode,
-                                 float baseline_value, float w_pg, float w_ctc, float* loss, float* dlogits,
-                                 float* rewards, float* logp, int32_t* hyp_len, int32_t* dist, float* nll,
-                                 uint8_t* samples, void* workspace, size_t workspace_bytes, void* stream) {
-    using namespace pgasr;
-    if (!logits || !targets || !loss || !dlogits || !workspace || B <= 0 || T <= 0 || V <= 0 || K <= 0 ||
-        Lmax <= 0 || blank < 0 || blank >= V)
+namespace pgasr {
+
+struct StepParams {
+    int B, T, V, K, Lmax, blank, reward_mode, baseline_mode;
+    float baseline_value, w_pg, w_ctc;
+};
+
+static int step_check(const StepParams& q, const void* workspace, size_t workspace_bytes) {
+    if (!workspace || q.B <= 0 || q.T <= 0 || q.V <= 0 || q.K <= 0 || q.Lmax <= 0 || q.blank < 0 || q.blank >= q.V)
         return PGASR_ERR_INVALID_ARG;
-    if (K > 64 || V > 32) return PGASR_ERR_UNSUPPORTED;
-    if (workspace_bytes < pgasr_pg_ctc_step_workspace_bytes(B, T, V, K, Lmax)) return PGASR_ERR_WORKSPACE;
-    cudaStream_t st = as_stream(stream);
-    const bool do_pg = w_pg != 0.0f, do_ctc = w_ctc != 0.0f;
-    const int cap = B + 4 <= 16384 ? fused_capability(T, V, K, Lmax) : 0;
+    if (q.reward_mode < 0 || q.reward_mode > PGASR_REWARD_MAX || q.baseline_mode < 0 || q.baseline_mode > 3)
+        return PGASR_ERR_INVALID_ARG;
+    if (q.K > 64 || q.V > kMaxV) return PGASR_ERR_UNSUPPORTED;
+    const size_t need = pgasr_pg_ctc_step_workspace_bytes(q.B, q.T, q.V, q.K, q.Lmax);
+    if (need == 0) return PGASR_ERR_UNSUPPORTED;
+    if (workspace_bytes < need) return PGASR_ERR_WORKSPACE;
+    return PGASR_OK;
+}
+
+// one step: one launch of the single-launch kernel when the shape fits, else the chain of stand-alone kernels
+static int step_one(const StepParams& q, const pgasr_step_io& io, uint64_t seed, void* workspace, cudaStream_t st) {
+    if (!io.logits || !io.targets || !io.loss || !io.dlogits) return PGASR_ERR_INVALID_ARG;
+    void* stream = reinterpret_cast<void*>(st);
+    const int B = q.B, T = q.T, V = q.V, K = q.K, Lmax = q.Lmax;
+    const bool do_pg = q.w_pg != 0.0f, do_ctc = q.w_ctc != 0.0f;
+    const int cap = step_fused_capability(B, T, V, K, Lmax);
     FusedArgs a;
-    a.logits = logits; a.targets = targets; a.in_len = in_len; a.tgt_len = tgt_len; a.uniforms = uniforms;
-    a.seed = seed; a.B = B; a.T = T; a.V = V; a.K = K; a.Lmax = Lmax; a.blank = blank;
-    a.reward_mode = reward_mode; a.baseline_mode = baseline_mode; a.baseline_value = baseline_value;
-    a.w_pg = w_pg; a.w_ctc = w_ctc; a.do_pg = do_pg; a.do_ctc = do_ctc;
-    a.loss = loss; a.dlogits = dlogits; a.rewards = rewards; a.logp = logp; a.hyp_len = hyp_len; a.dist = dist;
-    a.nll = nll; a.samples = samples;
+    a.logits = io.logits; a.targets = io.targets; a.in_len = io.in_len; a.tgt_len = io.tgt_len; a.uniforms = io.uniforms;
+    a.seed = seed; a.B = B; a.T = T; a.V = V; a.K = K; a.Lmax = Lmax; a.blank = q.blank;
+    a.reward_mode = q.reward_mode; a.baseline_mode = q.baseline_mode; a.baseline_value = q.baseline_value;
+    a.w_pg = q.w_pg; a.w_ctc = q.w_ctc; a.do_pg = do_pg; a.do_ctc = do_ctc;
+    a.loss = io.loss; a.dlogits = io.dlogits; a.rewards = io.rewards; a.logp = io.logp; a.hyp_len = io.hyp_len;
+    a.dist = io.dist; a.nll = io.nll; a.samples = io.samples; a.to_go = io.to_go; a.r_pos = io.r_pos;
     if ((do_pg || do_ctc) && (cap & 1) && (!do_pg || (cap & 2))) {
         // one launch: heterogeneous CTAs (CTC role / PG role per utterance), see fused.cu
         return fused_step(a, workspace, st);
     }
+    if (do_pg && q.reward_mode == PGASR_REWARD_ED_TO_GO) return PGASR_ERR_UNSUPPORTED;   // (single-launch kernel only)
     // long utterances: the PG role's tiles do not fit one SM -- the PG part runs as the chain of stand-alone
     // kernels, the CTC part still as the single-launch kernel (tile streamed from the workspace) when it fits
-    const size_t fused_bytes = align256(fused_workspace_bytes(B, T, V, K, Lmax));
+    const size_t fused_bytes = cap ? align256(fused_workspace_bytes(B, T, V, K, Lmax)) : 0;
     StepWorkspace w = carve(reinterpret_cast<char*>(workspace) + fused_bytes, B, T, V, K, Lmax);
     if (w.ctc_bytes == 0) return PGASR_ERR_UNSUPPORTED;
-    uint8_t* smp = samples ? samples : w.samples;
-    float* lp = logp ? logp : w.logp;
-    int32_t* hl = hyp_len ? hyp_len : w.hyp_len;
-    int32_t* ds = dist ? dist : w.dist;
-    float* rw = rewards ? rewards : w.rewards;
-    float* nl = nll ? nll : w.nll;
-    const bool dense = baseline_mode != PGASR_BASELINE_MEAN;   // sum_k A_k == 0 under the per-utterance mean
+    uint8_t* smp = io.samples ? io.samples : w.samples;
+    float* lp = io.logp ? io.logp : w.logp;
+    int32_t* hl = io.hyp_len ? io.hyp_len : w.hyp_len;
+    int32_t* ds = io.dist ? io.dist : w.dist;
+    float* rw = io.rewards ? io.rewards : w.rewards;
+    float* nl = io.nll ? io.nll : w.nll;
+    const bool dense = q.baseline_mode != PGASR_BASELINE_MEAN;   // sum_k A_k == 0 under the per-utterance mean
     int rc;
     if (do_pg || do_ctc) {
         // the sampler also produces the softmax the CTC lattice and the dense PG term read
-        rc = pgasr_softmax_sample(logits, in_len, uniforms, seed, B, T, V, K, smp, lp, w.probs, stream);
+        rc = pgasr_softmax_sample(io.logits, io.in_len, io.uniforms, seed, B, T, V, K, smp, lp, w.probs, stream);
         if (rc) return rc;
     }
     if (do_pg) {
-        rc = pgasr_collapse_u8(smp, in_len, K, B * K, T, blank, w.hyps, hl, stream);
+        rc = pgasr_collapse_u8(smp, io.in_len, K, B * K, T, q.blank, w.hyps, hl, stream);
         if (rc) return rc;
-        rc = pgasr_edit_distance_u8(w.hyps, hl, B * K, T, targets, tgt_len, K, Lmax, V, ds, nullptr, stream);
+        rc = pgasr_edit_distance_u8(w.hyps, hl, B * K, T, io.targets, io.tgt_len, K, Lmax, V, ds, nullptr, stream);
         if (rc) return rc;
-        rc = pgasr_pg_advantages(ds, tgt_len, lp, B, K, Lmax, reward_mode, baseline_mode, baseline_value, rw,
+        rc = pgasr_pg_advantages(ds, io.tgt_len, lp, B, K, Lmax, q.reward_mode, q.baseline_mode, q.baseline_value, rw,
                                  w.adv, w.loss_terms, stream);
         if (rc) return rc;
     }
@@ -166,18 +191,57 @@ extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, co
         rc = fused_step(a, workspace, st);                 // dlogits = (w_ctc / B) g_ctc, nll; loss is finalised below
         if (rc) return rc;
     } else if (do_ctc) {
-        rc = pgasr_ctc_loss_grad(logits, w.probs, targets, in_len, tgt_len, B, T, V, Lmax, blank,
-                                 w_ctc / (float)B, 0, nl, dlogits, w.ctc, w.ctc_bytes, stream);
+        rc = pgasr_ctc_loss_grad(io.logits, w.probs, io.targets, io.in_len, io.tgt_len, B, T, V, Lmax, q.blank,
+                                 q.w_ctc / (float)B, 0, nl, io.dlogits, w.ctc, w.ctc_bytes, stream);
         if (rc) return rc;
     }
     if (do_pg) {
-        rc = pgasr_pg_grad(smp, w.adv, dense ? w.probs : nullptr, in_len, B, T, V, K,
-                           w_pg / ((float)B * (float)K), do_ctc ? 1 : 0, dlogits, stream);
+        rc = pgasr_pg_grad(smp, w.adv, dense ? w.probs : nullptr, io.in_len, B, T, V, K,
+                           q.w_pg / ((float)B * (float)K), do_ctc ? 1 : 0, io.dlogits, stream);
         if (rc) return rc;
     }
-    if (!do_pg && !do_ctc) PGASR_CUDA_TRY(cudaMemsetAsync(dlogits, 0, (size_t)B * T * V * sizeof(float), st));
-    finalize_loss_kernel<<<1, 32, 0, st>>>(do_pg ? w.loss_terms : nullptr, do_ctc ? nl : nullptr, B, K, w_pg,
-                                           w_ctc, loss);
+    if (!do_pg && !do_ctc) PGASR_CUDA_TRY(cudaMemsetAsync(io.dlogits, 0, (size_t)B * T * V * sizeof(float), st));
+    finalize_loss_kernel<<<1, 32, 0, st>>>(do_pg ? w.loss_terms : nullptr, do_ctc ? nl : nullptr, B, K, q.w_pg,
+                                           q.w_ctc, io.loss);
     PGASR_LAUNCH_CHECK();
+    return PGASR_OK;
+}
+
+}  // namespace pgasr
+
+extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, const int32_t* in_len,
+                                 const int32_t* tgt_len, const float* uniforms, uint64_t seed, int B, int T,
+                                 int V, int K, int Lmax, int blank, int reward_mode, int baseline_mode,
+                                 float baseline_value, float w_pg, float w_ctc, float* loss, float* dlogits,
+                                 float* rewards, float* logp, int32_t* hyp_len, int32_t* dist, float* nll,
+                                 uint8_t* samples, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace pgasr;
+    const StepParams q = {B, T, V, K, Lmax, blank, reward_mode, baseline_mode, baseline_value, w_pg, w_ctc};
+    if (!logits || !targets || !loss || !dlogits) return PGASR_ERR_INVALID_ARG;
+    const int rc = step_check(q, workspace, workspace_bytes);
+    if (rc) return rc;
+    pgasr_step_io io;
+    io.logits = logits; io.targets = targets; io.in_len = in_len; io.tgt_len = tgt_len; io.uniforms = uniforms;
+    io.seed = 0; io.loss = loss; io.dlogits = dlogits; io.rewards = rewards; io.logp = logp; io.hyp_len = hyp_len;
+    io.dist = dist; io.nll = nll; io.samples = samples; io.to_go = nullptr; io.r_pos = nullptr;
+    return step_one(q, io, seed, workspace, as_stream(stream));
+}
+
+// n steps with one call: the per-step cost on the host is one cudaLaunchKernelEx, nothing else (no Python, no
+// allocation, no argument marshalling), and programmatic dependent launch overlaps each launch with the tail of the
+// step before it.
+extern "C" int pgasr_pg_ctc_step_multi(const pgasr_step_io* steps, int n_steps, uint64_t seed_base, int B, int T,
+                                       int V, int K, int Lmax, int blank, int reward_mode, int baseline_mode,
+                                       float baseline_value, float w_pg, float w_ctc, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+    using namespace pgasr;
+    const StepParams q = {B, T, V, K, Lmax, blank, reward_mode, baseline_mode, baseline_value, w_pg, w_ctc};
+    if (!steps || n_steps < 0) return PGASR_ERR_INVALID_ARG;
+    int rc = step_check(q, workspace, workspace_bytes);
+    if (rc) return rc;
+    for (int i = 0; i < n_steps; ++i) {
+        rc = step_one(q, steps[i], seed_base + steps[i].seed, workspace, as_stream(stream));
+        if (rc) return rc;
+    }
     return PGASR_OK;
 }

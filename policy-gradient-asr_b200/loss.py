@@ -37,7 +37,7 @@ class customNLLLoss(nn.Module):
         self.ignore_index = ignore_index
 
     def forward(self, inp, target):
-        ign = self.ignore_index if self.ignore_index else -1     # upstream loss.py:9: falsy -> not ignored
+        ign = self.ignore_index if self.ignore_index else F.NO_IGNORE     # upstream loss.py:9: falsy -> not ignored
         return _NLLSumFn.apply(inp, target, int(ign))
 
 
@@ -65,7 +65,11 @@ class PolicyGradCTCLoss(nn.Module):
 
     forward(logits[B,T,V] fp32 CUDA, targets[B,L] (pad 0), input_lengths[B]=None, target_lengths[B]=None,
             uniforms[B,K,T]=None) -> 0-d tensor attached to `logits`.
-    reward: 'ed' (-edit distance) or 'cer' (-edit distance / len(transcript), as metrics.evaluate's CER)
+    reward: 'ed' (-edit distance), 'cer' (-edit distance / len(transcript), as metrics.evaluate's CER) or
+            'ed_to_go' (upstream policy_grad.reward's per-position rewards, credited per frame as reward-to-go;
+            the baseline is then taken per frame over the K samples)
+    target_lengths=None: the lengths are taken from the padding -- the number of leading non-zero ids of each row
+            (upstream pads transcripts with 0 = '<pad>', data.py:99, which is also the CTC blank and never a label)
     baseline: 'mean' (over the K samples of the utterance), 'loo', 'none', or 'value' (baseline_value)
     After a call, .last holds rewards [B,K], nll [B], logp [B,K], dist [B,K], hyp_len [B,K].
     """
@@ -95,4 +99,10 @@ class PolicyGradCTCLoss(nn.Module):
             tl = target_lengths if isinstance(target_lengths, torch.Tensor) else torch.as_tensor(target_lengths)
             if not tl.is_cuda and bool((tl == 0).any()):
                 raise ZeroDivisionError("division by zero")
+        if target_lengths is None:
+            # the two-argument slot criterion(model_out, t): zero padding is not a label (it is the blank), so the
+            # true length is the number of leading non-pad ids -- computed on the device, no synchronisation
+            tg = targets if isinstance(targets, torch.Tensor) else torch.as_tensor(targets)
+            tg = tg.to(logits.device)
+            target_lengths = (tg != 0).to(torch.int32).cumprod(dim=1).sum(dim=1, dtype=torch.int32)
         return _PGCTCFn.apply(logits, self, targets, input_lengths, target_lengths, uniforms)

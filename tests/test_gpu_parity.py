@@ -29,6 +29,18 @@ def rel_err(got, want):
     return np.abs(got - want).max() / scale
 
 
+def grad_close(got, want, rtol=RTOL):
+    """Element-wise bar next to the max-norm one: |got - want| <= 1e-4 |want| + atol for EVERY entry, with
+    atol = max(1e-7, 1e-6 max|want|): 1e-7 absolute at the bench shape (rows are scaled by 1/B = 1/64), and never
+    below a few fp32 ulps of the largest entry (dlogits is fp32: an entry that is a difference of two O(scale)
+    terms cannot be closer to the fp64 oracle than that)."""
+    want = np.asarray(want, np.float64)
+    got = np.asarray(got, np.float64)
+    atol = max(1e-7, 1e-6 * float(np.abs(want).max()))
+    bad = np.abs(got - want) > rtol * np.abs(want) + atol
+    return not bad.any()
+
+
 def enc(s):
     return [ord(c) for c in s]
 
@@ -313,6 +325,7 @@ def step_case(cuda, B, T, V, K, L, seed, ragged, regime, reward="ed", baseline="
         assert np.abs(out["nll"].cpu().numpy() / nll_ref - 1).max() < RTOL
     assert abs(float(out["loss"]) - loss_ref) <= RTOL * abs(loss_ref) + 1e-5
     assert rel_err(out["dlogits"].cpu().numpy(), dl_ref) < RTOL
+    assert grad_close(out["dlogits"].cpu().numpy(), dl_ref)
     return out
 
 
@@ -677,10 +690,10 @@ def test_step_randomised_shapes_and_modes(cuda):
     the boundaries between the kernel's modes, every case against the C oracle with the usual bars."""
     import subprocess, sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_step.py"), "60", "5"], capture_output=True, text=True,
-                       timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_step.py"), "200", "5"], capture_output=True, text=True,
+                       timeout=1800)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    assert "all 60 cases passed" in r.stdout
+    assert "all 200 cases passed" in r.stdout
 
 
 @pytest.mark.gpu
@@ -738,3 +751,129 @@ def test_step_back_to_back_distinct_batches(cuda):
     for s, out in outs:
         for k in ("loss", "dlogits", "rewards", "nll"):
             assert torch.equal(out[k], refs[s][k]), (s, k)
+
+
+# ---------------------------------------------------------------- round 2
+@pytest.mark.gpu
+def test_step_stress_corner_all_three(cuda):
+    """K = 64 AND T = 2000 AND L = 400 together (BASELINE.json configs[4]'s far corner), B = 8."""
+    step_case(cuda, 8, 2000, 30, 64, 400, seed=64, ragged=True, regime="random", reward="cer", baseline="loo")
+
+
+@pytest.mark.gpu
+def test_step_queue_equals_single_steps(cuda):
+    """pgasr_pg_ctc_step_multi (functional.StepQueue): n steps enqueued by one C-ABI call give bit for bit what the
+    same steps give one call at a time, in any window of the cycle, and allocate nothing."""
+    from pgasr_b200 import functional as F
+    B, T, V, K, L = 16, 200, 30, 8, 40
+    batches = []
+    for s in range(5):
+        lg, tg, il, tl, _ = make_batch(B, T, V, K, L, seed=300 + s, ragged=(s % 2 == 0))
+        batches.append({"logits": dev_t(lg, cuda), "targets": dev_t(tg, cuda), "in_len": dev_t(il, cuda),
+                        "tgt_len": dev_t(tl, cuda)})
+    q = F.StepQueue(batches, K=K, reward="cer", baseline="loo", want=("rewards", "nll", "dist"))
+    for first, n, seed in [(0, 5, 7), (3, 4, 1000), (4, 1, 5), (2, 0, 0)]:
+        refs = []
+        for j in range(n):
+            b = batches[(first + j) % 5]
+            o = F.pg_ctc_step(b["logits"], b["targets"], b["in_len"], b["tgt_len"], K=K, reward="cer", baseline="loo",
+                              seed=seed + j, want=("rewards", "nll", "dist"))
+            refs.append({k: o[k].clone() for k in ("loss", "dlogits", "rewards", "nll", "dist")})
+        torch.cuda.synchronize()
+        mem0 = torch.cuda.memory_allocated()
+        assert q.run(first=first, n=n, seed=seed) == n
+        assert torch.cuda.memory_allocated() == mem0
+        torch.cuda.synchronize()
+        for j in range(n):
+            o = q.outputs[(first + j) % 5]
+            for k in ("dlogits", "rewards", "nll", "dist"):
+                assert torch.equal(o[k], refs[j][k]), (first, j, k)
+            assert torch.equal(o["loss"][0], refs[j]["loss"])
+    with pytest.raises(ValueError):
+        q.run(n=6)
+
+
+@pytest.mark.gpu
+def test_step_argument_validation(cuda):
+    from pgasr_b200 import functional as F
+    B, T, V, K, L = 2, 30, 6, 3, 4
+    lg, tg, il, tl, uni = make_batch(B, T, V, K, L, seed=3)
+    lg, tg, il, tl = dev_t(lg, cuda), dev_t(tg, cuda), dev_t(il, cuda), dev_t(tl, cuda)
+    with pytest.raises(ValueError):                      # uniforms of another batch size / length: no out-of-bounds read
+        F.pg_ctc_step(lg, tg, il, tl, uniforms=dev_t(uni[:1], cuda))
+    with pytest.raises(ValueError):
+        F.pg_ctc_step(lg, tg, il, tl, uniforms=dev_t(uni[:, :, :T - 1].copy(), cuda))
+    with pytest.raises(ValueError):                      # an unknown output name is not an uninitialised tensor
+        F.pg_ctc_step(lg, tg, il, tl, K=K, want=("rewards", "advantages"))
+    with pytest.raises(ValueError):
+        F.pg_ctc_step(lg, tg, il, tl, K=65)
+    out = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=1, want=("nll",))
+    ws = out["workspace"]
+    again = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=1, workspace=ws, out=ws.outputs(("nll",)))
+    assert torch.equal(again["dlogits"], out["dlogits"])
+
+
+@pytest.mark.gpu
+def test_workspace_init_resets_the_parity(cuda):
+    """pgasr_pg_ctc_step_workspace_init drops the host-side record of which control block comes next: a workspace
+    re-initialised after an odd number of steps (or a freed pointer handed out again) behaves like a fresh one."""
+    from pgasr_b200 import functional as F, _native
+    B, T, V, K, L = 8, 100, 30, 4, 20
+    lg, tg, il, tl, _ = make_batch(B, T, V, K, L, seed=77)
+    lg, tg, il, tl = dev_t(lg, cuda), dev_t(tg, cuda), dev_t(il, cuda), dev_t(tl, cuda)
+    ref = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=2, want=("nll",))
+    ws = ref["workspace"]
+    for n_before in (1, 2, 3):
+        for _ in range(n_before):
+            F.pg_ctc_step(lg, tg, il, tl, K=K, seed=2, workspace=ws, want=("nll",))
+        torch.cuda.synchronize()
+        ws.buf.fill_(0xFF)                               # as if the block had been freed and reused by someone else
+        _native.call("pgasr_pg_ctc_step_workspace_init", ws.buf.data_ptr(), ws.nbytes, torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            out = F.pg_ctc_step(lg, tg, il, tl, K=K, seed=2, workspace=ws, want=("nll",))
+            assert torch.equal(out["dlogits"], ref["dlogits"]) and torch.equal(out["nll"], ref["nll"])
+
+
+@pytest.mark.gpu
+def test_module_takes_lengths_from_the_padding(cuda):
+    """criterion(model_out, t) with zero-padded transcripts and NO lengths (the upstream slot, model.py:235): the pad
+    is not a label.  Must equal the call with explicit lengths; the Lmax fallback would differ."""
+    import pgasr_b200
+    B, T, V, K, L = 4, 80, 30, 8, 12
+    logits, targets, in_len, tgt_len, uni = make_batch(B, T, V, K, L, seed=19, ragged=True)
+    assert (tgt_len < L).any()
+    lg = dev_t(logits, cuda)
+    crit = pgasr_b200.PolicyGradCTCLoss(K=K, reward="cer")
+    a = crit(lg.clone().requires_grad_(True), dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda),
+             uniforms=dev_t(uni, cuda))
+    ra = crit.last["rewards"].clone()
+    b = crit(lg.clone().requires_grad_(True), dev_t(targets, cuda).long(), dev_t(in_len, cuda), None, uniforms=dev_t(uni, cuda))
+    assert torch.equal(a.detach(), b.detach()) and torch.equal(ra, crit.last["rewards"])
+    loss_ref, R_ref, _, _ = cport.pg_ctc_step(logits, targets, in_len, tgt_len, uni, reward_mode=1)
+    assert np.array_equal(ra.cpu().numpy(), R_ref) and abs(float(a) - loss_ref) <= RTOL * abs(loss_ref)
+
+
+@pytest.mark.gpu
+def test_out_of_range_labels_and_targets_are_loud(cuda):
+    """A label id >= V (or negative) inside the transcript: no read of the neighbouring row -- the utterance has no
+    alignment (nll = +inf, zero gradient), the others are untouched.  customNLLLoss: torch's ignore_index = -100 is
+    honoured, a class id outside [0,V) turns the loss NaN instead of reading out of bounds."""
+    import pgasr_b200
+    from pgasr_b200 import functional as F
+    B, T, V, L = 3, 60, 9, 7
+    logits, targets, in_len, tgt_len, _ = make_batch(B, T, V, 1, L, seed=2)
+    nll_ref, g_ref = cport.ctc_loss_grad(logits, targets, in_len, tgt_len)
+    bad = targets.copy()
+    bad[1, 3] = V + 5
+    nll, g = F.ctc_loss_grad(dev_t(logits, cuda), dev_t(bad, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda))
+    nll, g = nll.cpu().numpy(), g.cpu().numpy()
+    assert np.isinf(nll[1]) and (g[1] == 0).all()
+    assert np.abs(nll[[0, 2]] / nll_ref[[0, 2]] - 1).max() < RTOL and rel_err(g[[0, 2]], g_ref[[0, 2]]) < RTOL
+    inp = torch.log_softmax(torch.randn(5, 4, 6, device=cuda), -1)
+    tgt = torch.randint(0, 6, (4, 5), device=cuda)
+    tgt[1, 2] = -100
+    want = sum(torch.nn.functional.nll_loss(inp[i], tgt[:, i], ignore_index=-100) for i in range(5))
+    got = pgasr_b200.loss.customNLLLoss(ignore_index=-100)(inp, tgt)
+    assert abs(float(got) - float(want)) < 1e-5
+    tgt[0, 0] = 6
+    assert math.isnan(float(pgasr_b200.loss.customNLLLoss()(inp, tgt)))

@@ -217,3 +217,100 @@ def test_step_composition():
     assert abs(loss - (0.5 * lpg + 2.0 * nll2.mean())) < 1e-9
     np.testing.assert_allclose(dl, 0.5 * gpg + 2.0 / B * gctc, atol=1e-6)
     np.testing.assert_array_equal(R, R2)
+
+
+# ---------------------------------------------------------------- 8f.1 reward-to-go (DESIGN.md "reward-to-go spec")
+def test_togo_r_pos_is_upstream_reward_golden(golden):
+    """r_pos of the oracle IS upstream's policy_grad.reward sequence: r_t (t >= 2) equals r_pos[t], upstream's t == 1
+    branch equals r_pos[0] + r_pos[1] (policy_grad.py:14-15 subtracts len(y*) = c[0])."""
+    for e in golden["reward_positions"]:
+        y, h = enc(e["true_y"]), enc(e["hyp"])
+        if not h:
+            continue
+        V = 128
+        # a path that collapses to exactly `h`: every symbol once, a blank between equal neighbours
+        path = []
+        for i, c in enumerate(h):
+            if i and h[i - 1] == c:
+                path.append(0)
+            path.append(c)
+        T = len(path) + 2
+        samples = np.zeros((1, 1, T), np.uint8)
+        samples[0, 0, :len(path)] = path
+        logits = np.zeros((1, T, V), np.float32)
+        tg = np.array([y], np.int32)
+        loss, R, to_go, r_pos, _ = cport.pg_togo_loss_grad(logits, samples, tg, np.array([len(path)], np.int32),
+                                                           np.array([len(y)], np.int32), baseline_mode=0)
+        rp = r_pos[0, 0, :len(h)].tolist()
+        up = e["r"]                                            # upstream r_1, r_2, ...
+        assert rp[0] + (rp[1] if len(h) > 1 else 0) == up[0]
+        assert rp[2:] == up[1:len(h) - 1]
+        assert int(R[0, 0]) == len(y) - cport.edit_distance(y, h) == sum(rp)
+        assert int(to_go[0, 0, 0]) == sum(rp) and (to_go[0, 0, len(path):] == 0).all()
+
+
+@pytest.mark.parametrize("baseline_mode", [0, 1, 2, 3])
+def test_togo_oracle_against_autograd(baseline_mode):
+    """Credit assignment and gradient of the oracle against an independent numpy restatement + fp64 torch autograd."""
+    B, T, V, K, L = 3, 40, 7, 5, 6
+    logits, targets, in_len, tgt_len, uni = make_batch(B, T, V, K, L, seed=11 + baseline_mode, ragged=True)
+    samples, _ = cport.softmax_sample(logits, in_len, uni)
+    loss, R, to_go, r_pos, grad = cport.pg_togo_loss_grad(logits, samples, targets, in_len, tgt_len,
+                                                          baseline_mode=baseline_mode, baseline_value=-0.75)
+    # independent restatement: collapse with emission frames, last column by the pure-Python edit distance
+    G = np.zeros((B, K, T))
+    for b in range(B):
+        ref = targets[b, :tgt_len[b]].tolist()
+        for k in range(K):
+            path = samples[b, k, :in_len[b]].tolist()
+            emit = [t for t, c in enumerate(path) if c != 0 and (t == 0 or path[t - 1] != c)]
+            hyp = [path[t] for t in emit]
+            col = [pyref.edit_dist(ref, hyp[:i])[0] for i in range(len(hyp) + 1)]
+            r = [-(col[i + 1] - col[i]) for i in range(len(hyp))]
+            assert r_pos[b, k, :len(hyp)].tolist() == r and not r_pos[b, k, len(hyp):].any()
+            for t in range(in_len[b]):
+                G[b, k, t] = sum(r[i] for i, e in enumerate(emit) if e >= t)
+            assert R[b, k] == len(ref) - col[-1]
+    assert np.array_equal(to_go, G.astype(np.int16))
+    z = torch.tensor(logits, dtype=torch.float64, requires_grad=True)
+    lp = torch.log_softmax(z, -1)
+    Gt = torch.tensor(G)
+    if baseline_mode == 1:
+        base = Gt.mean(1, keepdim=True)
+    elif baseline_mode == 2:
+        base = (Gt.sum(1, keepdim=True) - Gt) / (K - 1)
+    elif baseline_mode == 3:
+        base = torch.full_like(Gt, -0.75)
+    else:
+        base = torch.zeros_like(Gt)
+    A = Gt - base
+    tot = 0.0
+    for b in range(B):
+        for k in range(K):
+            idx = torch.tensor(samples[b, k, :in_len[b]].astype(np.int64))
+            tot = tot - (A[b, k, :in_len[b]] * lp[b, torch.arange(in_len[b]), idx]).sum()
+    tot = tot / (B * K)
+    tot.backward()
+    assert abs(float(tot) - loss) <= 1e-12 * max(1.0, abs(loss))
+    np.testing.assert_allclose(grad, z.grad.numpy(), atol=1e-13)
+    # the whole-step entry with reward_mode 2 chains the same function
+    l2, R2, nll, dl = cport.pg_ctc_step(logits, targets, in_len, tgt_len, uni, reward_mode=2, baseline_mode=baseline_mode,
+                                        baseline_value=-0.75, w_pg=1.0, w_ctc=0.0)
+    assert np.array_equal(R2, R) and np.allclose(dl, grad, atol=1e-7)
+
+
+def test_reference_cpu_leg_runs_on_upstream_code():
+    """oracle/refpath.py (the `kind: reference` CPU leg of bench.py) imports the REAL upstream collapse_fn / edit_dist
+    from oracle/_ref and agrees with the oracle on the CTC part (the sampled part differs by construction: torch RNG)."""
+    from oracle import make_ref, refpath
+    make_ref.make()
+    if not refpath.available():
+        pytest.skip("no /root/reference here and oracle/_ref was not shipped")
+    B, T, V, K, L = 2, 30, 6, 3, 4
+    logits, targets, in_len, tgt_len, _ = make_batch(B, T, V, K, L, seed=5, ragged=True)
+    loss, R, g = refpath.step(logits, targets, in_len, tgt_len, K, w_pg=0.0, w_ctc=1.0)
+    nll, gref = cport.ctc_loss_grad(logits, targets, in_len, tgt_len)
+    assert abs(loss - nll.mean()) < 1e-4 * abs(nll.mean())
+    assert np.abs(g - gref / B).max() < 1e-5
+    loss, R, g = refpath.step(logits, targets, in_len, tgt_len, K, w_pg=1.0, w_ctc=0.0)
+    assert R.shape == (B, K) and (R <= 0).all() and np.isfinite(g).all()
