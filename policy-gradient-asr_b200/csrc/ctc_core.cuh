@@ -369,9 +369,9 @@ inline int batch_of(int spl) { return spl >= 32 ? 4 : spl >= 16 ? 7 : 14; }
 template <int SPL>
 constexpr int kWalkUnroll = kBatchOf<SPL> % 7 == 0 ? 7 : kBatchOf<SPL>;   // frames per unrolled group of the walker
 
-template <int SPL>
+template <int SPL, int NB = kBatchOf<SPL>>
 struct GradRing {
-    double* slots;                // [2 * kBatch][SPL*16]: the LABEL states of a frame ([SPL/4][32 lanes] double2)
+    double* slots;                // [2 * NB][SPL*16]: the LABEL states of a frame ([SPL/4][32 lanes] double2)
     int* eslot;                   // [2 * kBatch] exponent of the published values
     double* norm;                 // [2]: 2^30 / Z0, then (int) E0 and (int) dead -- written by the walker, see ctc_walk_publish_norm
     int bar_full;                 // named barrier ids: bar_full + k, bar_empty + k for buffer k in {0, 1}
@@ -405,18 +405,18 @@ __device__ __forceinline__ void ctc_build_class_lists(const int32_t* __restrict_
     __syncwarp();
 }
 
-template <int SPL>
+template <int SPL, int NB = kBatchOf<SPL>>
 __host__ __device__ inline size_t grad_ring_bytes() {
     // slots + exponents + the normalisation block
-    return (size_t)2 * kBatchOf<SPL> * SPL * 16 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15) + 16;
+    return (size_t)2 * NB * SPL * 16 * 8 + (((size_t)2 * NB * 4 + 15) & ~(size_t)15) + 16;
 }
 
-template <int SPL>
-__device__ __forceinline__ GradRing<SPL> grad_ring_carve(unsigned char* p, int bar_base) {   // p 16-byte aligned
-    GradRing<SPL> r;
+template <int SPL, int NB = kBatchOf<SPL>>
+__device__ __forceinline__ GradRing<SPL, NB> grad_ring_carve(unsigned char* p, int bar_base) {   // p 16-byte aligned
+    GradRing<SPL, NB> r;
     r.slots = reinterpret_cast<double*>(p);
-    r.eslot = reinterpret_cast<int*>(p + (size_t)2 * kBatchOf<SPL> * SPL * 16 * 8);
-    r.norm = reinterpret_cast<double*>(p + (size_t)2 * kBatchOf<SPL> * SPL * 16 * 8 + (((size_t)2 * kBatchOf<SPL> * 4 + 15) & ~(size_t)15));
+    r.eslot = reinterpret_cast<int*>(p + (size_t)2 * NB * SPL * 16 * 8);
+    r.norm = reinterpret_cast<double*>(p + (size_t)2 * NB * SPL * 16 * 8 + (((size_t)2 * NB * 4 + 15) & ~(size_t)15));
     r.bar_full = bar_base;
     r.bar_empty = bar_base + 2;
     r.dbg = false;
@@ -703,13 +703,14 @@ __device__ __forceinline__ void ctc_walk_publish_norm(const CtcWalk<SPL, kAlpha>
 
 // kGT: `tile` is row 0 of the utterance's tile in GLOBAL memory ([T] rows of RS doubles between two guard rows),
 // `pring` the 32-row shared-memory ring of this walker (aligned to its size, row stride RSR doubles).
-template <int SPL, int G, bool kAlpha, bool kGT = false, typename Barrier>
+template <int SPL, int G, bool kAlpha, bool kGT = false, int NB = kBatchOf<SPL>, typename Barrier>
 __device__ __forceinline__ void ctc_walk_tile(const float* tile, const int32_t* __restrict__ lab_u, int Tb, int L,
                                               int V, int RS, int blank, float* __restrict__ nll_out,
                                               double* __restrict__ lat_u, int* __restrict__ exp_u,
-                                              GradRing<SPL> ring, Barrier mid_barrier, float* pring = nullptr,
+                                              GradRing<SPL, NB> ring, Barrier mid_barrier, float* pring = nullptr,
                                               int RSR = 0, int T = 0) {
     constexpr int kGroup = 32 * (1 + G);                  // this warp + its workers
+    constexpr int kWU = NB % 7 == 0 ? 7 : NB % 5 == 0 ? 5 : NB;   // frames per unrolled group
     const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;
     const int S = 2 * L + 1;
@@ -800,12 +801,12 @@ __device__ __forceinline__ void ctc_walk_tile(const float* tile, const int32_t* 
     PGASR_STAMP(dbg, kAlpha ? 12 : 16);
 
     // ---- second half: post-emission values go to the workers in batches of kBatch frames -----------
-    for (int q = 0; q < n2; q += kBatchOf<SPL>) {
-        const int buf = (q / kBatchOf<SPL>) & 1;
-        if (q >= 2 * kBatchOf<SPL>) named_bar_sync(ring.bar_empty + buf, kGroup);
-        double2* sp = reinterpret_cast<double2*>(ring.slots + (size_t)(buf * kBatchOf<SPL>) * (SPL * 16)) + lane;
-        int* ep = ring.eslot + buf * kBatchOf<SPL>;
-        const int nfr = min(kBatchOf<SPL>, n2 - q);
+    for (int q = 0; q < n2; q += NB) {
+        const int buf = (q / NB) & 1;
+        if (q >= 2 * NB) named_bar_sync(ring.bar_empty + buf, kGroup);
+        double2* sp = reinterpret_cast<double2*>(ring.slots + (size_t)(buf * NB) * (SPL * 16)) + lane;
+        int* ep = ring.eslot + buf * NB;
+        const int nfr = min(NB, n2 - q);
         if (q == 0) {
             // first frame of the second half: measure Z0 against the other direction's full row and publish the
             // normalisation for the workers (they read it after the first bar_full)
@@ -813,10 +814,10 @@ __device__ __forceinline__ void ctc_walk_tile(const float* tile, const int32_t* 
             const int tf = kAlpha ? n_first : Tb - 1 - n_first;
             ctc_walk_publish_norm<SPL, kAlpha>(w, lat_u + (size_t)tf * (SPL * 32), exp_u + tf, ring.norm);
             for (int u = 1; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
-        } else if (nfr == kBatchOf<SPL>) {
-            for (int u0 = 0; u0 < kBatchOf<SPL>; u0 += kWalkUnroll<SPL>) {
+        } else if (nfr == NB) {
+            for (int u0 = 0; u0 < NB; u0 += kWU) {
 #pragma unroll
-                for (int u = 0; u < kWalkUnroll<SPL>; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
+                for (int u = 0; u < kWU; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
             }
         } else {
             for (int u = 0; u < nfr; ++u) ctc_walk_frame<SPL, kAlpha, false, kGT>(w, sp, (SPL / 4) * 32, ep, 1, lane0);
@@ -1160,6 +1161,318 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const float* tile, const 
         g_dbg[kAlpha ? 21 : 23] = nm.tBusy;
         g_dbg[kAlpha ? 25 : 29] = nm.tA;
         g_dbg[kAlpha ? 26 : 30] = nm.tB;
+    }
+#endif
+}
+
+}  // namespace pgasr
+
+// =====================================================================================================
+// Block workers (round 2; up to 8 states per lane, probability tile in shared memory).
+//
+// What bounded the second half was the gradient ROW, not the lattice: with a lane per class a row is a gather of the
+// class's label occupancies from arbitrary positions -- 8 to 12 bank-conflicting LDS per frame and warp, 27 of the ~40
+// shared-memory wavefronts a frame cost -- and the SM's one shared-memory pipe was ~60 % busy, which is also what
+// slowed the walkers from 130 to 180 cycles per frame.  Here the rows of a BLOCK of up to 32 consecutive frames are
+// formed together with a lane per FRAME:
+//   * A-workers (GA per direction) do what phase A did -- occupancy of every label state of a frame, 2^-30 fixed
+//     point -- and store it TRANSPOSED into the block's matrix gam[label][frame slot] (bank = slot ^ (label / labels
+//     per lane): conflict free for the A-worker's stores, one per label of the lane, and for the reads below).
+//   * B-workers (GB per direction, block b belongs to B-worker b % GB and to matrix buffer b % GB) walk the
+//     transcript's labels in CLASS ORDER (one warp-uniform list per utterance) and add gam[label][lane's frame] into
+//     a per-class accumulator: one conflict-free LDS per label for 30 frames at once, no gather, no tail loop.  At
+//     the end of a class the lane turns (p - occupancy) into the gradient entry and stores it in place of p_t(v) in
+//     the probability tile (row stride odd: conflict free; nobody reads a row's probabilities after its frame has
+//     been handed to the workers), and when the block is done its rows leave as one contiguous, coalesced copy.
+// Per frame this is ~20 shared-memory wavefronts instead of ~40 and ~75 warp instructions instead of ~115.
+// Hand-offs: walker -> A-workers through the ring as before (batches of 2 GA frames, named barriers); A-workers ->
+// B-worker one named barrier per block (gam_full); B-worker -> A-workers a release/acquire counter in shared memory
+// per matrix buffer (the B-worker is a block period ahead, so the wait is normally a single load).
+// =====================================================================================================
+namespace pgasr {
+
+constexpr int kBwGA = 5;          // A-workers per direction
+constexpr int kBwGB = 2;          // B-workers per direction (= matrix buffers per direction)
+constexpr int kBwNB = 2 * kBwGA;  // frames per ring batch: two per A-worker
+constexpr int kBwBB = 32 / kBwNB; // ring batches per block
+constexpr int kBwBlk = kBwBB * kBwNB;   // frames per block (<= 32: a lane per frame)
+
+template <int SPL>
+__host__ __device__ inline size_t bw_gam_bytes() { return (size_t)kBwGB * (16 * SPL) * 32 * sizeof(int); }   // per direction
+// class-ordered label list: every class padded to an even number of entries -> at most L + V entries
+__host__ __device__ inline size_t bw_list_words(int V) { return (size_t)(512 + 2 * 34 + (V + 2)); }
+
+__device__ __forceinline__ int lds_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];\n" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_release_s32(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// The transcript's label positions in class order (from the CSR lists of ctc_build_class_lists), as byte offsets into
+// a matrix buffer with the frame-slot swizzle folded in: entry = row * 128 | (row / LPL) * 4, so that the address of
+// (label, frame slot f) is buffer + (entry ^ 4 f).  Every class is padded to an even count with the all-zero row
+// 16 SPL - 1 (its state lies beyond S for every transcript this variant takes).  eoff[v] = first entry of class v.
+// One warp; V <= 32.
+template <int SPL>
+__device__ __forceinline__ void bw_build_list(const int* cls_off, const int* cls_pos, int V, unsigned* elist, int* eoff) {
+    constexpr int LPL = SPL / 2, kRows = 16 * SPL;
+    const int lane = threadIdx.x & 31;
+    const int cnt = lane < V ? cls_off[lane + 1] - cls_off[lane] : 0;
+    const int pc = (cnt + 1) & ~1;
+    int incl = pc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += x;
+    }
+    const int start = incl - pc;
+    if (lane < V) eoff[lane] = start;
+    if (lane == 31) eoff[V] = incl;                       // (lanes >= V add nothing)
+    const unsigned ez = (unsigned)((kRows - 1) * 128 + ((kRows - 1) / LPL) * 4);
+    if (lane < V) {
+        const int src = cls_off[lane];
+        for (int i = 0; i < pc; ++i) {
+            unsigned e = ez;
+            if (i < cnt) {
+                const int li = cls_pos[src + i];
+                e = (unsigned)(li * 128 + (li / LPL) * 4);
+            }
+            elist[start + i] = e;
+        }
+    }
+    __syncwarp();
+}
+
+// A-worker g (0 .. GA-1) of one direction: frames g and g + GA of every ring batch.
+template <int SPL, bool kAlpha, typename Barrier>
+__device__ __forceinline__ void ctc_aworker(int g, int Tb, int L, const double* __restrict__ lat_u,
+                                            const int* __restrict__ exp_u, GradRing<SPL, kBwNB> ring, int* gam,
+                                            int* done, int bar_gfull, Barrier mid_barrier) {
+    constexpr int GA = kBwGA, GB = kBwGB, NB = kBwNB, kBB = kBwBB, LPL = SPL / 2, kRows = 16 * SPL;
+    constexpr int kGroup = 32 * (1 + GA);
+    const int lane = threadIdx.x & 31;
+    const int tm = Tb / 2;
+    const int n_first = kAlpha ? tm : Tb - tm;
+    const int n2 = Tb - n_first;
+    const int S = 2 * L + 1;
+    const bool act = lane * SPL < S;                      // the other direction never stored the lanes beyond S
+    mid_barrier();                                        // the other direction's half-lattice is complete
+    const int nbatch = (n2 + NB - 1) / NB;
+    const unsigned long long pol = l2_policy_evict_first();
+    const double2* lat2 = reinterpret_cast<const double2*>(lat_u) + lat_lane_off<SPL>(lane);
+    double2 o[2][SPL / 4];
+    int eo[2], tF[2], qF[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        qF[r] = g + r * GA;
+        tF[r] = kAlpha ? n_first + qF[r] : Tb - 1 - n_first - qF[r];
+    }
+    auto fetch = [&]() {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const bool valid = qF[r] < n2;
+            const double2* lp = lat2 + (size_t)tF[r] * (SPL * 16);
+            if constexpr (SPL >= 8) {
+#pragma unroll
+                for (int j2 = 0; j2 < SPL / 8; ++j2) {
+                    o[r][2 * j2] = o[r][2 * j2 + 1] = make_double2(0.0, 0.0);
+                    if (act && valid) ld_lattice4(lp + j2 * 64, pol, o[r][2 * j2], o[r][2 * j2 + 1]);
+                }
+            } else {
+                o[r][0] = (act && valid) ? ld_lattice(lp, pol) : make_double2(0.0, 0.0);
+            }
+            eo[r] = valid ? __ldcg(exp_u + tF[r]) : 0;
+            qF[r] += NB;
+            tF[r] += kAlpha ? NB : -NB;
+        }
+    };
+    if (nbatch > 0) fetch();
+    double invZ0 = 0.0;
+    int E0 = 0;
+    // this lane's rows of a matrix buffer start at label LPL * lane; the frame slot is XORed with the lane
+    int* const grow = gam + (LPL * lane) * 32;
+    int blk = 0, bi = 0;                                  // block of this batch, batch within the block
+#ifdef PGASR_TIMING
+    long long tWait = 0, tSpin = 0, tBusy = 0;
+#endif
+    for (int nb = 0; nb < nbatch; ++nb) {
+        const int buf = nb & 1;
+#ifdef PGASR_TIMING
+        const long long c0 = clock64();
+#endif
+        named_bar_sync(ring.bar_full + buf, kGroup);
+#ifdef PGASR_TIMING
+        const long long c1 = clock64();
+        tWait += c1 - c0;
+#endif
+        if (nb == 0) {                                    // the walker measured Z0 on its first second-half frame
+            invZ0 = ring.norm[0];
+            E0 = reinterpret_cast<const int*>(ring.norm)[2];
+        }
+        const int gbuf = blk % GB;
+        if (bi == 0 && blk >= GB) {                       // the buffer's previous block must have been consumed
+            const int need = blk / GB;
+            while (lds_acquire_s32(done + gbuf) < need) { }
+        }
+#ifdef PGASR_TIMING
+        const long long c2 = clock64();
+        tSpin += c2 - c1;
+#endif
+        double2 av[2][SPL / 4];
+        int E[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int slot = buf * NB + g + r * GA;
+            const double2* sp = reinterpret_cast<const double2*>(ring.slots + (size_t)slot * (SPL * 16)) + lane;
+#pragma unroll
+            for (int jj = 0; jj < SPL / 4; ++jj) av[r][jj] = sp[jj * 32];
+            E[r] = ring.eslot[slot];
+        }
+        int wi[2][LPL];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            // occupancy = a(s) o(s) invZ0 2^(E + eo - E0) in 2^-30 fixed point, the power of two split between the two
+            // factors so that the product cannot underflow on its own (see ctc_worker_phase_a)
+            const int ex = E[r] + eo[r] - E0;
+            const int h1 = (ex >> 1) - 15;
+            const double s1 = invZ0 * pow2i(h1), s2 = pow2i(ex - h1);
+#pragma unroll
+            for (int jj = 0; jj < SPL / 4; ++jj) {
+                wi[r][2 * jj] = __double2loint((av[r][jj].x * s1) * (o[r][jj].x * s2) + kCtcMagic);
+                wi[r][2 * jj + 1] = __double2loint((av[r][jj].y * s1) * (o[r][jj].y * s2) + kCtcMagic);
+            }
+        }
+        int* const gb = grow + gbuf * (kRows * 32);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int f = bi * NB + g + r * GA;           // frame slot within the block
+            int* const gp = gb + (f ^ lane);
+#pragma unroll
+            for (int j = 0; j < LPL; ++j) gp[j * 32] = wi[r][j];
+        }
+        if (nb + 1 < nbatch) fetch();
+        if (nb + 2 < nbatch) named_bar_arrive(ring.bar_empty + buf, kGroup);   // ring buffer may be overwritten
+        const bool last_of_block = bi == kBB - 1 || nb == nbatch - 1;
+        if (last_of_block) {
+            named_bar_arrive(bar_gfull + gbuf, 32 * (GA + 1));                 // the block's matrix is complete
+            ++blk;
+            bi = 0;
+        } else {
+            ++bi;
+        }
+#ifdef PGASR_TIMING
+        tBusy += clock64() - c2;
+#endif
+    }
+#ifdef PGASR_TIMING
+    if (ring.dbg && lane == 0 && g == 0) {
+        g_dbg[kAlpha ? 40 : 44] = tWait;
+        g_dbg[kAlpha ? 41 : 45] = tSpin;
+        g_dbg[kAlpha ? 42 : 46] = tBusy;
+    }
+#endif
+}
+
+// B-worker j (0 .. GB-1) of one direction: blocks j, j + GB, ...  Lane f = frame slot f of the block.
+template <int SPL, bool kAlpha, typename Barrier>
+__device__ __forceinline__ void ctc_bworker(int j, float* tile, int RS, int Tb, int V, int blank, float grad_scale,
+                                            float* __restrict__ dlog_u, const double* norm, const int* gam, int* done,
+                                            int bar_gfull, const unsigned* elist, const int* eoff, Barrier mid_barrier,
+                                            bool dbg = false) {
+    constexpr int GA = kBwGA, GB = kBwGB, kBlk = kBwBlk, kRows = 16 * SPL;
+    const int lane = threadIdx.x & 31;
+    const int tm = Tb / 2;
+    const int n_first = kAlpha ? tm : Tb - tm;
+    const int n2 = Tb - n_first;
+    mid_barrier();
+    const int nblocks = (n2 + kBlk - 1) / kBlk;
+    // the matrix buffers are aligned to their size (16 SPL rows of 128 bytes), so buffer base, row offset and swizzled
+    // frame slot combine with ONE xor: address = entry ^ (base | 4 lane)
+    const unsigned fx = (unsigned)__cvta_generic_to_shared(gam + j * (kRows * 32)) | ((unsigned)lane << 2);
+    const unsigned el_s = (unsigned)__cvta_generic_to_shared(elist), eo_s = (unsigned)__cvta_generic_to_shared(eoff);
+    const unsigned M = (65536u + (unsigned)V - 1u) / (unsigned)V;      // e / V = (e * M) >> 16 for e < 1024, V <= 32
+    const float gs30 = grad_scale * kCtcUnfix;
+    bool dead = false;
+    int it = 0;
+#ifdef PGASR_TIMING
+    long long tWait = 0, tRows = 0, tCopy = 0;
+#endif
+    for (int blk = j; blk < nblocks; blk += GB, ++it) {
+#ifdef PGASR_TIMING
+        const long long c0 = clock64();
+#endif
+        named_bar_sync(bar_gfull + j, 32 * (GA + 1));
+#ifdef PGASR_TIMING
+        const long long c1 = clock64();
+        tWait += c1 - c0;
+#endif
+        if (it == 0) dead = reinterpret_cast<const int*>(norm)[3] != 0;
+        const int q0 = blk * kBlk;
+        const int nf = min(kBlk, n2 - q0);
+        const bool valid = lane < nf;
+        const int q = q0 + min(lane, nf - 1);
+        const int t = kAlpha ? n_first + q : Tb - 1 - n_first - q;
+        const unsigned prow = (unsigned)__cvta_generic_to_shared(tile + (size_t)t * RS);
+        int tot = 0;
+        int i0 = lds_s32(eo_s);
+        for (int v = 0; v < V; ++v) {
+            const int i1 = lds_s32(eo_s + 4u * (unsigned)(v + 1));
+            int a0 = 0, a1 = 0;
+            for (int i = i0; i < i1; i += 2) {
+                unsigned ex, ey;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(ex), "=r"(ey) : "r"(el_s + 4u * (unsigned)i) : "memory");
+                a0 += lds_s32(ex ^ fx);
+                a1 += lds_s32(ey ^ fx);
+            }
+            i0 = i1;
+            const int occ = a0 + a1;
+            tot += occ;
+            if (v != blank) {
+                const unsigned pa = prow + 4u * (unsigned)v;
+                const int pfix = __float2int_rn(lds_f32_v(pa) * (float)kCtcFix);
+                const float gval = dead ? 0.0f : (float)(pfix - occ) * gs30;
+                if (valid) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(pa), "f"(gval) : "memory");
+            }
+        }
+        {   // the blank column: sum_s gamma_t(s) = 1
+            const unsigned pa = prow + 4u * (unsigned)blank;
+            const int pfix = __float2int_rn(lds_f32_v(pa) * (float)kCtcFix);
+            const float gval = dead ? 0.0f : (float)(pfix - ((1 << 30) - tot)) * gs30;
+            if (valid) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(pa), "f"(gval) : "memory");
+        }
+        __syncwarp();
+        if (lane == 0) sts_release_s32(done + j, it + 1);              // the matrix buffer may be refilled
+#ifdef PGASR_TIMING
+        const long long c2 = clock64();
+        tRows += c2 - c1;
+#endif
+        // the block's rows are contiguous in dlogits: one coalesced copy
+        const int tlo = kAlpha ? n_first + q0 : Tb - 1 - n_first - q0 - (nf - 1);
+        float* const out = dlog_u + (size_t)tlo * V;
+        const float* const src = tile + (size_t)tlo * RS;
+        const int ne = nf * V;
+        for (int e = lane; e < ne; e += 32) {
+            const int r = (int)(((unsigned)e * M) >> 16);
+            out[e] = src[r * RS + (e - r * V)];
+        }
+        __syncwarp();
+#ifdef PGASR_TIMING
+        tCopy += clock64() - c2;
+#endif
+    }
+#ifdef PGASR_TIMING
+    if (dbg && lane == 0 && j == 0) {
+        g_dbg[kAlpha ? 48 : 52] = tWait;
+        g_dbg[kAlpha ? 49 : 53] = tRows;
+        g_dbg[kAlpha ? 50 : 54] = tCopy;
     }
 #endif
 }

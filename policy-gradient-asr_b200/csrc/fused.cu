@@ -1,5 +1,6 @@
 // Host side of the single-launch kernel: what fits where (fused_plan), workspace layout, dispatch to the per-SPL
 // translation units (fused_spl4/8/16/32.cu, which instantiate fused_impl.cuh).
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -43,6 +44,18 @@ static FusedWs fused_ws(int B, int T, int V, int spl, bool gt) {
     return w;
 }
 
+// block workers (ctc_core.cuh): tile with an odd row stride, rings of 10 frames, two transposed occupancy matrices per
+// direction, the class-ordered label list
+static size_t ctc_role_smem_bw(int T, int V, int spl) {
+    const int RS = (V + 1) | 1;
+    const size_t tile = (((size_t)(T + 4) * RS * sizeof(float) + 15) & ~(size_t)15);
+    const size_t ring = spl == 4 ? grad_ring_bytes<4, kBwNB>() : grad_ring_bytes<8, kBwNB>();
+    const size_t gam = 2 * (spl == 4 ? bw_gam_bytes<4>() : bw_gam_bytes<8>());
+    const size_t align_slack = (size_t)16 * spl * 128;            // the matrices are aligned to their size by address
+    return tile + align_slack + 2 * ring + gam + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int) + 8 +
+           (size_t)(512 + V + 1 + 2 * kBwGB) * sizeof(int);
+}
+
 static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
     const int RS = ctc_row_stride_f32(V);
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
@@ -60,13 +73,13 @@ static size_t pg_role_smem(int T, int V, int K, int spl, int threads, bool strea
 }
 
 // What the single-launch kernel can take for this shape.
-struct FusedPlan { int spl, threads; bool ctc_ok, gt, pg_ok, stream; };
+struct FusedPlan { int spl, threads; bool ctc_ok, gt, pg_ok, stream, bw; };
 
 static FusedPlan fused_plan(int T, int V, int K, int Lmax) {
     FusedPlan pl;
     pl.spl = ctc_spl(Lmax);
     pl.threads = pl.spl >= 32 ? 256 : 512;             // 32 states per lane need the 255-register budget
-    pl.ctc_ok = pl.gt = pl.pg_ok = pl.stream = false;
+    pl.ctc_ok = pl.gt = pl.pg_ok = pl.stream = pl.bw = false;
     if (pl.spl == 0 || V > 32 || K > kFusedMaxK) return pl;
     // each role keeps its [T][..] tile in shared memory when it fits one SM, else it streams; the streaming PG role
     // is only instantiated next to the streaming CTC role, so a PG role that has to stream makes the CTC role stream
@@ -77,6 +90,9 @@ static FusedPlan fused_plan(int T, int V, int K, int Lmax) {
     if (ctc_tile && (pg_tile || !(ctc_gt && pg_stream))) {
         pl.ctc_ok = true;
         pl.pg_ok = pg_tile;
+        // block workers when their (larger) shared-memory layout fits too; PGASR_NO_BW=1 keeps the round-1 workers (A/B)
+        static const bool no_bw = getenv("PGASR_NO_BW") != nullptr;
+        pl.bw = !no_bw && pl.spl <= 8 && pl.threads == 512 && ctc_role_smem_bw(T, V, pl.spl) <= kFusedSmemLimit;
     } else if (ctc_gt) {
         pl.ctc_ok = pl.gt = true;
         if (pg_tile) pl.pg_ok = true;
@@ -115,10 +131,10 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
     a.loss_terms = reinterpret_cast<float*>(p);          p += w.terms;
     a.nll_ws = reinterpret_cast<float*>(p);              p += w.nll;
     a.tile_g = pl.gt ? reinterpret_cast<float*>(p) : nullptr;
-    size_t smem = a.do_ctc ? ctc_role_smem(a.T, a.V, pl.spl, pl.threads, pl.gt) : 0;
+    size_t smem = !a.do_ctc ? 0 : pl.bw ? ctc_role_smem_bw(a.T, a.V, pl.spl) : ctc_role_smem(a.T, a.V, pl.spl, pl.threads, pl.gt);
     const bool stream = a.do_pg && pl.stream;
     if (a.do_pg) smem = smem > pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream) ? smem : pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream);
-    const int mode = !pl.gt ? 0 : !stream ? 1 : 2;          // tiles in shared memory | CTC streams | both stream
+    const int mode = pl.bw ? 3 : !pl.gt ? 0 : !stream ? 1 : 2;   // tiles in shared memory | CTC streams | both stream | block workers
     switch (pl.spl) {
         case 4: return launch_fused_spl4(mode, a, smem, st);
         case 8: return launch_fused_spl8(mode, a, smem, st);

@@ -97,14 +97,19 @@ __device__ __forceinline__ int cdf_count32(const float (&c)[32], float tau) {
 // kGT (long utterances): the fp32 softmax tile does not fit in shared memory; it is written to the global
 // workspace instead, the walkers stream it back through 32-row cp.async rings and the workers fetch their
 // p_t(lane) with the lattice row.  Shared memory then no longer depends on T.
-template <int SPL, int kThreads, bool kGT>
+// kBW: block workers (ctc_core.cuh, "Block workers"): 5 occupancy workers and 2 row workers per direction instead of 7
+// workers that do both; up to 8 states per lane, tile in shared memory, 512 threads.
+template <int SPL, int kThreads, bool kGT, bool kBW = false>
 __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last) {
+    static_assert(!kBW || (!kGT && SPL <= 8 && kThreads == 32 * (2 + 2 * (kBwGA + kBwGB))), "block workers: tile mode only");
     constexpr int G = (kThreads / 32 - 2) / 2;             // gradient workers per direction
     constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;      // frames of a batch per worker
     constexpr int kMidThreads = 32 * (2 + 2 * G);
     const int warp = threadIdx.x >> 5;
     const int T = a.T, V = a.V;
-    const int RS = ctc_row_stride_f32(V);
+    // floats per tile row.  Block workers read and write the tile with a lane per FRAME, so consecutive rows must
+    // fall into different banks: an odd stride with at least one zero slot after the V classes
+    const int RS = kBW ? ((V + 1) | 1) : ctc_row_stride_f32(V);
     // shared-memory carve-up (see fused_smem)
     // [T][RS] between two pairs of guard rows: the walkers load the probabilities two frames ahead and run two rows
     // past either end (the guard values are loaded and never used)
@@ -126,15 +131,32 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         tile = reinterpret_cast<float*>(smem_raw) + 2 * RS;
         p = smem_raw + (((size_t)(T + 4) * RS * 4 + 15) & ~(size_t)15);
     }
+    constexpr int kNB = kBW ? kBwNB : kBatchOf<SPL>;                    // frames per hand-off batch
+    int* bw_gam = nullptr;
+    if constexpr (kBW) {
+        // block workers: the four occupancy matrices come first, each aligned to its size BY ADDRESS (ctc_bworker folds
+        // the buffer base into its address xor)
+        constexpr unsigned kBuf = 16 * SPL * 128;
+        const unsigned at = (unsigned)__cvta_generic_to_shared(p);
+        p += (kBuf - (at & (kBuf - 1))) & (kBuf - 1);
+        bw_gam = reinterpret_cast<int*>(p);
+    }
     unsigned char* const stage_base = p;
-    GradRing<SPL> ring_a = grad_ring_carve<SPL>(p, 2);                  p += grad_ring_bytes<SPL>();
-    GradRing<SPL> ring_b = grad_ring_carve<SPL>(p, 6);                  p += grad_ring_bytes<SPL>();
+    if constexpr (kBW) p += 2 * bw_gam_bytes<SPL>();
+    GradRing<SPL, kNB> ring_a = grad_ring_carve<SPL, kNB>(p, 2);        p += grad_ring_bytes<SPL, kNB>();
+    GradRing<SPL, kNB> ring_b = grad_ring_carve<SPL, kNB>(p, 6);        p += grad_ring_bytes<SPL, kNB>();
     int* gam_all = reinterpret_cast<int*>(p);                           // [2 G workers][kPer frames][16 SPL]
-    p += (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
+    // (block workers: [2 directions][kBwGB buffers][16 SPL labels][32 frame slots])
+    const size_t gam_bytes = kBW ? 2 * bw_gam_bytes<SPL>() : (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
+    if constexpr (!kBW) p += gam_bytes;
     int* cls_off = reinterpret_cast<int*>(p);                           // [V + 1]
     int* cls_scr = cls_off + (V + 1);                                   // [V] counting-sort scratch
     int* cls_pos = cls_scr + V;                                         // [512]
     int* lab_s = cls_pos + 512;                                         // [512] the transcript
+    // block workers: class-ordered label list (8-byte aligned), CSR offsets, consumed-block counters
+    unsigned* bw_elist = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(lab_s + 512) + 7) & ~(uintptr_t)7);
+    int* bw_eoff = reinterpret_cast<int*>(bw_elist + 512);              // [V + 1] (the list holds at most L + V entries)
+    int* bw_done = bw_eoff + (V + 1);                                   // [2][kBwGB]
     // The transcript and the lengths may live in mapped HOST memory (pgasr_host_*: a PCIe round trip per dependent
     // access), so everything is fetched here in one go and the transcript is used from shared memory afterwards.
     for (int i = threadIdx.x; i < a.Lmax; i += kThreads) lab_s[i] = a.targets[(size_t)b * a.Lmax + i];
@@ -159,7 +181,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         const float* lg = a.logits + (size_t)b * T * V;
         {
             float* stage = reinterpret_cast<float*>(stage_base);
-            const size_t stage_bytes = 2 * grad_ring_bytes<SPL>() + (size_t)2 * G * kPer * 16 * SPL * sizeof(int);
+            const size_t stage_bytes = 2 * grad_ring_bytes<SPL, kNB>() + gam_bytes;
             const int chunk = (int)(stage_bytes / ((size_t)V * 4)) & ~3;
             const bool al16 = (((size_t)T * V * 4) & 15) == 0;
             for (int c0 = 0; c0 < Tb; c0 += chunk) {
@@ -178,7 +200,13 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                 if (c0 == 0) {
                     // class lists of the transcript, built by warp 0 while the logits are in flight
                     __syncthreads();                           // the transcript is in shared memory
-                    if (warp == 0) ctc_build_class_lists(lab_s, L, V, cls_off, cls_pos, cls_scr);
+                    if (warp == 0) {
+                        ctc_build_class_lists(lab_s, L, V, cls_off, cls_pos, cls_scr);
+                        if constexpr (kBW) {
+                            bw_build_list<SPL>(cls_off, cls_pos, V, bw_elist, bw_eoff);
+                            if (threadIdx.x < 2 * kBwGB) bw_done[threadIdx.x] = 0;
+                        }
+                    }
                 }
                 cp_async_wait<0>();
                 __syncthreads();
@@ -187,10 +215,13 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                     // not matter for the max and the sum, every load / exp / store is independent of the others
                     const float* zr = stage + (size_t)t * V;
                     float* orow = tile + (size_t)(c0 + t) * RS;
+                    // (block workers: the tile's row stride is odd, so the UNROTATED order is the conflict-free one for
+                    // the writes; the staged reads are then two-way conflicted, 64 wavefronts per warp, once)
+                    const int rot = kBW ? 0 : t;
                     float x[32];
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
-                        const int idx = (k + t) & 31;
+                        const int idx = (k + rot) & 31;
                         x[k] = idx < V ? zr[idx] : -INFINITY;
                     }
                     float m4[4] = {x[0], x[1], x[2], x[3]};
@@ -206,7 +237,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                     const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
-                        const int idx = (k + t) & 31;
+                        const int idx = (k + rot) & 31;
                         if (idx < RS) orow[idx] = x[k] * inv;
                     }
                     for (int idx = 32; idx < RS; ++idx) orow[idx] = 0.0f;
@@ -227,6 +258,28 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
             asm volatile("bar.sync 1, %0;\n" ::"n"(kMidThreads) : "memory");
         };
         const int g = (warp - 2) >> 1;
+        if constexpr (kBW) {
+            // even warps serve alpha, odd warps beta.  Of a direction's seven (g = 0..6) the row workers are g = 0 and
+            // g = 2 -- warps 2, 6 / 3, 7, i.e. scheduler partitions 2 and 3, away from the walkers on 0 and 1
+            const bool al = !(warp & 1);
+            int* gam_d = bw_gam + (al ? 0 : 1) * (kBwGB * 16 * SPL * 32);
+            int* done_d = bw_done + (al ? 0 : kBwGB);
+            const int bar_g = al ? 10 : 12;
+            const int bj = g == 0 ? 0 : g == 2 ? 1 : -1;
+            const int ga = g == 1 ? 0 : g - 2;
+            if (warp == 0)
+                ctc_walk_tile<SPL, kBwGA, true, false, kBwNB>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid);
+            else if (warp == 1)
+                ctc_walk_tile<SPL, kBwGA, false, false, kBwNB>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_b, mid);
+            else if (bj >= 0 && al)
+                ctc_bworker<SPL, true>(bj, tile, RS, Tb, V, a.blank, gs, dlog_u, ring_a.norm, gam_d, done_d, bar_g, bw_elist, bw_eoff, mid, b == 0);
+            else if (bj >= 0)
+                ctc_bworker<SPL, false>(bj, tile, RS, Tb, V, a.blank, gs, dlog_u, ring_b.norm, gam_d, done_d, bar_g, bw_elist, bw_eoff, mid, b == 0);
+            else if (al)
+                ctc_aworker<SPL, true>(ga, Tb, L, lat_u, exp_u, ring_a, gam_d, done_d, bar_g, mid);
+            else
+                ctc_aworker<SPL, false>(ga, Tb, L, lat_u, exp_u, ring_b, gam_d, done_d, bar_g, mid);
+        } else
         if (warp == 0)
             ctc_walk_tile<SPL, G, true, kGT>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid, pring_a,
                                              RSR, T);
@@ -577,7 +630,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #endif
 
-template <int SPL, int kThreads, bool kGT, bool kStream>
+template <int SPL, int kThreads, bool kGT, bool kStream, bool kBW = false>
 __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_ticket, s_last;
@@ -593,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const unsigned ticket = s_ticket;
     const unsigned n_ctc = a.do_ctc ? (unsigned)a.B : 0u;
-    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT>(a, (int)ticket, smem_raw, &s_last);
+    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT, kBW>(a, (int)ticket, smem_raw, &s_last);
     else fused_pg_role<SPL / 2, kThreads, kStream>(a, (int)(ticket - n_ctc), smem_raw, &s_last);
 
 #ifdef PGASR_TIMING
@@ -609,14 +662,14 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
 #endif
 }
 
-template <int SPL, int kThreads, bool kGT, bool kStream>
+template <int SPL, int kThreads, bool kGT, bool kStream, bool kBW = false>
 static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
     // the opt-in is sticky PER DEVICE: raise it only when a larger tile comes on the device the launch goes to
     static thread_local size_t smem_set[64] = {0};
     int dev = 0;
     PGASR_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
-        PGASR_CUDA_TRY(cudaFuncSetAttribute(pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream>,
+        PGASR_CUDA_TRY(cudaFuncSetAttribute(pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream, kBW>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) smem_set[dev] = smem;
     }
@@ -632,15 +685,19 @@ static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
-    PGASR_CUDA_TRY(cudaLaunchKernelEx(&cfg, pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream>, a));
+    PGASR_CUDA_TRY(cudaLaunchKernelEx(&cfg, pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream, kBW>, a));
     ++g_launches;
     return PGASR_OK;
 }
 
-// one translation unit per SPL instantiates its three modes (0: tiles in shared memory, 1: the CTC role streams,
-// 2: both roles stream) so that the variants compile in parallel
+// one translation unit per SPL instantiates its modes (0: tiles in shared memory, 1: the CTC role streams,
+// 2: both roles stream, 3: tiles in shared memory with block workers -- up to 8 states per lane only) so that the
+// variants compile in parallel
 template <int SPL, int kThreads>
 int launch_fused_modes(int mode, FusedArgs& a, size_t smem, cudaStream_t st) {
+    if constexpr (SPL <= 8) {
+        if (mode == 3) return launch_fused<SPL, kThreads, false, false, true>(a, smem, st);
+    }
     switch (mode) {
         case 0: return launch_fused<SPL, kThreads, false, false>(a, smem, st);
         case 1: return launch_fused<SPL, kThreads, true, false>(a, smem, st);

@@ -31,12 +31,14 @@ def rel_err(got, want):
 
 def grad_close(got, want, rtol=RTOL):
     """Element-wise bar next to the max-norm one: |got - want| <= 1e-4 |want| + atol for EVERY entry, with
-    atol = max(1e-7, 1e-6 max|want|): 1e-7 absolute at the bench shape (rows are scaled by 1/B = 1/64), and never
-    below a few fp32 ulps of the largest entry (dlogits is fp32: an entry that is a difference of two O(scale)
-    terms cannot be closer to the fp64 oracle than that)."""
+    atol = max(1e-7, 1e-5 max|want|): 1e-7 absolute at the bench shape (rows are scaled by 1/B = 1/64, mean baseline),
+    and never below ~100 fp32 ulps of the largest entry: dlogits is fp32 and an entry is a difference of O(max)
+    terms -- without a baseline the REINFORCE row is p * sum_k A_k minus K scatter terms of the same size, each
+    rounded in fp32 (measured 1.6e-6 of the maximum at K = 33), so an entry cannot be closer to the fp64 oracle
+    than that.  Still ten times tighter than the max-norm bar, and applied to every entry."""
     want = np.asarray(want, np.float64)
     got = np.asarray(got, np.float64)
-    atol = max(1e-7, 1e-6 * float(np.abs(want).max()))
+    atol = max(1e-7, 1e-5 * float(np.abs(want).max()))
     bad = np.abs(got - want) > rtol * np.abs(want) + atol
     return not bad.any()
 
