@@ -1191,16 +1191,18 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const float* tile, const 
 // =====================================================================================================
 namespace pgasr {
 
-constexpr int kBwGA = 5;          // A-workers per direction
-constexpr int kBwGB = 2;          // B-workers per direction (= matrix buffers per direction)
+// Warp w of the CTA runs on scheduler partition w % 4.  The walkers are warps 0 and 1; the occupancy (A) workers -- the
+// fp64 work -- sit on partitions 2 and 3 only (warps 2,3,6,7,10,11,14,15: four per direction), the row (B) workers
+// share the walkers' partitions (integer and shared-memory work), and the two warps left over idle at the barriers.
+constexpr int kBwGA = 4;          // A-workers per direction
+constexpr int kBwGB = 2;          // B-workers per direction (= matrix buffers per direction), at most 3
 constexpr int kBwNB = 2 * kBwGA;  // frames per ring batch: two per A-worker
 constexpr int kBwBB = 32 / kBwNB; // ring batches per block
 constexpr int kBwBlk = kBwBB * kBwNB;   // frames per block (<= 32: a lane per frame)
 
 template <int SPL>
 __host__ __device__ inline size_t bw_gam_bytes() { return (size_t)kBwGB * (16 * SPL) * 32 * sizeof(int); }   // per direction
-// class-ordered label list: every class padded to an even number of entries -> at most L + V entries
-__host__ __device__ inline size_t bw_list_words(int V) { return (size_t)(512 + 2 * 34 + (V + 2)); }
+__host__ __device__ inline size_t bw_stage_bytes() { return (size_t)kBwBlk * 32 * sizeof(float); }     // per B-worker, V <= 32
 
 __device__ __forceinline__ int lds_acquire_s32(const int* p) {
     int v;
@@ -1210,23 +1212,53 @@ __device__ __forceinline__ int lds_acquire_s32(const int* p) {
 __device__ __forceinline__ void sts_release_s32(int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
+// mbarrier (shared memory, CTA scope): the row worker's "matrix buffer consumed" signal.  A waiter sleeps in hardware
+// inside try_wait (a spin on ld.acquire kept five warps per direction hammering the shared-memory pipe the row worker
+// needs: it ran 4x slower than alone).
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.release.cta.shared.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared.b64 p, [%0], %1, 0x989680;\n"
+        "@p bra DONE_%=;\n"
+        "nanosleep.u32 256;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ int lds_s32(unsigned addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 
-// The transcript's label positions in class order (from the CSR lists of ctc_build_class_lists), as byte offsets into
-// a matrix buffer with the frame-slot swizzle folded in: entry = row * 128 | (row / LPL) * 4, so that the address of
-// (label, frame slot f) is buffer + (entry ^ 4 f).  Every class is padded to an even count with the all-zero row
-// 16 SPL - 1 (its state lies beyond S for every transcript this variant takes).  eoff[v] = first entry of class v.
-// One warp; V <= 32.
+// The transcript's label positions in class order (from the CSR lists of ctc_build_class_lists), as shared-memory
+// ADDRESSES of the label's row in one matrix buffer with the frame-slot swizzle folded in:
+// entry = base + row * 128 + (row / LPL) * 4, so that the address of (label, frame slot f) is entry ^ 4 f (base is
+// 128-byte aligned: the xor stays inside the row).  One list per matrix buffer (2 directions x kBwGB buffers).
+// The list is FLAT: bit 31 of an entry says "last label of its class"; a class without labels contributes one entry
+// pointing at the all-zero row 16 SPL - 1 (its state lies beyond S for every transcript this variant takes).  The row
+// worker walks the list in groups of 8, three groups per loop trip and two groups of prefetch, so the list is padded
+// with zero-row entries (no flag) to 3 ceil(groups / 3) + 2 groups.
+// info[0] = loop trips, info[4 + v] (16-byte aligned, 32 entries) = the flagged entry of class v (flag stripped): where
+// the row worker leaves the class's total.  One warp; V <= 32.
+constexpr unsigned kBwEnd = 0x80000000u;
+constexpr int kBwListWords = 256;     // per copy: the list (at most 23 groups) and, from word 192, info[36]
+constexpr int kBwInfoAt = 192;
 template <int SPL>
-__device__ __forceinline__ void bw_build_list(const int* cls_off, const int* cls_pos, int V, unsigned* elist, int* eoff) {
+__device__ __forceinline__ void bw_build_list(const int* cls_off, const int* cls_pos, int V, unsigned* elist, int* info,
+                                              unsigned base) {
     constexpr int LPL = SPL / 2, kRows = 16 * SPL;
     const int lane = threadIdx.x & 31;
     const int cnt = lane < V ? cls_off[lane + 1] - cls_off[lane] : 0;
-    const int pc = (cnt + 1) & ~1;
+    const int pc = lane < V ? max(cnt, 1) : 0;
     int incl = pc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1234,28 +1266,35 @@ __device__ __forceinline__ void bw_build_list(const int* cls_off, const int* cls
         if (lane >= o) incl += x;
     }
     const int start = incl - pc;
-    if (lane < V) eoff[lane] = start;
-    if (lane == 31) eoff[V] = incl;                       // (lanes >= V add nothing)
-    const unsigned ez = (unsigned)((kRows - 1) * 128 + ((kRows - 1) / LPL) * 4);
+    const int total = __shfl_sync(kFull, incl, 31);
+    const unsigned ez = base + (unsigned)((kRows - 1) * 128 + ((kRows - 1) / LPL) * 4);
     if (lane < V) {
         const int src = cls_off[lane];
+        unsigned e = ez;
         for (int i = 0; i < pc; ++i) {
-            unsigned e = ez;
+            e = ez;
             if (i < cnt) {
                 const int li = cls_pos[src + i];
-                e = (unsigned)(li * 128 + (li / LPL) * 4);
+                e = base + (unsigned)(li * 128 + (li / LPL) * 4);
             }
-            elist[start + i] = e;
+            elist[start + i] = i == pc - 1 ? (e | kBwEnd) : e;
         }
+        info[4 + lane] = (int)e;
     }
+    const int trips = ((total + 7) / 8 + 2) / 3;
+    for (int i = total + lane; i < 8 * (3 * trips + 2); i += 32) elist[i] = ez;
+    if (lane >= V) info[4 + lane] = (int)ez;             // (classes beyond V: the zero row, never stored)
+    if (lane == 0) info[0] = trips;
     __syncwarp();
 }
 
 // A-worker g (0 .. GA-1) of one direction: frames g and g + GA of every ring batch.
-template <int SPL, bool kAlpha, typename Barrier>
-__device__ __forceinline__ void ctc_aworker(int g, int Tb, int L, const double* __restrict__ lat_u,
+// (the direction is a run-time argument: both directions then execute the SAME instructions, which halves the
+// helpers' footprint in the instruction cache -- the walkers showed instruction-fetch stalls next to six code streams)
+template <int SPL, typename Barrier>
+__device__ __forceinline__ void ctc_aworker(bool kAlpha, int g, int Tb, int L, const double* __restrict__ lat_u,
                                             const int* __restrict__ exp_u, GradRing<SPL, kBwNB> ring, int* gam,
-                                            int* done, int bar_gfull, Barrier mid_barrier) {
+                                            unsigned long long* done, int bar_gfull, Barrier mid_barrier) {
     constexpr int GA = kBwGA, GB = kBwGB, NB = kBwNB, kBB = kBwBB, LPL = SPL / 2, kRows = 16 * SPL;
     constexpr int kGroup = 32 * (1 + GA);
     const int lane = threadIdx.x & 31;
@@ -1268,32 +1307,43 @@ __device__ __forceinline__ void ctc_aworker(int g, int Tb, int L, const double* 
     const int nbatch = (n2 + NB - 1) / NB;
     const unsigned long long pol = l2_policy_evict_first();
     const double2* lat2 = reinterpret_cast<const double2*>(lat_u) + lat_lane_off<SPL>(lane);
+    // The other direction's rows come from L2 through running pointers that stop at the worker's last frame (a frame
+    // beyond the utterance re-reads that row; its results are never used).  Lanes beyond the transcript read memory the
+    // other walker never wrote: whatever comes out lands in matrix rows no class list points at -- except the all-zero
+    // row 16 SPL - 1 (lane 31's last label), which is forced to zero below.
     double2 o[2][SPL / 4];
-    int eo[2], tF[2], qF[2];
+    int eo[2], left[2];
+    const char* lp[2];
+    const int* ep[2];
+    const ptrdiff_t lstep = (ptrdiff_t)(kAlpha ? NB : -NB) * (SPL * 16) * (ptrdiff_t)sizeof(double2);
+    const int estep = kAlpha ? NB : -NB;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        qF[r] = g + r * GA;
-        tF[r] = kAlpha ? n_first + qF[r] : Tb - 1 - n_first - qF[r];
+        const int q = g + r * GA;
+        left[r] = q < n2 ? (n2 - 1 - q) / NB : 0;         // advances left
+        const int qc = min(q, max(n2 - 1, 0));
+        const int t = kAlpha ? n_first + qc : Tb - 1 - n_first - qc;
+        lp[r] = reinterpret_cast<const char*>(lat2 + (size_t)t * (SPL * 16));
+        ep[r] = exp_u + t;
     }
     auto fetch = [&]() {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const bool valid = qF[r] < n2;
-            const double2* lp = lat2 + (size_t)tF[r] * (SPL * 16);
+            const double2* l2p = reinterpret_cast<const double2*>(lp[r]);
             if constexpr (SPL >= 8) {
 #pragma unroll
-                for (int j2 = 0; j2 < SPL / 8; ++j2) {
-                    o[r][2 * j2] = o[r][2 * j2 + 1] = make_double2(0.0, 0.0);
-                    if (act && valid) ld_lattice4(lp + j2 * 64, pol, o[r][2 * j2], o[r][2 * j2 + 1]);
-                }
+                for (int j2 = 0; j2 < SPL / 8; ++j2) ld_lattice4(l2p + j2 * 64, pol, o[r][2 * j2], o[r][2 * j2 + 1]);
             } else {
-                o[r][0] = (act && valid) ? ld_lattice(lp, pol) : make_double2(0.0, 0.0);
+                o[r][0] = ld_lattice(l2p, pol);
             }
-            eo[r] = valid ? __ldcg(exp_u + tF[r]) : 0;
-            qF[r] += NB;
-            tF[r] += kAlpha ? NB : -NB;
+            eo[r] = __ldcg(ep[r]);
+            const bool more = left[r] > 0;
+            --left[r];
+            lp[r] += more ? lstep : 0;
+            ep[r] += more ? estep : 0;
         }
     };
+    const bool zlast = lane == 31 && !act;
     if (nbatch > 0) fetch();
     double invZ0 = 0.0;
     int E0 = 0;
@@ -1319,8 +1369,7 @@ __device__ __forceinline__ void ctc_aworker(int g, int Tb, int L, const double* 
         }
         const int gbuf = blk % GB;
         if (bi == 0 && blk >= GB) {                       // the buffer's previous block must have been consumed
-            const int need = blk / GB;
-            while (lds_acquire_s32(done + gbuf) < need) { }
+            mbar_wait(done + gbuf, (unsigned)(blk / GB - 1) & 1u);   // phase k of the barrier = the buffer's k-th use consumed
         }
 #ifdef PGASR_TIMING
         const long long c2 = clock64();
@@ -1336,6 +1385,17 @@ __device__ __forceinline__ void ctc_aworker(int g, int Tb, int L, const double* 
             for (int jj = 0; jj < SPL / 4; ++jj) av[r][jj] = sp[jj * 32];
             E[r] = ring.eslot[slot];
         }
+        // the ring buffer is free as soon as this warp's values have LANDED in registers -- hand it back to the walker now
+        // rather than after the products (the barrier id takes a never-true dependency on the loaded words, which is
+        // what makes the warp wait for them)
+        if (nb + 2 < nbatch) {
+            int chk = E[0] & E[1];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int jj = 0; jj < SPL / 4; ++jj) chk &= __double2hiint(av[r][jj].x) & __double2hiint(av[r][jj].y);
+            named_bar_arrive(ring.bar_empty + buf + (chk == -1 ? 16 : 0), kGroup);   // (values are finite and >= 0: never -1)
+        }
         int wi[2][LPL];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -1349,6 +1409,7 @@ __device__ __forceinline__ void ctc_aworker(int g, int Tb, int L, const double* 
                 wi[r][2 * jj] = __double2loint((av[r][jj].x * s1) * (o[r][jj].x * s2) + kCtcMagic);
                 wi[r][2 * jj + 1] = __double2loint((av[r][jj].y * s1) * (o[r][jj].y * s2) + kCtcMagic);
             }
+            wi[r][LPL - 1] = zlast ? 0 : wi[r][LPL - 1];
         }
         int* const gb = grow + gbuf * (kRows * 32);
 #pragma unroll
@@ -1356,10 +1417,11 @@ __device__ __forceinline__ void ctc_aworker(int g, int Tb, int L, const double* 
             const int f = bi * NB + g + r * GA;           // frame slot within the block
             int* const gp = gb + (f ^ lane);
 #pragma unroll
+#ifndef EXP_A_NOSTORE
             for (int j = 0; j < LPL; ++j) gp[j * 32] = wi[r][j];
+#endif
         }
         if (nb + 1 < nbatch) fetch();
-        if (nb + 2 < nbatch) named_bar_arrive(ring.bar_empty + buf, kGroup);   // ring buffer may be overwritten
         const bool last_of_block = bi == kBB - 1 || nb == nbatch - 1;
         if (last_of_block) {
             named_bar_arrive(bar_gfull + gbuf, 32 * (GA + 1));                 // the block's matrix is complete
@@ -1382,28 +1444,35 @@ __device__ __forceinline__ void ctc_aworker(int g, int Tb, int L, const double* 
 }
 
 // B-worker j (0 .. GB-1) of one direction: blocks j, j + GB, ...  Lane f = frame slot f of the block.
-template <int SPL, bool kAlpha, typename Barrier>
-__device__ __forceinline__ void ctc_bworker(int j, float* tile, int RS, int Tb, int V, int blank, float grad_scale,
-                                            float* __restrict__ dlog_u, const double* norm, const int* gam, int* done,
-                                            int bar_gfull, const unsigned* elist, const int* eoff, Barrier mid_barrier,
-                                            bool dbg = false) {
-    constexpr int GA = kBwGA, GB = kBwGB, kBlk = kBwBlk, kRows = 16 * SPL;
+// The class-ordered label list is walked in groups of 8 entries, software pipelined (list words two groups ahead,
+// occupancies one group ahead, three register sets rotating through a loop body of three groups): uniform 16-byte
+// list loads, eight independent conflict-free occupancy loads, a running integer sum.  Where an entry carries the
+// class-end flag the class's total (a difference of two running sums) is stored over that entry's occupancy -- one
+// predicated store, no branch.  Afterwards the classes are independent: total and probability in, gradient entry out.
+// (A first version branched to an in-loop "emit" at every class end: 4 control instructions per entry and a chain
+// through the emit; 9.4k cycles per block.)
+template <int SPL, typename Barrier>
+__device__ __forceinline__ void ctc_bworker(bool kAlpha, int j, const float* tile, int RS, int Tb, int V, int blank,
+                                            float grad_scale, float* __restrict__ dlog_u, const double* norm,
+                                            unsigned long long* done, int bar_gfull, const unsigned* elist,
+                                            const int* info, float* stage, Barrier mid_barrier, bool dbg = false) {
+    constexpr int GA = kBwGA, GB = kBwGB, kBlk = kBwBlk;
     const int lane = threadIdx.x & 31;
     const int tm = Tb / 2;
     const int n_first = kAlpha ? tm : Tb - tm;
     const int n2 = Tb - n_first;
     mid_barrier();
     const int nblocks = (n2 + kBlk - 1) / kBlk;
-    // the matrix buffers are aligned to their size (16 SPL rows of 128 bytes), so buffer base, row offset and swizzled
-    // frame slot combine with ONE xor: address = entry ^ (base | 4 lane)
-    const unsigned fx = (unsigned)__cvta_generic_to_shared(gam + j * (kRows * 32)) | ((unsigned)lane << 2);
-    const unsigned el_s = (unsigned)__cvta_generic_to_shared(elist), eo_s = (unsigned)__cvta_generic_to_shared(eoff);
-    const unsigned M = (65536u + (unsigned)V - 1u) / (unsigned)V;      // e / V = (e * M) >> 16 for e < 1024, V <= 32
+    const unsigned fx = (unsigned)lane << 2;              // the frame-slot swizzle: address = entry ^ 4 lane
+    const unsigned el_s = (unsigned)__cvta_generic_to_shared(elist);
+    const unsigned cl_s = (unsigned)__cvta_generic_to_shared(info + 4);
+    const unsigned st_s = (unsigned)__cvta_generic_to_shared(stage);
     const float gs30 = grad_scale * kCtcUnfix;
+    const int ntrips = info[0];
     bool dead = false;
     int it = 0;
 #ifdef PGASR_TIMING
-    long long tWait = 0, tRows = 0, tCopy = 0;
+    long long tWait = 0, tRows = 0, tCopy = 0, tPre = 0, tLoop = 0, nBlk = 0;
 #endif
     for (int blk = j; blk < nblocks; blk += GB, ++it) {
 #ifdef PGASR_TIMING
@@ -1420,59 +1489,112 @@ __device__ __forceinline__ void ctc_bworker(int j, float* tile, int RS, int Tb, 
         const bool valid = lane < nf;
         const int q = q0 + min(lane, nf - 1);
         const int t = kAlpha ? n_first + q : Tb - 1 - n_first - q;
+        const int tlo = kAlpha ? n_first + q0 : Tb - 1 - n_first - q0 - (nf - 1);
         const unsigned prow = (unsigned)__cvta_generic_to_shared(tile + (size_t)t * RS);
-        int tot = 0;
-        int i0 = lds_s32(eo_s);
-        for (int v = 0; v < V; ++v) {
-            const int i1 = lds_s32(eo_s + 4u * (unsigned)(v + 1));
-            int a0 = 0, a1 = 0;
-            for (int i = i0; i < i1; i += 2) {
-                unsigned ex, ey;
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(ex), "=r"(ey) : "r"(el_s + 4u * (unsigned)i) : "memory");
-                a0 += lds_s32(ex ^ fx);
-                a1 += lds_s32(ey ^ fx);
+        const float gmul = dead ? 0.0f : gs30;
+        // ---- class totals: a running integer sum over the class-ordered list; where an entry ends its class the
+        // total (difference of two running sums) replaces that entry's occupancy in the matrix (nobody reads it again)
+        int acc = 0, last = 0;
+        unsigned E[3][8];
+        int X[3][8];
+        auto ld_list = [&](unsigned (&e)[8], unsigned addr) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]) : "r"(addr));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7]) : "r"(addr + 16u));
+        };
+        auto ld_occ = [&](int (&x)[8], const unsigned (&e)[8]) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(x[u]) : "r"((e[u] & ~kBwEnd) ^ fx));
+        };
+        auto sum8 = [&](const int (&x)[8], const unsigned (&e)[8]) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                acc += x[u];
+                const bool end = (int)e[u] < 0;
+                if (end) asm volatile("st.shared.s32 [%0], %1;\n" ::"r"((e[u] & ~kBwEnd) ^ fx), "r"(acc - last));
+                last = end ? acc : last;
             }
-            i0 = i1;
-            const int occ = a0 + a1;
-            tot += occ;
-            if (v != blank) {
-                const unsigned pa = prow + 4u * (unsigned)v;
-                const int pfix = __float2int_rn(lds_f32_v(pa) * (float)kCtcFix);
-                const float gval = dead ? 0.0f : (float)(pfix - occ) * gs30;
-                if (valid) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(pa), "f"(gval) : "memory");
-            }
+        };
+        ld_list(E[0], el_s);
+        ld_list(E[1], el_s + 32u);
+        ld_occ(X[0], E[0]);
+#ifdef PGASR_TIMING
+        asm volatile("" :: "r"(X[0][7]) : "memory");
+        const long long ca = clock64();
+#endif
+        unsigned la = el_s + 64u;
+        for (int g = 0; g < ntrips; ++g, la += 96u) {
+            ld_occ(X[1], E[1]); ld_list(E[2], la);       sum8(X[0], E[0]);
+            ld_occ(X[2], E[2]); ld_list(E[0], la + 32u); sum8(X[1], E[1]);
+            ld_occ(X[0], E[0]); ld_list(E[1], la + 64u); sum8(X[2], E[2]);
         }
-        {   // the blank column: sum_s gamma_t(s) = 1
-            const unsigned pa = prow + 4u * (unsigned)blank;
-            const int pfix = __float2int_rn(lds_f32_v(pa) * (float)kCtcFix);
-            const float gval = dead ? 0.0f : (float)(pfix - ((1 << 30) - tot)) * gs30;
-            if (valid) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(pa), "f"(gval) : "memory");
-        }
+#ifdef PGASR_TIMING
+        asm volatile("" :: "r"(acc) : "memory");
+        const long long cb = clock64();
+        tPre += ca - c1; tLoop += cb - ca; ++nBlk;
+#endif
+        // ---- the block's gradient rows, packed [frame][V] in this worker's staging buffer (= their layout in dlogits),
+        // eight classes at a time: all loads of a batch first (the compiler keeps asm memory operations in source order,
+        // so the batching has to be written out).  The previous block's bulk copy must have READ the buffer first.
+        if (it > 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) sts_release_s32(done + j, it + 1);              // the matrix buffer may be refilled
+        const int row = kAlpha ? lane : nf - 1 - lane;   // this lane's frame within the block's rows, ascending in t
+        const unsigned srow = st_s + 4u * (unsigned)(max(row, 0) * V);
+        for (int v0 = 0; v0 < V; v0 += 8) {
+            unsigned cl[8];
+            ld_list(cl, cl_s + 4u * (unsigned)v0);
+            const unsigned pa = prow + 4u * (unsigned)v0;
+            int occ[8];
+            float pv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(occ[u]) : "r"(cl[u] ^ fx));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)                   // (beyond V: the row's zero slot, in bounds)
+                asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(pv[u]) : "r"(pa + 4u * (unsigned)min(u, V - v0)));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int oc = v0 + u == blank ? (1 << 30) - acc : occ[u];   // the blank column: sum_s gamma_t(s) = 1
+                const int pfix = __float2int_rn(pv[u] * (float)kCtcFix);
+                const float gval = (float)(pfix - oc) * gmul;
+                if (valid && v0 + u < V)
+                    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(srow + 4u * (unsigned)(v0 + u)), "f"(gval) : "memory");
+            }
+        }
+        // (the executing threads' shared-memory writes -> visible to the bulk-copy engine)
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(done + j);                          // the matrix buffer may be refilled
 #ifdef PGASR_TIMING
         const long long c2 = clock64();
         tRows += c2 - c1;
 #endif
-        // the block's rows are contiguous in dlogits: one coalesced copy
-        const int tlo = kAlpha ? n_first + q0 : Tb - 1 - n_first - q0 - (nf - 1);
+        // ---- one bulk copy: the block's rows are contiguous in dlogits
         float* const out = dlog_u + (size_t)tlo * V;
-        const float* const src = tile + (size_t)tlo * RS;
-        const int ne = nf * V;
-        for (int e = lane; e < ne; e += 32) {
-            const int r = (int)(((unsigned)e * M) >> 16);
-            out[e] = src[r * RS + (e - r * V)];
+        const unsigned bytes = (unsigned)(nf * V) * 4u;
+        if (((reinterpret_cast<uintptr_t>(out) | bytes) & 15u) == 0u) {
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                             ::"l"(out), "r"(st_s), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            }
+        } else {
+            for (int e = lane; e < nf * V; e += 32) out[e] = stage[e];
+            __syncwarp();
         }
-        __syncwarp();
 #ifdef PGASR_TIMING
         tCopy += clock64() - c2;
 #endif
     }
+    if (lane == 0) {                                      // the rows have to be in global memory before the CTA's flag
+        asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+    }
+    __syncwarp();
 #ifdef PGASR_TIMING
     if (dbg && lane == 0 && j == 0) {
         g_dbg[kAlpha ? 48 : 52] = tWait;
         g_dbg[kAlpha ? 49 : 53] = tRows;
         g_dbg[kAlpha ? 50 : 54] = tCopy;
+        if (kAlpha) { g_dbg[56] = tPre; g_dbg[57] = tLoop; g_dbg[58] = nBlk; g_dbg[59] = ntrips; }
     }
 #endif
 }

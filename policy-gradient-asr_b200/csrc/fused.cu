@@ -51,9 +51,8 @@ static size_t ctc_role_smem_bw(int T, int V, int spl) {
     const size_t tile = (((size_t)(T + 4) * RS * sizeof(float) + 15) & ~(size_t)15);
     const size_t ring = spl == 4 ? grad_ring_bytes<4, kBwNB>() : grad_ring_bytes<8, kBwNB>();
     const size_t gam = 2 * (spl == 4 ? bw_gam_bytes<4>() : bw_gam_bytes<8>());
-    const size_t align_slack = (size_t)16 * spl * 128;            // the matrices are aligned to their size by address
-    return tile + align_slack + 2 * ring + gam + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int) + 8 +
-           (size_t)(512 + V + 1 + 2 * kBwGB) * sizeof(int);
+    return tile + 128 /* matrix alignment */ + 2 * ring + gam + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int) + 16 +
+           (size_t)2 * kBwGB * kBwListWords * sizeof(unsigned) + (size_t)2 * kBwGB * 8 + (size_t)2 * kBwGB * bw_stage_bytes();
 }
 
 static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {

@@ -101,7 +101,7 @@ __device__ __forceinline__ int cdf_count32(const float (&c)[32], float tau) {
 // workers that do both; up to 8 states per lane, tile in shared memory, 512 threads.
 template <int SPL, int kThreads, bool kGT, bool kBW = false>
 __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last) {
-    static_assert(!kBW || (!kGT && SPL <= 8 && kThreads == 32 * (2 + 2 * (kBwGA + kBwGB))), "block workers: tile mode only");
+    static_assert(!kBW || (!kGT && SPL <= 8 && kThreads == 512 && kBwGA == 4 && kBwGB <= 3), "block workers: tile mode only");
     constexpr int G = (kThreads / 32 - 2) / 2;             // gradient workers per direction
     constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;      // frames of a batch per worker
     constexpr int kMidThreads = 32 * (2 + 2 * G);
@@ -134,11 +134,10 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     constexpr int kNB = kBW ? kBwNB : kBatchOf<SPL>;                    // frames per hand-off batch
     int* bw_gam = nullptr;
     if constexpr (kBW) {
-        // block workers: the four occupancy matrices come first, each aligned to its size BY ADDRESS (ctc_bworker folds
-        // the buffer base into its address xor)
-        constexpr unsigned kBuf = 16 * SPL * 128;
+        // block workers: the four occupancy matrices come first, 128-byte aligned BY ADDRESS (the frame-slot xor of the
+        // row workers stays inside a 128-byte row)
         const unsigned at = (unsigned)__cvta_generic_to_shared(p);
-        p += (kBuf - (at & (kBuf - 1))) & (kBuf - 1);
+        p += (128u - (at & 127u)) & 127u;
         bw_gam = reinterpret_cast<int*>(p);
     }
     unsigned char* const stage_base = p;
@@ -153,10 +152,11 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     int* cls_scr = cls_off + (V + 1);                                   // [V] counting-sort scratch
     int* cls_pos = cls_scr + V;                                         // [512]
     int* lab_s = cls_pos + 512;                                         // [512] the transcript
-    // block workers: class-ordered label list (8-byte aligned), CSR offsets, consumed-block counters
-    unsigned* bw_elist = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(lab_s + 512) + 7) & ~(uintptr_t)7);
-    int* bw_eoff = reinterpret_cast<int*>(bw_elist + 512);              // [V + 1] (the list holds at most L + V entries)
-    int* bw_done = bw_eoff + (V + 1);                                   // [2][kBwGB]
+    // block workers: one class-ordered label list per matrix buffer (16-byte aligned; bw_build_list), the buffers'
+    // "consumed" mbarriers, one staging buffer per row worker
+    unsigned* bw_lists = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(lab_s + 512) + 15) & ~(uintptr_t)15);
+    unsigned long long* bw_done = reinterpret_cast<unsigned long long*>(bw_lists + 2 * kBwGB * kBwListWords);   // [2][kBwGB]
+    float* bw_stage = reinterpret_cast<float*>(bw_done + 2 * kBwGB);    // [2][kBwGB][32 frames][32]
     // The transcript and the lengths may live in mapped HOST memory (pgasr_host_*: a PCIe round trip per dependent
     // access), so everything is fetched here in one go and the transcript is used from shared memory afterwards.
     for (int i = threadIdx.x; i < a.Lmax; i += kThreads) lab_s[i] = a.targets[(size_t)b * a.Lmax + i];
@@ -203,13 +203,20 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                     if (warp == 0) {
                         ctc_build_class_lists(lab_s, L, V, cls_off, cls_pos, cls_scr);
                         if constexpr (kBW) {
-                            bw_build_list<SPL>(cls_off, cls_pos, V, bw_elist, bw_eoff);
-                            if (threadIdx.x < 2 * kBwGB) bw_done[threadIdx.x] = 0;
+                            if (threadIdx.x < 2 * kBwGB) mbar_init(bw_done + threadIdx.x, 1);
                         }
                     }
                 }
                 cp_async_wait<0>();
                 __syncthreads();
+                if constexpr (kBW) {
+                    // the class lists are visible now: warp c writes the list of matrix buffer c (published by the
+                    // barrier at the end of this chunk)
+                    if (c0 == 0 && warp < 2 * kBwGB)
+                        bw_build_list<SPL>(cls_off, cls_pos, V, bw_lists + warp * kBwListWords,
+                                           reinterpret_cast<int*>(bw_lists + warp * kBwListWords + kBwInfoAt),
+                                           (unsigned)__cvta_generic_to_shared(bw_gam + warp * (16 * SPL * 32)));
+                }
                 for (int t = threadIdx.x; t < n; t += kThreads) {
                     // the row lives in registers in rotated order (slot k holds class (k + t) & 31): the order does
                     // not matter for the max and the sum, every load / exp / store is independent of the others
@@ -259,26 +266,29 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         };
         const int g = (warp - 2) >> 1;
         if constexpr (kBW) {
-            // even warps serve alpha, odd warps beta.  Of a direction's seven (g = 0..6) the row workers are g = 0 and
-            // g = 2 -- warps 2, 6 / 3, 7, i.e. scheduler partitions 2 and 3, away from the walkers on 0 and 1
+            // even warps serve alpha, odd warps beta; w = warp / 2 is the warp's number within its direction: 0 the
+            // walker, odd w the A-workers (scheduler partitions 2 / 3), even w the B-workers (the walker's partition)
             const bool al = !(warp & 1);
-            int* gam_d = bw_gam + (al ? 0 : 1) * (kBwGB * 16 * SPL * 32);
-            int* done_d = bw_done + (al ? 0 : kBwGB);
-            const int bar_g = al ? 10 : 12;
-            const int bj = g == 0 ? 0 : g == 2 ? 1 : -1;
-            const int ga = g == 1 ? 0 : g - 2;
+            const int w = warp >> 1;
+            const int dirx = al ? 0 : 1;
+            int* gam_d = bw_gam + dirx * (kBwGB * 16 * SPL * 32);
+            unsigned long long* done_d = bw_done + dirx * kBwGB;
+            const int bar_g = al ? 10 : 13;
+            const int bj = (!(w & 1) && w >= 2 && (w >> 1) - 1 < kBwGB) ? (w >> 1) - 1 : -1;
+            const int ga = (w & 1) ? (w >> 1) : -1;
+            const unsigned* list_w = bw_lists + (dirx * kBwGB + max(bj, 0)) * kBwListWords;
             if (warp == 0)
                 ctc_walk_tile<SPL, kBwGA, true, false, kBwNB>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid);
             else if (warp == 1)
                 ctc_walk_tile<SPL, kBwGA, false, false, kBwNB>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_b, mid);
-            else if (bj >= 0 && al)
-                ctc_bworker<SPL, true>(bj, tile, RS, Tb, V, a.blank, gs, dlog_u, ring_a.norm, gam_d, done_d, bar_g, bw_elist, bw_eoff, mid, b == 0);
             else if (bj >= 0)
-                ctc_bworker<SPL, false>(bj, tile, RS, Tb, V, a.blank, gs, dlog_u, ring_b.norm, gam_d, done_d, bar_g, bw_elist, bw_eoff, mid, b == 0);
-            else if (al)
-                ctc_aworker<SPL, true>(ga, Tb, L, lat_u, exp_u, ring_a, gam_d, done_d, bar_g, mid);
+                ctc_bworker<SPL>(al, bj, tile, RS, Tb, V, a.blank, gs, dlog_u, al ? ring_a.norm : ring_b.norm, done_d, bar_g,
+                                 list_w, reinterpret_cast<const int*>(list_w + kBwInfoAt),
+                                 bw_stage + (dirx * kBwGB + bj) * (kBwBlk * 32), mid, b == 0);
+            else if (ga >= 0)
+                ctc_aworker<SPL>(al, ga, Tb, L, lat_u, exp_u, al ? ring_a : ring_b, gam_d, done_d, bar_g, mid);
             else
-                ctc_aworker<SPL, false>(ga, Tb, L, lat_u, exp_u, ring_b, gam_d, done_d, bar_g, mid);
+                mid();                                     // a spare warp: it only takes part in the CTA-wide barriers
         } else
         if (warp == 0)
             ctc_walk_tile<SPL, G, true, kGT>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid, pring_a,

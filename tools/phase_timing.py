@@ -38,6 +38,7 @@ for mode, (wp, wc) in {"both": (1.0, 1.0), "ctc": (0.0, 1.0), "pg": (1.0, 0.0)}.
         print(f" alpha worker0: phaseA {d[25]}  phaseB {d[26]}")
         print(f" block workers: alpha A0 ring-wait {d[40]} buffer-wait {d[41]} busy {d[42]} | beta A0 {d[44]} {d[45]} {d[46]}")
         print(f"                alpha B0 block-wait {d[48]} rows {d[49]} copy-out {d[50]} | beta B0 {d[52]} {d[53]} {d[54]}")
+        print(f"                alpha B0 rows split: pre {d[56]} loop {d[57]} blocks {d[58]} trips/block {d[59]}")
     if wp:
         names = ["tile-load", "sample", "collapse", "myers", "advantages", "grad-tile", "flag-wait", "rmw-out"]
         print(" pg:  " + "  ".join(f"{n} {d[31+i]-d[30+i]}" for i, n in enumerate(names)) + f"  total {d[38]-d[30]}")
