@@ -296,8 +296,16 @@ def run_ours(args):
             done += c
 
     # ---- device-resident throughput ("value") --------------------------------------------------
+    # warm-up: at least W (>= 3) steps, and at least ~30 ms of them so that the SM clock has left its idle state before
+    # the timed region (a 20-step run is 1 ms of GPU time; the clocks line of the JSON shows what the timed region saw)
     warm = max(args.warmup, 3)
     run_steps(0, warm)
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.03:
+        run_steps(warm, pool)
+        torch.cuda.synchronize()
+        warm += pool
     D.barrier()
     sampler = ClockSampler(D.local)
     sampler.start()
@@ -409,7 +417,8 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "launch_path": "functional.pg_ctc_step per step (Python)" if args.python_loop else
-                           f"pgasr_pg_ctc_step_multi: one C-ABI call per {min(pool, args.steps)} steps",
+                           f"pgasr_pg_ctc_step_multi: one C-ABI call per {min(pool, args.steps)} steps; consecutive steps of a "
+                           "call overlap on two streams (independent batches, own workspace lane each)",
         }
         if cpu_ref:
             line["cpu_baseline_reference"] = cpu_ref

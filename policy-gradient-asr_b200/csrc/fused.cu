@@ -2,7 +2,7 @@
 // translation units (fused_spl4/8/16/32.cu, which instantiate fused_impl.cuh).
 #include <cstdlib>
 #include <mutex>
-#include <unordered_map>
+#include <map>
 
 #include "ctc_core.cuh"
 #include "fused_args.cuh"
@@ -17,17 +17,22 @@ int launch_fused_spl32(int mode, FusedArgs& a, size_t smem, cudaStream_t st);
 
 constexpr size_t kFusedSmemLimit = 220 * 1024;
 
-// The only host-side state of the library: which of a workspace's two control blocks its next step uses.  The entry
-// is dropped by pgasr_pg_ctc_step_workspace_init (which zeroes both blocks), so a recycled pointer starts afresh.
+// Host-side state of the library: which of a fused workspace's two control blocks its next step uses (ordered map:
+// pgasr_pg_ctc_step_workspace_init drops every entry inside the range it is given, so a recycled pointer starts
+// afresh).  A fused workspace seen for the first time gets its control blocks zeroed on the launching stream.
 static std::mutex g_parity_mu;
-static std::unordered_map<const void*, unsigned> g_parity;
-static unsigned workspace_parity(const void* ws) {
+static std::map<uintptr_t, unsigned> g_parity;
+static unsigned workspace_parity(const void* ws, bool* fresh) {
     std::lock_guard<std::mutex> lk(g_parity_mu);
-    return g_parity[ws]++ & 1u;
+    auto it = g_parity.find(reinterpret_cast<uintptr_t>(ws));
+    *fresh = it == g_parity.end();
+    if (*fresh) it = g_parity.emplace(reinterpret_cast<uintptr_t>(ws), 0u).first;
+    return it->second++ & 1u;
 }
-void fused_workspace_reset(const void* ws) {
+void fused_workspace_reset(const void* ws, size_t bytes) {
     std::lock_guard<std::mutex> lk(g_parity_mu);
-    g_parity.erase(ws);
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(ws);
+    g_parity.erase(g_parity.lower_bound(lo), g_parity.lower_bound(lo + (bytes ? bytes : 1)));
 }
 
 struct FusedWs { size_t ctrl, lat, exps, terms, nll, tile, total; };
@@ -123,7 +128,10 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
     // launch the CTAs of step n + 1 take their role tickets while step n is still running on its own block.  (Step
     // n + 2 is launched only after every CTA of step n + 1 has passed its grid-dependency wait, i.e. after step n
     // completed and re-armed the block.)  The parity lives on the host, per workspace.
-    a.ctrl = reinterpret_cast<unsigned*>(p) + (size_t)workspace_parity(workspace) * (4 + a.B);
+    bool fresh = false;
+    const unsigned parity = workspace_parity(workspace, &fresh);
+    if (fresh) PGASR_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.ctrl, st));
+    a.ctrl = reinterpret_cast<unsigned*>(p) + (size_t)parity * (4 + a.B);
     p += w.ctrl;
     a.lattice = reinterpret_cast<double*>(p);            p += w.lat;
     a.lat_exp = reinterpret_cast<int*>(p);               p += w.exps;

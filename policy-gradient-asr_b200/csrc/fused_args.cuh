@@ -26,6 +26,6 @@ size_t fused_workspace_bytes(int B, int T, int V, int K, int Lmax);
 // (armed once: the kernel re-arms it when it finishes)
 int fused_step(FusedArgs& a, void* workspace, cudaStream_t st);
 size_t align256(size_t x);
-void fused_workspace_reset(const void* workspace);      // forget the control-block parity kept for this pointer
+void fused_workspace_reset(const void* workspace, size_t bytes);   // forget the control-block parity of every fused workspace in the range
 
 }  // namespace pgasr

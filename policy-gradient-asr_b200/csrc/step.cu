@@ -1,5 +1,7 @@
 // The whole loss step behind one C-ABI call (upstream call site: criterion(model_out, t) followed by
 // loss.backward(), model.py:235-237), plus the small ABI utilities.
+#include <cstdlib>
+
 #include "fused_args.cuh"
 
 namespace pgasr {
@@ -98,25 +100,33 @@ extern "C" int pgasr_device_check(void) {
     return major == 10 ? PGASR_OK : PGASR_ERR_NO_DEVICE;
 }
 
-// layout: [fused-kernel workspace (control block first)][scratch of the stand-alone kernels]
-extern "C" size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax) {
+// layout of ONE lane: [fused-kernel workspace (control block first)][scratch of the stand-alone kernels]; the workspace
+// holds two lanes (pgasr_pg_ctc_step_multi runs consecutive steps on two streams, each with its own lane)
+namespace pgasr {
+static size_t step_lane_bytes(int B, int T, int V, int K, int Lmax) {
     if (B < 0 || T <= 0 || V <= 0 || K <= 0 || Lmax <= 0) return 0;
-    const size_t fused = pgasr::step_fused_capability(B, T, V, K, Lmax)
-                             ? pgasr::align256(pgasr::fused_workspace_bytes(B, T, V, K, Lmax)) : 0;
-    const pgasr::StepWorkspace w = pgasr::carve(nullptr, B, T, V, K, Lmax);
+    const size_t fused = step_fused_capability(B, T, V, K, Lmax) ? align256(fused_workspace_bytes(B, T, V, K, Lmax)) : 0;
+    const StepWorkspace w = carve(nullptr, B, T, V, K, Lmax);
     if (w.ctc_bytes == 0) return 0;
-    return fused + w.total;
+    return align256(fused + w.total);
+}
+}  // namespace pgasr
+
+extern "C" size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax) {
+    return 2 * pgasr::step_lane_bytes(B, T, V, K, Lmax);
 }
 
 extern "C" int pgasr_pg_ctc_step_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
     if (!workspace) return PGASR_ERR_INVALID_ARG;
-    // only the two control blocks at the front have to start at zero (2 * (4 + kFusedMaxB) words = 128 KB at most);
-    // the kernel re-arms its block after every step.  The host-side record of which block the next step uses is
-    // dropped with it, so a recycled pointer starts from block 0 again.
+    // The control blocks of a fused workspace have to start at zero; the kernel re-arms its block after every step.
+    // The first lane's blocks sit at the front (2 * (4 + kFusedMaxB) words = 128 KB at most) and are cleared here; any
+    // other fused workspace inside the range (the second lane, whose offset depends on the shape) is cleared on the
+    // launching stream the first time a step uses it -- which it will be again after this call, because the host-side
+    // records of every workspace in the range are dropped here (a recycled pointer therefore starts afresh).
     const size_t ctrl = (size_t)2 * (4 + pgasr::kFusedMaxB) * sizeof(unsigned);
     const size_t n = workspace_bytes < ctrl ? workspace_bytes : ctrl;
     PGASR_CUDA_TRY(cudaMemsetAsync(workspace, 0, n, pgasr::as_stream(stream)));
-    pgasr::fused_workspace_reset(workspace);
+    pgasr::fused_workspace_reset(workspace, workspace_bytes);
     return PGASR_OK;
 }
 
@@ -136,6 +146,7 @@ static int step_check(const StepParams& q, const void* workspace, size_t workspa
     const size_t need = pgasr_pg_ctc_step_workspace_bytes(q.B, q.T, q.V, q.K, q.Lmax);
     if (need == 0) return PGASR_ERR_UNSUPPORTED;
     if (workspace_bytes < need) return PGASR_ERR_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return PGASR_ERR_INVALID_ARG;
     return PGASR_OK;
 }
 
@@ -227,9 +238,35 @@ extern "C" int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, co
     return step_one(q, io, seed, workspace, as_stream(stream));
 }
 
+namespace pgasr {
+// The second stream of pgasr_pg_ctc_step_multi and the events that fork it from / join it to the caller's stream:
+// one set per host thread and device, created on first use (the only objects the library keeps besides the
+// control-block parity; they live as long as the thread).
+struct AuxLane { cudaStream_t stream; cudaEvent_t fork, join; bool ok; };
+static int aux_lane(AuxLane** out) {
+    static thread_local AuxLane lanes[64] = {};
+    int dev = 0;
+    PGASR_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return PGASR_ERR_UNSUPPORTED;
+    AuxLane& a = lanes[dev];
+    if (!a.ok) {
+        PGASR_CUDA_TRY(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+        PGASR_CUDA_TRY(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+        PGASR_CUDA_TRY(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+        a.ok = true;
+    }
+    *out = &a;
+    return PGASR_OK;
+}
+}  // namespace pgasr
+
 // n steps with one call: the per-step cost on the host is one cudaLaunchKernelEx, nothing else (no Python, no
-// allocation, no argument marshalling), and programmatic dependent launch overlaps each launch with the tail of the
-// step before it.
+// allocation, no argument marshalling).  The steps of one call are independent by contract (no step's output is
+// another step's input), so they alternate between the caller's stream and a second stream, each with its own lane
+// of the workspace: consecutive steps OVERLAP -- the CTAs of step n + 1 fill the SMs step n leaves idle (2B of 148
+// at the headline shape) and its tail -- while steps two apart stay ordered (same stream; programmatic dependent
+// launch overlaps their launch latency).  The second stream is forked from and joined back into `stream` with
+// events, so to the caller the call is ordered on `stream` like any other.  PGASR_NO_OVERLAP=1: one stream.
 extern "C" int pgasr_pg_ctc_step_multi(const pgasr_step_io* steps, int n_steps, uint64_t seed_base, int B, int T,
                                        int V, int K, int Lmax, int blank, int reward_mode, int baseline_mode,
                                        float baseline_value, float w_pg, float w_ctc, void* workspace,
@@ -239,9 +276,25 @@ extern "C" int pgasr_pg_ctc_step_multi(const pgasr_step_io* steps, int n_steps, 
     if (!steps || n_steps < 0) return PGASR_ERR_INVALID_ARG;
     int rc = step_check(q, workspace, workspace_bytes);
     if (rc) return rc;
-    for (int i = 0; i < n_steps; ++i) {
-        rc = step_one(q, steps[i], seed_base + steps[i].seed, workspace, as_stream(stream));
+    static const bool no_overlap = getenv("PGASR_NO_OVERLAP") != nullptr;
+    cudaStream_t s0 = as_stream(stream);
+    void* lane1 = reinterpret_cast<char*>(workspace) + step_lane_bytes(B, T, V, K, Lmax);
+    AuxLane* aux = nullptr;
+    const bool overlap = n_steps >= 2 && !no_overlap;
+    if (overlap) {
+        rc = aux_lane(&aux);
         if (rc) return rc;
+        PGASR_CUDA_TRY(cudaEventRecord(aux->fork, s0));
+        PGASR_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
     }
-    return PGASR_OK;
+    for (int i = 0; i < n_steps; ++i) {
+        const bool second = overlap && (i & 1);
+        rc = step_one(q, steps[i], seed_base + steps[i].seed, second ? lane1 : workspace, second ? aux->stream : s0);
+        if (rc) break;
+    }
+    if (overlap) {                                         // join, also after an error: the caller's stream stays the one order
+        PGASR_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
+        PGASR_CUDA_TRY(cudaStreamWaitEvent(s0, aux->join, 0));
+    }
+    return rc;
 }
