@@ -71,7 +71,9 @@ static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
 
 static size_t pg_role_smem(int T, int V, int K, int spl, int threads, bool stream) {
     const int Tp = (T + 15) & ~15, W = spl / 2;
-    size_t pg = (stream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15)) + (size_t)2 * K * Tp + (size_t)(V + 1) * W * 4 + 16;
+    const int Tp2 = (T / 2 + 16) & ~15;
+    size_t pg = (stream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15)) + (size_t)2 * K * Tp + (size_t)K * Tp2 +
+                (size_t)2 * (V + 1) * W * 4 + (size_t)((K + 7) & ~7) * (W * 32 + 2) * 2 + 16;
     pg += (size_t)(threads / 32) * kFusedMaxK * 8 + 3 * kFusedMaxK * 4 + 16;
     return pg;
 }

@@ -333,7 +333,11 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     size_t off = kStream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15);
     uint8_t* samples_s = smem_raw + off;            off += (size_t)K * Tp;            // [K][Tp]
     uint8_t* hyp_s = smem_raw + off;                off += (size_t)K * Tp;            // [K][Tp]
+    const int Tp2 = (T / 2 + 16) & ~15;
+    uint8_t* hrev_s = smem_raw + off;               off += (size_t)K * Tp2;           // [K][Tp2] second halves, reversed
     uint32_t* peq = reinterpret_cast<uint32_t*>(smem_raw + off); off += (size_t)(V + 1) * W * 4;
+    uint32_t* peq_r = reinterpret_cast<uint32_t*>(smem_raw + off); off += (size_t)(V + 1) * W * 4;   // reversed transcript
+    int16_t* fg_s = reinterpret_cast<int16_t*>(smem_raw + off);  off += (size_t)((K + 7) & ~7) * (W * 32 + 2) * 2;   // (idle groups of the last warp get their own scratch)
     off = (off + 15) & ~(size_t)15;
     double* warp_acc = reinterpret_cast<double*>(smem_raw + off); off += (size_t)kWarps * kFusedMaxK * 8;   // log-prob partial sums
     float* adv_s = reinterpret_cast<float*>(smem_raw + off);     off += kFusedMaxK * 4;
@@ -364,7 +368,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
         ref_r[q] = j < m ? ref[j] : -1;
     }
     for (int i = threadIdx.x; i < kWarps * kFusedMaxK; i += kThreads) warp_acc[i] = 0.0;
-    for (int i = threadIdx.x; i < (V + 1) * W; i += kThreads) peq[i] = 0u;
+    for (int i = threadIdx.x; i < (V + 1) * W; i += kThreads) { peq[i] = 0u; peq_r[i] = 0u; }
     cp_async_wait<0>();
     __syncthreads();
 
@@ -427,11 +431,19 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     for (int q = 0; q < 2; ++q) {
         const int j = threadIdx.x + q * kThreads;
         const uint32_t c = (uint32_t)ref_r[q];
-        if (j < m && c < (uint32_t)V) atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+        if (j < m && c < (uint32_t)V) {
+            atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+            const int jr = m - 1 - j;
+            atomicOr(&peq_r[c * W + (jr >> 5)], 1u << (jr & 31));
+        }
     }
     for (int j = threadIdx.x + 2 * kThreads; j < m; j += kThreads) {     // (Lmax > 2 * threads: never with Lmax <= 511)
         const uint32_t c = (uint32_t)ref[j];
-        if (c < (uint32_t)V) atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+        if (c < (uint32_t)V) {
+            atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+            const int jr = m - 1 - j;
+            atomicOr(&peq_r[c * W + (jr >> 5)], 1u << (jr & 31));
+        }
     }
     for (int k = warp; k < K; k += kWarps) {
         const uint8_t* in = samples_s + (size_t)k * Tp;
@@ -449,6 +461,9 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
             carry = __shfl_sync(kFull, x, 31);
         }
         if (lane == 0) hlen_s[k] = base;
+        __syncwarp();
+        uint8_t* orv = hrev_s + (size_t)k * Tp2;          // the edit distance meets in the middle: second half backwards
+        for (int i = lane; i < base / 2; i += 32) orv[i] = o[base - 1 - i];
     }
     __syncthreads();
 
@@ -458,13 +473,42 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     // instructions, and lanes of one warp share them; one sample per warp was measured 3.6x slower.  The words of a
     // sample are spread over P lanes that run one symbol apart, see myers_row_split)
     if constexpr (W >= 4) {
-        constexpr int P = 4;                              // lanes per sample (myers_row_split)
-        if (warp * 32 < K * P) {                          // whole warps: the lanes shuffle with a full mask
-            const int k = (int)threadIdx.x / P, p = (int)threadIdx.x % P;
+        // forward halves on the first nw warps, backward halves on the next nw (myers_core.cuh, "Meeting in the middle")
+        constexpr int P = 4;                              // lanes per sample
+        const int nw = (K * P + 31) / 32;
+        const bool bidir = 2 * nw <= kWarps;              // (K = 64 in the 256-thread variant: forward only, all of h)
+        uint32_t VPh[W / P], VNh[W / P];
+        int k = 0, p = 0, n = 0, n1 = 0;
+        if (warp < (bidir ? 2 : 1) * nw) {                // whole warps: the lanes shuffle with a full mask
+            const bool fwd = warp < nw;
+            const int tid = (int)threadIdx.x - (fwd ? 0 : nw * 32);
+            k = tid / P; p = tid % P;
             const int kc = min(k, K - 1);
-            const int n = k < K ? hlen_s[kc] : 0;
-            const int nmax = __reduce_max_sync(kFull, n);
-            const int d = myers_row_split<W, P>(hyp_s + (size_t)kc * Tp, n, peq, V, m, p, nmax);
+            n = k < K ? hlen_s[kc] : 0;
+            n1 = bidir ? myers_split_point(n) : n;
+            const int nsym = fwd ? n1 : n - n1;
+            const int nmax = __reduce_max_sync(kFull, nsym);
+            myers_half<W, P>(fwd ? hyp_s + (size_t)kc * Tp : hrev_s + (size_t)kc * Tp2, nsym, fwd ? peq : peq_r, V, p, nmax,
+                             VPh, VNh);
+            if (!fwd) myers_store_column<W, P>(VPh, VNh, n - n1, p, fg_s + (size_t)k * (W * 32 + 2));
+        }
+        __syncthreads();
+        if (warp < nw) {
+            int d;
+            if (bidir) {
+                d = myers_meet<W, P>(VPh, VNh, n1, m, p, fg_s + (size_t)k * (W * 32 + 2));
+            } else {                                      // dp[n, m] = n + sum_{j<m} (VP_j - VN_j)
+                d = 0;
+#pragma unroll
+                for (int w = 0; w < W / P; ++w) {
+                    const int lo = (p * (W / P) + w) * 32;
+                    const uint32_t msk = m >= lo + 32 ? 0xffffffffu : (m > lo ? (1u << (m - lo)) - 1u : 0u);
+                    d += __popc(VPh[w] & msk) - __popc(VNh[w] & msk);
+                }
+#pragma unroll
+                for (int o = 1; o < P; o <<= 1) d += __shfl_xor_sync(kFull, d, o);
+                d += n;
+            }
             if (k < K && p == 0) dist_s[k] = d;
         }
     } else {                                              // two words: one thread per sample is as fast (measured)

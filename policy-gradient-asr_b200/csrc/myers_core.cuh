@@ -221,4 +221,147 @@ __device__ __forceinline__ int myers_row_split(const uint8_t* __restrict__ h, in
     return n + d;
 }
 
+// One block of up to 8 hypothesis symbols (packed little endian in sy) on this lane's WL words of a P-lane group: the
+// body of myers_row_split's pipeline as a function, so that two independent streams can be interleaved in one thread.
+// cinw: the carry bits this lane receives (3 per symbol, see myers_row_split); returns the ones it passes on.
+template <int W, int WL, bool kWhole>
+__device__ __forceinline__ uint32_t myers_block8(uint32_t (&VP)[WL], uint32_t (&VN)[WL], uint32_t cinw, uint2 sy,
+                                                 const uint32_t* __restrict__ pq, uint32_t vmax, int nvalid) {
+    constexpr int BS = 8;
+    uint32_t eq[BS][WL];
+#pragma unroll
+    for (int q = 0; q < BS; ++q) {
+        const uint32_t c = min(((q < 4 ? sy.x : sy.y) >> (8 * (q & 3))) & 0xffu, vmax);
+        if constexpr (WL == 1) {
+            eq[q][0] = pq[c * W];
+        } else if constexpr (WL == 2) {
+            const uint2 e = *reinterpret_cast<const uint2*>(pq + c * W);
+            eq[q][0] = e.x; eq[q][1] = e.y;
+        } else {
+            const uint4 e = *reinterpret_cast<const uint4*>(pq + c * W);
+            eq[q][0] = e.x; eq[q][1] = e.y; eq[q][2] = e.z; eq[q][3] = e.w;
+        }
+    }
+    uint32_t coutw = 0u;
+#pragma unroll
+    for (int q = 0; q < BS; ++q) {
+        if (kWhole || q < nvalid) {
+            uint32_t D0[WL], HP[WL], HN[WL];
+            uint32_t carry = (cinw >> (3 * q)) & 1u;
+#pragma unroll
+            for (int w = 0; w < WL; ++w) {
+                const uint64_t sum = (uint64_t)(eq[q][w] & VP[w]) + VP[w] + carry;
+                carry = (uint32_t)(sum >> 32);
+                D0[w] = (((uint32_t)sum ^ VP[w]) | eq[q][w]) | VN[w];
+                HP[w] = VN[w] | ~(D0[w] | VP[w]);
+                HN[w] = D0[w] & VP[w];
+            }
+            coutw |= (carry | ((HP[WL - 1] >> 31) << 1) | ((HN[WL - 1] >> 31) << 2)) << (3 * q);
+#pragma unroll
+            for (int w = WL - 1; w >= 0; --w) {
+                const uint32_t hps = (HP[w] << 1) | (w ? HP[w - 1] >> 31 : (cinw >> (3 * q + 1)) & 1u);
+                const uint32_t hns = (HN[w] << 1) | (w ? HN[w - 1] >> 31 : (cinw >> (3 * q + 2)) & 1u);
+                VP[w] = hns | ~(D0[w] | hps);
+                VN[w] = hps & D0[w];
+            }
+        }
+    }
+    return coutw;
+}
+
+// Meeting in the middle: ED(ref[:m], h[:n]) = min_j ED(ref[:j], h[:n1]) + ED(ref[j:], h[n1:]).  The forward half
+// walks h[:n1] against the match table of the reference, the backward half walks the REVERSED second half
+// (hrev[i] = h[n-1-i], n - n1 symbols) against the table of the reversed reference; the two halves run in DIFFERENT
+// warps (the phase is bound by the integer pipe of the scheduler partition a warp sits on -- two interleaved chains in
+// one warp took exactly as long as one chain of twice the length, measured -- so the halves must sit on different
+// partitions), each as the block-skewed pipeline of myers_row_split.  The column of a half is its VP / VN vectors
+// (vertical differences): the backward warps write theirs out as prefix sums (G), and after a CTA barrier the forward
+// warps form theirs on the fly and take the minimum over the m + 1 meeting points.
+__host__ __device__ __forceinline__ int myers_split_point(int n) { return min(n, ((n + 1) / 2 + 7) & ~7); }
+
+// one half: nsym symbols of h (8-byte aligned, readable to the next multiple of 8) on this lane's WL words; the state
+// is left in VP / VN.  Call with all 32 lanes; nmax = the largest nsym of the warp.
+template <int W, int P>
+__device__ __forceinline__ void myers_half(const uint8_t* __restrict__ h, int nsym, const uint32_t* __restrict__ peq_any,
+                                           int vocab, int p, int nmax, uint32_t (&VP)[W / P], uint32_t (&VN)[W / P]) {
+    constexpr int WL = W / P;
+    constexpr int BS = 8;
+#pragma unroll
+    for (int w = 0; w < WL; ++w) { VP[w] = 0xffffffffu; VN[w] = 0u; }
+    const uint32_t vmax = (uint32_t)vocab;
+    const uint32_t* pq = peq_any + p * WL;
+    constexpr uint32_t kLow = 0x00492492u;
+    uint32_t cinw = kLow;
+    const int iters = (nmax + BS - 1) / BS + P - 1;
+    for (int it = 0; it < iters; ++it) {
+        const int i0 = (it - p) * BS;
+        uint32_t coutw = 0u;
+        if (i0 >= 0 && i0 < nsym) {
+            const uint2 sy = *reinterpret_cast<const uint2*>(h + i0);
+            if (i0 + BS <= nsym) coutw = myers_block8<W, WL, true>(VP, VN, cinw, sy, pq, vmax, BS);
+            else coutw = myers_block8<W, WL, false>(VP, VN, cinw, sy, pq, vmax, nsym - i0);
+        }
+        cinw = __shfl_up_sync(kFull, coutw, 1);
+        cinw = p == 0 ? kLow : cinw;
+    }
+}
+
+// backward warps: G[j] = ED(rev ref[:j], rev h second half) = n2 + sum_{i<j} (VP_i - VN_i), j = 0 .. W*32, as int16
+template <int W, int P>
+__device__ __forceinline__ void myers_store_column(const uint32_t (&VP)[W / P], const uint32_t (&VN)[W / P], int n2, int p,
+                                                   int16_t* __restrict__ G) {
+    constexpr int WL = W / P;
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < WL; ++w) tot += __popc(VP[w]) - __popc(VN[w]);
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < P; o <<= 1) {
+        const int x = __shfl_up_sync(kFull, incl, o);
+        if (p >= o) incl += x;
+    }
+    int base = n2 + incl - tot;
+    if (p == 0) G[0] = (int16_t)n2;
+#pragma unroll
+    for (int w = 0; w < WL; ++w) {
+        const int j0 = (p * WL + w) * 32;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            base += (int)((VP[w] >> i) & 1u) - (int)((VN[w] >> i) & 1u);
+            G[j0 + i + 1] = (int16_t)base;
+        }
+    }
+}
+
+// forward warps, after the barrier: min_j F[j] + G[m - j]; every lane of a group returns the distance
+template <int W, int P>
+__device__ __forceinline__ int myers_meet(const uint32_t (&VP)[W / P], const uint32_t (&VN)[W / P], int n1, int m, int p,
+                                          const int16_t* __restrict__ G) {
+    constexpr int WL = W / P;
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < WL; ++w) tot += __popc(VP[w]) - __popc(VN[w]);
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < P; o <<= 1) {
+        const int x = __shfl_up_sync(kFull, incl, o);
+        if (p >= o) incl += x;
+    }
+    int base = n1 + incl - tot;
+    int best = p == 0 ? n1 + (int)G[m] : 1 << 20;          // j = 0
+#pragma unroll
+    for (int w = 0; w < WL; ++w) {
+        const int j0 = (p * WL + w) * 32;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            base += (int)((VP[w] >> i) & 1u) - (int)((VN[w] >> i) & 1u);      // F[j0 + i + 1]
+            const int j = j0 + i + 1;
+            if (j <= m) best = min(best, base + (int)G[m - j]);
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < P; o <<= 1) best = min(best, __shfl_xor_sync(kFull, best, o));
+    return best;
+}
+
 }  // namespace pgasr
