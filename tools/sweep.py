@@ -90,6 +90,11 @@ def merge_measured_traffic(cases, path):
 
 
 if __name__ == "__main__":
+    if "--one" in sys.argv:                           # one case, few repetitions: the driver of tools/sweep_ncu.py
+        i = sys.argv.index("--one")
+        B, T, V, K, L = (int(x) for x in sys.argv[i + 1:i + 6])
+        case(B, T, V, K, L, reps=1, quiet=True)
+        sys.exit(0)
     quick = "--quick" in sys.argv
     case(128, 1000, 30, 16, 200)                      # configs[2] shape (CTC alone: the K5 line)
     case(64, 500, 30, 16, 100)                        # configs[1] shape, kernel by kernel
