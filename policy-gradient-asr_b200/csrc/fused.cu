@@ -69,12 +69,14 @@ static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
     return tile + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int);
 }
 
-static size_t pg_role_smem(int T, int V, int K, int spl, int threads, bool stream) {
+static size_t pg_role_smem(int T, int V, int K, int spl, int threads, bool stream, bool togo = false) {
     const int Tp = (T + 15) & ~15, W = spl / 2;
     const int Tp2 = (T / 2 + 16) & ~15;
     size_t pg = (stream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15)) + (size_t)2 * K * Tp + (size_t)K * Tp2 +
                 (size_t)2 * (V + 1) * W * 4 + (size_t)((K + 7) & ~7) * (W * 32 + 2) * 2 + 16;
-    pg += (size_t)(threads / 32) * kFusedMaxK * 8 + 3 * kFusedMaxK * 4 + 16;
+    pg += (size_t)(threads / 32) * kFusedMaxK * 8 + 3 * kFusedMaxK * 4 + 16 + 16;
+    // reward-to-go: log-sum-exp per frame, chunk counters, the last column / reward-to-go of every sample (int16)
+    if (togo) pg += (size_t)Tp * 4 + (size_t)(threads / 32) * 64 * 4 + (size_t)K * (Tp + 16) * 2;
     return pg;
 }
 
@@ -86,7 +88,7 @@ static FusedPlan fused_plan(int T, int V, int K, int Lmax) {
     pl.spl = ctc_spl(Lmax);
     pl.threads = pl.spl >= 32 ? 256 : 512;             // 32 states per lane need the 255-register budget
     pl.ctc_ok = pl.gt = pl.pg_ok = pl.stream = pl.bw = false;
-    if (pl.spl == 0 || V > 32 || K > kFusedMaxK) return pl;
+    if (pl.spl == 0 || V > kMaxV || K > kFusedMaxK) return pl;
     // each role keeps its [T][..] tile in shared memory when it fits one SM, else it streams; the streaming PG role
     // is only instantiated next to the streaming CTC role, so a PG role that has to stream makes the CTC role stream
     const bool ctc_tile = ctc_role_smem(T, V, pl.spl, pl.threads, false) <= kFusedSmemLimit;
@@ -98,7 +100,7 @@ static FusedPlan fused_plan(int T, int V, int K, int Lmax) {
         pl.pg_ok = pg_tile;
         // block workers when their (larger) shared-memory layout fits too; PGASR_NO_BW=1 keeps the round-1 workers (A/B)
         static const bool no_bw = getenv("PGASR_NO_BW") != nullptr;
-        pl.bw = !no_bw && pl.spl <= 8 && pl.threads == 512 && ctc_role_smem_bw(T, V, pl.spl) <= kFusedSmemLimit;
+        pl.bw = !no_bw && V <= 32 && pl.spl <= 8 && pl.threads == 512 && ctc_role_smem_bw(T, V, pl.spl) <= kFusedSmemLimit;
     } else if (ctc_gt) {
         pl.ctc_ok = pl.gt = true;
         if (pg_tile) pl.pg_ok = true;
@@ -142,7 +144,13 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
     a.tile_g = pl.gt ? reinterpret_cast<float*>(p) : nullptr;
     size_t smem = !a.do_ctc ? 0 : pl.bw ? ctc_role_smem_bw(a.T, a.V, pl.spl) : ctc_role_smem(a.T, a.V, pl.spl, pl.threads, pl.gt);
     const bool stream = a.do_pg && pl.stream;
-    if (a.do_pg) smem = smem > pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream) ? smem : pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream);
+    const bool togo = a.do_pg && a.reward_mode == PGASR_REWARD_ED_TO_GO;
+    if (togo && stream) return PGASR_ERR_UNSUPPORTED;      // (reward-to-go needs the logits tile in shared memory)
+    if (a.do_pg) {
+        const size_t pg = pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream, togo);
+        if (pg > kFusedSmemLimit) return PGASR_ERR_UNSUPPORTED;
+        smem = smem > pg ? smem : pg;
+    }
     const int mode = pl.bw ? 3 : !pl.gt ? 0 : !stream ? 1 : 2;   // tiles in shared memory | CTC streams | both stream | block workers
     switch (pl.spl) {
         case 4: return launch_fused_spl4(mode, a, smem, st);

@@ -17,6 +17,7 @@
 // dlogits is written once by the CTC role and updated once by the PG role; every sum is order independent or
 // fixed-order, so the step is bit-reproducible run to run.
 #include <cstdlib>
+#include <type_traits>
 
 #include "ctc_core.cuh"
 #include "fused_args.cuh"
@@ -217,6 +218,19 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                                            reinterpret_cast<int*>(bw_lists + warp * kBwListWords + kBwInfoAt),
                                            (unsigned)__cvta_generic_to_shared(bw_gam + warp * (16 * SPL * 32)));
                 }
+                if (V > 32) {
+                    // wide alphabets (33..64 classes): three plain passes over the staged row, no register-resident row
+                    for (int t = threadIdx.x; t < n; t += kThreads) {
+                        const float* zr = stage + (size_t)t * V;
+                        float* orow = tile + (size_t)(c0 + t) * RS;
+                        float m = -INFINITY, s = 0.0f;
+                        for (int v = 0; v < V; ++v) m = fmaxf(m, zr[v]);
+                        for (int v = 0; v < V; ++v) s += __expf(zr[v] - m);
+                        const float inv = 1.0f / s;
+                        for (int v = 0; v < V; ++v) orow[v] = __expf(zr[v] - m) * inv;
+                        for (int v = V; v < RS; ++v) orow[v] = 0.0f;
+                    }
+                } else
                 for (int t = threadIdx.x; t < n; t += kThreads) {
                     // the row lives in registers in rotated order (slot k holds class (k + t) & 31): the order does
                     // not matter for the max and the sum, every load / exp / store is independent of the others
@@ -319,7 +333,6 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
 template <int W, int kThreads, bool kStream>
 __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last) {
     constexpr int kWarps = kThreads / 32;
-    constexpr int VP = 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = a.T, V = a.V, K = a.K;
     const int Tp = (T + 15) & ~15;
@@ -343,7 +356,14 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     float* adv_s = reinterpret_cast<float*>(smem_raw + off);     off += kFusedMaxK * 4;
     int* hlen_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
     int* dist_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
-    float* misc_s = reinterpret_cast<float*>(smem_raw + off);    // [0] sum of advantages
+    float* misc_s = reinterpret_cast<float*>(smem_raw + off);    off += 16;          // [0] sum of advantages
+    // reward-to-go mode: log-sum-exp of every frame (P1 -> P5) and, per sample, the last column of the edit-distance
+    // table c[i] = ED(ref, hyp[:i]) (int16, i = 0..n), later overwritten in place by the reward-to-go of every frame
+    const bool togo = a.reward_mode == PGASR_REWARD_ED_TO_GO;
+    const int Tc = Tp + 16;
+    float* lz_s = reinterpret_cast<float*>(smem_raw + off);      if (togo) off += (size_t)Tp * 4;
+    int* warp_acc_i = reinterpret_cast<int*>(smem_raw + off);    if (togo) off += (size_t)kWarps * 64 * 4;   // emitted symbols before each 32-frame chunk
+    int16_t* col_s = reinterpret_cast<int16_t*>(smem_raw + off); // [K][Tc]
 
     const bool dbg = b == 0 && threadIdx.x == 0;
     PGASR_STAMP(dbg, 30);
@@ -379,49 +399,66 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
         const int t = t0 + threadIdx.x;
         const bool live = t < Tb;
         const float* z = (kStream ? lg : ztile) + (size_t)(live ? t : 0) * V;
-        float cdf[VP];
-        float mx = -INFINITY, S = 0.0f, logS = 0.0f;
-        if (live) {
-#pragma unroll
-            for (int v = 0; v < VP; ++v) cdf[v] = v < V ? z[v] : -INFINITY;
-#pragma unroll
-            for (int v = 0; v < VP; ++v) mx = fmaxf(mx, cdf[v]);
-            float c = 0.0f;
-#pragma unroll
-            for (int v = 0; v < VP; ++v) {
-                if (v < V) c = __fadd_rn(c, exp_spec(__fsub_rn(cdf[v], mx)));
-                cdf[v] = c;
-            }
-            S = c;
-            logS = logf(S);
-        }
-        uint4 rnd = make_uint4(0, 0, 0, 0);
-        for (int k = 0; k < K; ++k) {
-            float term = 0.0f;
-            int pi = 0;
+        // one code path per alphabet width: the CDF lives in 32 registers (V <= 32, the common case) or in 64
+        auto sample_frame = [&](auto vp_tag) {
+            constexpr int VPW = decltype(vp_tag)::value;
+            float cdf[VPW];
+            float mx = -INFINITY, S = 0.0f, logS = 0.0f;
             if (live) {
-                float u;
-                if (a.uniforms) {
-                    u = __ldg(a.uniforms + ((size_t)b * K + k) * T + t);
-                } else {
-                    if ((k & 3) == 0)
-                        rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k >> 2), 0x50474153u), key);
-                    const uint32_t x = (k & 3) == 0 ? rnd.x : (k & 3) == 1 ? rnd.y : (k & 3) == 2 ? rnd.z : rnd.w;
-                    u = u32_to_uniform(x);
+#pragma unroll
+                for (int v = 0; v < VPW; ++v) cdf[v] = v < V ? z[v] : -INFINITY;
+#pragma unroll
+                for (int v = 0; v < VPW; ++v) mx = fmaxf(mx, cdf[v]);
+                float c = 0.0f;
+#pragma unroll
+                for (int v = 0; v < VPW; ++v) {
+                    if (v < V) c = __fadd_rn(c, exp_spec(__fsub_rn(cdf[v], mx)));
+                    cdf[v] = c;
                 }
-                const float tau = __fmul_rn(u, S);
-                // (entries V..31 of cdf[] repeat S, so the count over all 32 entries differs from the spec's count
-                // over V entries only when tau == S, where both clamp to V - 1)
-                pi = min(cdf_count32(cdf, tau), V - 1);
-                term = (z[pi] - mx) - logS;
+                S = c;
+                logS = logf(S);
+                if (togo) lz_s[t] = mx + logS;
             }
-            if (t < T) {
-                samples_s[(size_t)k * Tp + t] = (uint8_t)pi;
-                if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi;
+            uint4 rnd = make_uint4(0, 0, 0, 0);
+            for (int k = 0; k < K; ++k) {
+                float term = 0.0f;
+                int pi = 0;
+                if (live) {
+                    float u;
+                    if (a.uniforms) {
+                        u = __ldg(a.uniforms + ((size_t)b * K + k) * T + t);
+                    } else {
+                        if ((k & 3) == 0)
+                            rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k >> 2), 0x50474153u), key);
+                        const uint32_t x = (k & 3) == 0 ? rnd.x : (k & 3) == 1 ? rnd.y : (k & 3) == 2 ? rnd.z : rnd.w;
+                        u = u32_to_uniform(x);
+                    }
+                    const float tau = __fmul_rn(u, S);
+                    // (entries V.. of cdf[] repeat S, so the count over all entries differs from the spec's count
+                    // over V entries only when tau == S, where both clamp to V - 1)
+                    int cnt;
+                    if constexpr (VPW == 32) {
+                        cnt = cdf_count32(cdf, tau);
+                    } else {
+                        const bool hi = cdf[31] <= tau;           // the CDF is non-decreasing: pick the half, search it
+                        float half[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) half[i] = hi ? cdf[32 + i] : cdf[i];
+                        cnt = (hi ? 32 : 0) + cdf_count32(half, tau);
+                    }
+                    pi = min(cnt, V - 1);
+                    term = (z[pi] - mx) - logS;
+                }
+                if (t < T) {
+                    samples_s[(size_t)k * Tp + t] = (uint8_t)pi;
+                    if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi;
+                }
+                term = warp_sum(term);
+                if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)term;   // across passes and warps in fp64: log p ~ -1000
             }
-            term = warp_sum(term);
-            if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)term;   // across passes and warps in fp64: log p ~ -1000
-        }
+        };
+        if (V <= 32) sample_frame(std::integral_constant<int, 32>{});
+        else sample_frame(std::integral_constant<int, 64>{});
     }
     __syncthreads();
 
@@ -468,6 +505,57 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     __syncthreads();
 
     PGASR_STAMP(dbg, 33);
+    // ---- P3 (reward-to-go): one thread per sample, the whole last column; then one warp per sample turns it into the
+    // per-position rewards (output) and, in place, into the reward-to-go of every frame ----------------------------
+    if (togo) {
+        if ((int)threadIdx.x < K) {
+            const int k = threadIdx.x;
+            dist_s[k] = myers_row<W, true, int16_t>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, col_s + (size_t)k * Tc);
+        }
+        __syncthreads();
+        for (int k = warp; k < K; k += kWarps) {
+            int16_t* c = col_s + (size_t)k * Tc;
+            const int n = hlen_s[k];
+            const int cn = c[n];
+            if (a.r_pos) {                                 // r_i = -(c[i+1] - c[i]), zero beyond the hypothesis
+                int8_t* rp = a.r_pos + ((size_t)b * K + k) * T;
+                for (int i = lane; i < T; i += 32) rp[i] = i < n ? (int8_t)(c[i] - c[i + 1]) : (int8_t)0;
+            }
+            __syncwarp();
+            // G_t = c[pos(t)] - c[n], pos(t) = symbols emitted at frames < t; frames from the end towards the start so
+            // that slot t can take G_t (every later read is at pos(t') <= t' < t)
+            const uint8_t* in = samples_s + (size_t)k * Tp;
+            const int nch = (T + 31) / 32;
+            // emitted symbols before each chunk: one forward pass of ballots
+            int before = 0;
+            for (int ch = 0; ch < nch; ++ch) {
+                const int t = ch * 32 + lane;
+                const int x = t < Tb ? (int)in[t] : -2;
+                const int pv = t > 0 && t - 1 < Tb ? (int)in[t - 1] : -1;
+                const bool keep = t < Tb && x != pv && x != a.blank;
+                const unsigned mask = __ballot_sync(kFull, keep);
+                if (lane == 0) warp_acc_i[warp * 64 + (ch & 63)] = before;   // (T <= 2048: at most 64 chunks)
+                before += __popc(mask);
+            }
+            __syncwarp();
+            for (int ch = nch - 1; ch >= 0; --ch) {
+                const int t = ch * 32 + lane;
+                const int x = t < Tb ? (int)in[t] : -2;
+                const int pv = t > 0 && t - 1 < Tb ? (int)in[t - 1] : -1;
+                const bool keep = t < Tb && x != pv && x != a.blank;
+                const unsigned mask = __ballot_sync(kFull, keep);
+                const int pos = warp_acc_i[warp * 64 + (ch & 63)] + __popc(mask & ((1u << lane) - 1u));
+                const int g = t < Tb ? (int)c[pos] - cn : 0;
+                __syncwarp();
+                if (t < T) {
+                    c[t] = (int16_t)g;
+                    if (a.to_go) a.to_go[((size_t)b * K + k) * T + t] = (int16_t)g;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    } else
     // ---- P3: edit distance, P lanes per sample ---------------------------------------------------
     // (all K samples in the lanes of as few warps as possible: a Myers step is a chain of dependent integer
     // instructions, and lanes of one warp share them; one sample per warp was measured 3.6x slower.  The words of a
@@ -514,7 +602,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     } else {                                              // two words: one thread per sample is as fast (measured)
         if ((int)threadIdx.x < K) {
             const int k = threadIdx.x;
-            dist_s[k] = myers_row<W, false>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, nullptr);
+            dist_s[k] = myers_row<W, false>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, static_cast<int32_t*>(nullptr));
         }
     }
     __syncthreads();
@@ -528,6 +616,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
         for (int k = lane; k < K; k += 32) {
             float R = -(float)dist_s[k];
             if (a.reward_mode == PGASR_REWARD_NEG_CER) R = __fdiv_rn(R, (float)m);
+            if (togo) R = (float)(m - dist_s[k]);         // G_0 = c[0] - c[n]: what the whole hypothesis earned
             adv_s[k] = R;
             sumR += (double)R;
         }
@@ -555,7 +644,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
         }
         term = warp_sum(term);
         sumA = warp_sum(sumA);
-        if (lane == 0) {
+        if (lane == 0 && !togo) {                         // (reward-to-go: advantages are per frame, the loss term comes from P5)
             a.loss_terms[b] = (float)term;
             misc_s[0] = sumA;
         }
@@ -605,6 +694,52 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
         }
         PGASR_STAMP(dbg, 38);
     } else {
+    if (togo) {
+        // per-frame advantages A_kt = G_kt - b_kt (baseline over the K samples of the frame), the loss term
+        // -sum_kt A_kt log p_t(pi_kt) and the gradient row (1/BK) (p_tv sum_k A_kt - sum_k A_kt [pi_kt = v])
+        double lt = 0.0;
+        for (int t = threadIdx.x; t < T; t += kThreads) {
+            float* row = ztile + (size_t)t * V;
+            if (t < Tb) {
+                const float lz = lz_s[t];
+                int sumGi = 0;
+                for (int k = 0; k < K; ++k) sumGi += (int)col_s[(size_t)k * Tc + t];
+                const float sumG = (float)sumGi;
+                auto adv_of = [&](int k) {
+                    const float G = (float)col_s[(size_t)k * Tc + t];
+                    float base = 0.0f;
+                    if (a.baseline_mode == PGASR_BASELINE_MEAN) base = sumG / (float)K;
+                    else if (a.baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumG - G) / (float)(K - 1) : 0.0f;
+                    else if (a.baseline_mode == PGASR_BASELINE_VALUE) base = a.baseline_value;
+                    return G - base;
+                };
+                float sumA = 0.0f;
+                for (int k = 0; k < K; ++k) {
+                    const float A = adv_of(k);
+                    lt += -(double)A * (double)(row[samples_s[(size_t)k * Tp + t]] - lz);
+                    sumA += A;
+                }
+                if (dense) {
+                    const float sc = coef * sumA;
+                    for (int v = 0; v < V; ++v) row[v] = __expf(row[v] - lz) * sc;
+                } else {
+                    for (int v = 0; v < V; ++v) row[v] = 0.0f;
+                }
+                for (int k = 0; k < K; ++k) row[samples_s[(size_t)k * Tp + t]] -= coef * adv_of(k);
+            } else {
+                for (int v = 0; v < V; ++v) row[v] = 0.0f;
+            }
+        }
+        lt = warp_sum(lt);
+        __syncthreads();                                   // (warp_acc: the log-prob partial sums are consumed)
+        if (lane == 0) warp_acc[warp] = lt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < kWarps; ++w) tot += warp_acc[w];
+            a.loss_terms[b] = (float)tot;
+        }
+    } else
     for (int t = threadIdx.x; t < T; t += kThreads) {
         float* row = ztile + (size_t)t * V;
         if (t < Tb) {

@@ -87,7 +87,7 @@ extern "C" int pgasr_host_create(int B, int T, int V, int K, int Lmax, int depth
     if (!out || B <= 0 || T <= 0 || V <= 0 || K <= 0 || Lmax <= 0 || depth <= 0 || depth > 16)
         return PGASR_ERR_INVALID_ARG;
     *out = nullptr;
-    if (K > 64 || V > 32) return PGASR_ERR_UNSUPPORTED;
+    if (K > 64 || V > pgasr::kMaxV) return PGASR_ERR_UNSUPPORTED;
     const int dc = pgasr_device_check();
     if (dc != PGASR_OK) return dc;
     const size_t ws = pgasr_pg_ctc_step_workspace_bytes(B, T, V, K, Lmax);

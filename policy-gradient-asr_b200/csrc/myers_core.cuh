@@ -75,9 +75,9 @@ __device__ __forceinline__ int myers_step(MyersState<W>& s, const uint32_t (&eq)
 }
 
 // ED(ref[:m], h[:n]).  col (kLastCol) receives dp[i, m] for i = 0..n.  h may live in shared or global memory.
-template <int W, bool kLastCol>
+template <int W, bool kLastCol, typename ColT = int32_t>
 __device__ __forceinline__ int myers_row(const uint8_t* __restrict__ h, int n, const uint32_t* __restrict__ peq,
-                                         int vocab, int m, int32_t* __restrict__ col) {
+                                         int vocab, int m, ColT* __restrict__ col) {
     MyersState<W> s;
     uint32_t sel[W];
     const int wm = m > 0 ? (m - 1) >> 5 : 0;
@@ -89,7 +89,7 @@ __device__ __forceinline__ int myers_row(const uint8_t* __restrict__ h, int n, c
         sel[w] = (w == wm) ? bm : 0u;
     }
     int score = m;
-    if (kLastCol) col[0] = m;
+    if (kLastCol) col[0] = (ColT)m;
     const uint32_t vmax = (uint32_t)vocab;
     int i = 0;
     if ((reinterpret_cast<uintptr_t>(h) & 3u) == 0u) {    // four symbols per load, next word prefetched
@@ -105,7 +105,7 @@ __device__ __forceinline__ int myers_row(const uint8_t* __restrict__ h, int n, c
                 const int d = myers_step<W, kLastCol>(s, eq[q], sel);
                 if (kLastCol) {
                     score += d;
-                    col[i + q + 1] = m > 0 ? score : i + q + 1;
+                    col[i + q + 1] = (ColT)(m > 0 ? score : i + q + 1);
                 }
             }
             pack = nxt;
@@ -117,7 +117,7 @@ __device__ __forceinline__ int myers_row(const uint8_t* __restrict__ h, int n, c
         const int d = myers_step<W, kLastCol>(s, eq, sel);
         if (kLastCol) {
             score += d;
-            col[i + 1] = m > 0 ? score : i + 1;
+            col[i + 1] = (ColT)(m > 0 ? score : i + 1);
         }
     }
     // dp[n, m] = dp[n, 0] + sum_{j<m} (VP_j - VN_j)

@@ -103,10 +103,14 @@ extern "C" int pgasr_softmax_sample(const float* logits, const int32_t* in_len, 
                                     float* logp, float* probs, void* stream) {
     using namespace pgasr;
     if (!logits || !samples || !logp || B < 0 || T <= 0 || V <= 0 || K <= 0) return PGASR_ERR_INVALID_ARG;
-    if (V > 32 || K > kSamplerMaxK) return PGASR_ERR_UNSUPPORTED;
+    if (V > kMaxV || K > kSamplerMaxK) return PGASR_ERR_UNSUPPORTED;
     if (B == 0) return PGASR_OK;
-    softmax_sample_kernel<32><<<B, kSamplerThreads, 0, as_stream(stream)>>>(
-        logits, in_len, uniforms, seed, T, V, K, samples, logp, probs);
+    if (V <= 32)
+        softmax_sample_kernel<32><<<B, kSamplerThreads, 0, as_stream(stream)>>>(
+            logits, in_len, uniforms, seed, T, V, K, samples, logp, probs);
+    else
+        softmax_sample_kernel<64><<<B, kSamplerThreads, 0, as_stream(stream)>>>(
+            logits, in_len, uniforms, seed, T, V, K, samples, logp, probs);
     PGASR_LAUNCH_CHECK();
     return PGASR_OK;
 }

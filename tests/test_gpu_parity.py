@@ -879,3 +879,56 @@ def test_out_of_range_labels_and_targets_are_loud(cuda):
     assert abs(float(got) - float(want)) < 1e-5
     tgt[0, 0] = 6
     assert math.isnan(float(pgasr_b200.loss.customNLLLoss()(inp, tgt)))
+
+
+# ---------------------------------------------------------------- 8f.1 reward-to-go in the training step
+@pytest.mark.parametrize("B,T,V,K,L,baseline,ragged,wc", [
+    (3, 120, 30, 8, 20, "mean", True, 0.0), (2, 500, 30, 16, 100, "loo", False, 1.0), (4, 77, 5, 5, 9, "none", True, 0.7),
+    (2, 300, 17, 33, 40, "value", True, 0.0), (1, 64, 30, 4, 64, "mean", False, 1.0), (64, 500, 30, 16, 100, "mean", False, 1.0)])
+def test_step_reward_to_go(cuda, B, T, V, K, L, baseline, ragged, wc):
+    """reward='ed_to_go' (SURVEY 8f.1): r_pos and to_go bit-exact against the oracle (whose r_pos is pinned to upstream's
+    policy_grad.reward by tests/test_oracle.py), rewards exact, loss and gradient within 1e-4 -- in ONE launch."""
+    from pgasr_b200 import _native, functional as F
+    logits, targets, in_len, tgt_len, uni = make_batch(B, T, V, K, L, seed=B * 7 + T + K, ragged=ragged)
+    d = lambda a: dev_t(a, cuda)
+    kw = dict(uniforms=d(uni), reward="ed_to_go", baseline=baseline, baseline_value=1.25, pg_weight=1.0, ctc_weight=wc,
+              want=("rewards", "samples", "to_go", "r_pos", "nll", "dist", "hyp_len"))
+    out = F.pg_ctc_step(d(logits), d(targets), d(in_len), d(tgt_len), **kw)
+    n0 = _native.lib().pgasr_launch_count()
+    out = F.pg_ctc_step(d(logits), d(targets), d(in_len), d(tgt_len), workspace=out["workspace"], **kw)
+    assert _native.lib().pgasr_launch_count() - n0 == 1
+    samples = out["samples"].cpu().numpy()
+    s_ref, _ = cport.softmax_sample(logits, in_len, uni)
+    assert np.array_equal(samples, s_ref)
+    bm = F.BASELINE_MODES[baseline]
+    loss_pg, R, to_go, r_pos, g_pg = cport.pg_togo_loss_grad(logits, samples, targets, in_len, tgt_len,
+                                                             baseline_mode=bm, baseline_value=1.25)
+    assert np.array_equal(out["to_go"].cpu().numpy(), to_go)
+    assert np.array_equal(out["r_pos"].cpu().numpy(), r_pos)
+    assert np.array_equal(out["rewards"].cpu().numpy(), R)
+    want_loss, want_g = loss_pg, g_pg
+    if wc:
+        nll_ref, g_ctc = cport.ctc_loss_grad(logits, targets, in_len, tgt_len)
+        fin = np.isfinite(nll_ref)
+        g_ctc[~fin] = 0.0
+        want_g = g_pg + (wc / B) * g_ctc
+        want_loss = loss_pg + wc * nll_ref.mean()
+    got = out["dlogits"].cpu().numpy()
+    assert rel_err(got, want_g) < RTOL
+    assert grad_close(got, want_g)
+    if np.isfinite(want_loss):
+        # the terms of the PG loss cancel; judge the scalar against their size
+        scale = max(abs(want_loss), np.abs(to_go).mean() * 4.0)
+        assert abs(float(out["loss"]) - want_loss) <= RTOL * scale
+
+
+def test_step_reward_to_go_through_the_loss_module(cuda):
+    """PolicyGradCTCLoss(reward='ed_to_go') in the criterion(model_out, t) slot: autograd hands back the fused gradient."""
+    import pgasr_b200
+    B, T, V, K, L = 3, 90, 30, 8, 12
+    logits, targets, in_len, tgt_len, _ = make_batch(B, T, V, K, L, seed=5, ragged=True)
+    crit = pgasr_b200.PolicyGradCTCLoss(K=K, reward="ed_to_go", baseline="mean", seed=3)
+    x = dev_t(logits, cuda).requires_grad_(True)
+    loss = crit(x, dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda))
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(x.grad).all() and float(x.grad.abs().sum()) > 0

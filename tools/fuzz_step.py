@@ -25,7 +25,7 @@ for case in range(n_cases):
     B = int(rng.choice([1, 2, 3, 5]))
     if T * K * B * L > 4e8:
         K = 2
-    reward = str(rng.choice(["ed", "cer"]))
+    reward = str(rng.choice(["ed", "cer", "ed_to_go"], p=[0.4, 0.35, 0.25]))
     baseline = str(rng.choice(["mean", "loo", "none", "value"]))
     philox = bool(rng.integers(0, 2))
     regime = str(rng.choice(["random", "peaky"]))
@@ -33,8 +33,14 @@ for case in range(n_cases):
     lg, tg, il, tl, uni = make_batch(B, T, V, K, L, seed=int(rng.integers(0, 1 << 30)), ragged=True, regime=regime)
     kw = dict(reward_mode=F.REWARD_MODES[reward], baseline_mode=F.BASELINE_MODES[baseline], baseline_value=-1.5, w_pg=w_pg, w_ctc=w_ctc)
     loss_ref, R_ref, nll_ref, dl_ref = cport.pg_ctc_step(lg, tg, il, tl, None if philox else uni, seed=77, K=K, **kw)
-    out = F.pg_ctc_step(t(lg), t(tg), t(il), t(tl), K=K, reward=reward, baseline=baseline, baseline_value=-1.5,
-                        pg_weight=w_pg, ctc_weight=w_ctc, uniforms=None if philox else t(uni), seed=77, want=("rewards", "nll"))
+    try:
+        out = F.pg_ctc_step(t(lg), t(tg), t(il), t(tl), K=K, reward=reward, baseline=baseline, baseline_value=-1.5,
+                            pg_weight=w_pg, ctc_weight=w_ctc, uniforms=None if philox else t(uni), seed=77, want=("rewards", "nll"))
+    except Exception as e:                                 # reward-to-go lives in the single-launch kernel with the logits tile
+        if reward == "ed_to_go" and w_pg and "unsupported" in str(e).lower():
+            print(f"skip B={B} T={T} V={V} K={K} L={L} ed_to_go: shape outside the tile mode of the single-launch kernel")
+            continue
+        raise
     g = out["dlogits"].cpu().numpy()
     err = float(np.abs(g - dl_ref).max() / max(np.abs(dl_ref).max(), 1e-30))
     ok = err < 1e-4
@@ -48,7 +54,8 @@ for case in range(n_cases):
         fin = np.isfinite(nll_ref)
         ok = ok and np.array_equal(np.isfinite(nll), fin) and (not fin.any() or np.abs(nll[fin] / nll_ref[fin] - 1).max() < 1e-4)
     if np.isfinite(loss_ref):
-        ok = ok and abs(float(out["loss"]) - loss_ref) <= 1e-4 * abs(loss_ref) + 1e-5
+        # (reward-to-go: the loss is a sum of T K cancelling terms of size ~L log V; the advantages are fp32)
+        ok = ok and abs(float(out["loss"]) - loss_ref) <= 1e-4 * abs(loss_ref) + 1e-5 + (1e-6 * T * L if reward == "ed_to_go" else 0.0)
     worst = max(worst, err)
     print(f"{'ok  ' if ok else 'FAIL'} B={B} T={T} V={V} K={K} L={L} {reward}/{baseline} philox={philox} {regime} w=({w_pg},{w_ctc}) grad err {err:.2e}",
           flush=True)
