@@ -51,7 +51,7 @@ extern "C" {
 typedef enum {
     PGASR_OK = 0,
     PGASR_ERR_INVALID_ARG = -1,   /* NULL pointer, negative size, size over a documented limit */
-    PGASR_ERR_UNSUPPORTED = -2,   /* legal request this build has no kernel for (e.g. V > 32 sampler) */
+    PGASR_ERR_UNSUPPORTED = -2,   /* legal request this build has no kernel for (e.g. V > 64 sampler) */
     PGASR_ERR_NO_DEVICE = -3,     /* no CUDA device of compute capability 10.x */
     PGASR_ERR_WORKSPACE = -4,     /* workspace too small; ask pgasr_*_workspace_bytes */
     PGASR_ERR_CUDA = -5           /* a CUDA call failed; pgasr_last_cuda_error() has the code */
@@ -74,7 +74,7 @@ PGASR_API int         pgasr_device_check(void);             /* PGASR_OK iff the 
  * samples[b,k,t] ~ Categorical(softmax(logits[b,t,:])) for t < in_len[b] (0 beyond), from
  * uniforms[b,k,t] when given, else Philox4x32-10(seed; counter (t, b, k/4, 'PGAS'), lane k%4).
  * logp[b,k] = sum_t log_softmax(logits[b,t,:])[samples[b,k,t]].  probs (optional) receives the
- * softmax.  Bit-exact contract: DESIGN.md "sampler spec".  V <= 32, K <= 64.                   */
+ * softmax.  Bit-exact contract: DESIGN.md "sampler spec".  V <= 64, K <= 64.                   */
 PGASR_API int pgasr_softmax_sample(const float* logits, const int32_t* in_len, const float* uniforms,
                          uint64_t seed, int B, int T, int V, int K,
                          uint8_t* samples, float* logp, float* probs, void* stream);
@@ -114,7 +114,7 @@ PGASR_API int pgasr_pg_grad(const uint8_t* samples, const float* adv, const floa
  * nll[b] = -log p(targets[b] | logits[b]); dlogits (+)= grad_scale * d nll[b] / d logits[b].
  * probs: softmax of logits if the caller already has it (pgasr_softmax_sample), else NULL and the
  * kernel computes it into its workspace.  No valid alignment: nll = +inf, zero gradient.
- * With logits given, accumulate == 0 and V <= 32 this is the CTC role of the single-launch kernel below (walker and
+ * With logits given, accumulate == 0 and V <= 64 this is the CTC role of the single-launch kernel below (walker and
  * gradient-worker warps, any T); otherwise the classic one-CTA-per-utterance kernel.
  * Lmax <= 511.  workspace: pgasr_ctc_workspace_bytes(B,T,V,Lmax) bytes, 256-byte aligned.       */
 PGASR_API size_t pgasr_ctc_workspace_bytes(int B, int T, int V, int Lmax);
@@ -145,8 +145,8 @@ PGASR_API int pgasr_nll_sum_backward(const int64_t* target, const float* grad_ou
  * back-to-back steps on one stream overlap the launch of step n+1 with the tail of step n (the CTAs of n+1 wait on
  * the grid dependency before they touch any input or output); for that the workspace holds two control blocks that
  * consecutive calls use alternately -- the library remembers, per workspace pointer, which one is next (host side).
- * V <= 32, K <= 64.  One kernel launch for every shape whose sample
- * buffers fit an SM (2 K T <= ~215 KB); targets / in_len / tgt_len and the small outputs may live in pinned host
+ * V <= 64 (register-resident fast paths up to 32 classes), K <= 64.  One kernel launch for every shape whose sample
+ * buffers fit an SM (2.5 K T <= ~200 KB); targets / in_len / tgt_len and the small outputs may live in pinned host
  * memory mapped into the device (they are read once per CTA / written once).                       */
 PGASR_API size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax);
 /* (init also forgets which control block the workspace pointer used last, so a freed and recycled pointer is safe) */

@@ -64,7 +64,7 @@ static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
     const int RS = ctc_row_stride_f32(V);
     const size_t ring = spl == 4 ? grad_ring_bytes<4>() : spl == 8 ? grad_ring_bytes<8>() : spl == 16 ? grad_ring_bytes<16>() : grad_ring_bytes<32>();
     const int G = (threads / 32 - 2) / 2, per = (batch_of(spl) + G - 1) / G;
-    const size_t pring = (size_t)kPRows * (RS <= 32 ? 32 : 64) * 4;
+    const size_t pring = (size_t)kPRows * (RS <= 32 ? 32 : RS <= 64 ? 64 : 128) * 4;
     const size_t tile = gt ? 3 * pring /* two rings + alignment slack */ : (((size_t)(T + 4) * RS * sizeof(float) + 15) & ~(size_t)15);
     return tile + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int);
 }

@@ -114,7 +114,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     // shared-memory carve-up (see fused_smem)
     // [T][RS] between two pairs of guard rows: the walkers load the probabilities two frames ahead and run two rows
     // past either end (the guard values are loaded and never used)
-    const int RSR = RS <= 32 ? 32 : 64;                                  // ring row stride (power of two)
+    const int RSR = RS <= 32 ? 32 : RS <= 64 ? 64 : 128;                                  // ring row stride (power of two)
     const size_t pring_bytes = (size_t)kPRows * RSR * 4;
     float* tile;
     float* pring_a = nullptr;

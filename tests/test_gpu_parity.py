@@ -49,7 +49,8 @@ def enc(s):
 
 # ---------------------------------------------------------------- a6 sampler
 @pytest.mark.parametrize("B,T,V,K,ragged", [(3, 37, 30, 4, True), (2, 300, 5, 16, False), (64, 500, 30, 16, False),
-                                            (2, 700, 32, 7, True), (1, 1, 2, 1, False)])
+                                            (2, 700, 32, 7, True), (1, 1, 2, 1, False), (3, 90, 33, 5, True),
+                                            (2, 200, 64, 16, False), (2, 64, 47, 3, True)])
 def test_sampler_bit_exact_injected_uniforms(cuda, B, T, V, K, ragged):
     from pgasr_b200 import functional as F
     logits, _, in_len, _, uni = make_batch(B, T, V, K, max(T // 5, 1), seed=B + T, ragged=ragged)
@@ -454,7 +455,7 @@ def test_host_pipeline_rejects_bad_arguments(cuda):
     import pgasr_b200
     from pgasr_b200 import _native
     with pytest.raises(_native.PgasrError):
-        pgasr_b200.HostPipeline(4, 50, 40, 8, 10)             # V > 32: unsupported
+        pgasr_b200.HostPipeline(4, 50, 65, 8, 10)             # V > 64: unsupported
     with pgasr_b200.HostPipeline(2, 20, 30, 4, 5, depth=2) as pipe:
         with pytest.raises(TypeError):
             pipe.submit(torch.zeros(2, 20, 30, device=cuda), torch.zeros(2, 5, dtype=torch.int32))
@@ -613,9 +614,14 @@ def test_acoustic_harness_trains(cuda):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,T,V,K,L,philox", [(1, 33, 30, 1, 4, False), (2, 70, 9, 5, 11, True), (3, 65, 32, 7, 6, False),
-                                               (2, 500, 30, 64, 100, True), (5, 48, 3, 2, 47, False)])
+                                               (2, 500, 30, 64, 100, True), (5, 48, 3, 2, 47, False),
+                                               (3, 120, 33, 5, 20, False), (2, 500, 40, 16, 100, True), (2, 260, 64, 8, 70, False),
+                                               (1, 1300, 64, 4, 150, False), (2, 90, 47, 3, 200, True)])
 def test_step_odd_shapes(cuda, B, T, V, K, L, philox):
-    """K not a multiple of the Philox block, single utterance / single sample, V = 32 (row stride 34), tiny V."""
+    """K not a multiple of the Philox block, single utterance / single sample, V = 32 (row stride 34), tiny V, and
+    alphabets wider than 32 classes (33 / 40 / 47 / 64: upstream's alphabet is a character set plus punctuation,
+    model.py:195): samples bit-exact, gradients within 1e-4, also in the streaming modes (T = 1300) and with 16 CTC
+    states per lane (L = 150 / 200)."""
     step_case(cuda, B, T, V, K, L, seed=B + K, ragged=True, regime="random", philox=philox)
 
 

@@ -20,7 +20,7 @@ worst = 0.0
 for case in range(n_cases):
     L = int(rng.choice([1, 3, 20, 63, 64, 100, 127, 128, 200, 255, 256, 300, 400]))
     T = int(min(2500, max(L + int(rng.integers(0, 60)), int(rng.choice([L + 5, 2 * L + 9, 60, 333, 500, 801, 1000, 1777])))))
-    V = int(rng.choice([2, 5, 17, 30, 31, 32]))
+    V = int(rng.choice([2, 5, 17, 30, 31, 32, 33, 40, 64]))
     K = int(rng.choice([1, 2, 4, 7, 16, 33, 64]))
     B = int(rng.choice([1, 2, 3, 5]))
     if T * K * B * L > 4e8:
