@@ -33,6 +33,77 @@ __global__ void myers_u8_kernel(const uint8_t* __restrict__ hyps, const int32_t*
     dist[row] = myers_row<W, kLastCol>(hyps + (size_t)row * hyp_stride, n, peq, vocab, m, col);
 }
 
+// The same distance with the work of a row spread out (what the single-launch step does, fused_impl.cuh P3): the W
+// words of a row on 4 adjacent lanes as a block-skewed pipeline, and the hypothesis cut in two -- forward half on the
+// first warps, reversed second half on the others (myers_core.cuh, "Meeting in the middle").  One CTA per reference
+// group; the rows are staged in shared memory (8-byte aligned, second halves reversed).  Used when no last column is
+// asked for, W >= 4 and the group fits (rows_per_ref <= 64).
+template <int W>
+__global__ void myers_u8_split_kernel(const uint8_t* __restrict__ hyps, const int32_t* __restrict__ hyp_len,
+                                      int N, int hyp_stride, const int32_t* __restrict__ refs,
+                                      const int32_t* __restrict__ ref_len, int rows_per_ref, int ref_stride,
+                                      int vocab, int32_t* __restrict__ dist) {
+    constexpr int P = 4;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int K = rows_per_ref;
+    const int Tp = (hyp_stride + 15) & ~15, Tp2 = (hyp_stride / 2 + 16) & ~15;
+    uint32_t* peq = reinterpret_cast<uint32_t*>(sm_raw);                       // [vocab + 1][W]
+    uint32_t* peq_r = peq + (size_t)(vocab + 1) * W;                           // reversed reference
+    int16_t* fg = reinterpret_cast<int16_t*>(peq_r + (size_t)(vocab + 1) * W); // [(K + 7) & ~7][W * 32 + 2]
+    uint8_t* hf = reinterpret_cast<uint8_t*>(fg + (size_t)((K + 7) & ~7) * (W * 32 + 2));
+    hf += (16 - (reinterpret_cast<uintptr_t>(hf) & 15)) & 15;                  // [K][Tp]
+    uint8_t* hr = hf + (size_t)K * Tp;                                         // [K][Tp2]
+    const int g = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int m = ref_len ? ref_len[g] : ref_stride;
+    m = min(max(m, 0), ref_stride);
+    for (int i = threadIdx.x; i < 2 * (vocab + 1) * W; i += blockDim.x) peq[i] = 0u;
+    __syncthreads();
+    const int32_t* ref = refs + (size_t)g * ref_stride;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const uint32_t c = (uint32_t)ref[j];
+        if (c < (uint32_t)vocab) {
+            atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+            const int jr = m - 1 - j;
+            atomicOr(&peq_r[c * W + (jr >> 5)], 1u << (jr & 31));
+        }
+    }
+    for (int k = warp; k < K; k += blockDim.x / 32) {      // stage the rows: first part forwards, second half reversed
+        const int row = g * K + k;
+        int n = row < N ? hyp_len[row] : 0;
+        n = min(max(n, 0), hyp_stride);
+        const uint8_t* src = hyps + (size_t)min(row, N - 1) * hyp_stride;
+        const int n1 = myers_split_point(n);
+        for (int i = lane; i < n1; i += 32) hf[(size_t)k * Tp + i] = src[i];
+        for (int i = lane; i < n - n1; i += 32) hr[(size_t)k * Tp2 + i] = src[n - 1 - i];
+    }
+    __syncthreads();
+    const int nw = (K * P + 31) / 32;
+    uint32_t VPh[W / P], VNh[W / P];
+    const bool fwd = warp < nw;
+    const int tid = (int)threadIdx.x - (fwd ? 0 : nw * 32);
+    const int k = tid / P, p = tid % P;
+    const int kc = min(k, K - 1);
+    const int row = g * K + kc;
+    int n = (k < K && row < N) ? hyp_len[row] : 0;
+    n = min(max(n, 0), hyp_stride);
+    const int n1 = myers_split_point(n);
+    const int nsym = fwd ? n1 : n - n1;
+    const int nmax = __reduce_max_sync(kFull, nsym);
+    myers_half<W, P>(fwd ? hf + (size_t)kc * Tp : hr + (size_t)kc * Tp2, nsym, fwd ? peq : peq_r, vocab, p, nmax, VPh, VNh);
+    if (!fwd) myers_store_column<W, P>(VPh, VNh, n - n1, p, fg + (size_t)k * (W * 32 + 2));
+    __syncthreads();
+    if (fwd) {
+        const int d = myers_meet<W, P>(VPh, VNh, n1, m, p, fg + (size_t)k * (W * 32 + 2));
+        if (k < K && p == 0 && g * K + k < N) dist[g * K + k] = d;
+    }
+}
+
+static size_t myers_split_smem(int W, int K, int hyp_stride, int vocab) {
+    const int Tp = (hyp_stride + 15) & ~15, Tp2 = (hyp_stride / 2 + 16) & ~15;
+    return (size_t)2 * (vocab + 1) * W * 4 + (size_t)((K + 7) & ~7) * (W * 32 + 2) * 2 + 16 + (size_t)K * (Tp + Tp2);
+}
+
 // Anti-diagonal wavefront.  Cell (i, j), i over the hypothesis, j over the reference, sits on diagonal
 // i + j.  Three rotating diagonals of len(ref)+1 entries live in shared memory, indexed by j.
 __global__ void wavefront_i32_kernel(const int32_t* __restrict__ hyps, const int32_t* __restrict__ hyp_len,
@@ -84,6 +155,18 @@ static int launch_myers(const uint8_t* hyps, const int32_t* hyp_len, int N, int 
                         const int32_t* refs, const int32_t* ref_len, int rows_per_ref, int ref_stride,
                         int vocab, int32_t* dist, int32_t* last_col, cudaStream_t st) {
     const int groups = (N + rows_per_ref - 1) / rows_per_ref;
+    if constexpr (W >= 4) {
+        const size_t need = myers_split_smem(W, rows_per_ref, hyp_stride, vocab);
+        if (!last_col && rows_per_ref <= 64 && need <= 200 * 1024) {
+            if (need > 48 * 1024)
+                PGASR_CUDA_TRY(cudaFuncSetAttribute(myers_u8_split_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            const int nw = (rows_per_ref * 4 + 31) / 32;
+            myers_u8_split_kernel<W><<<groups, 2 * nw * 32, need, st>>>(hyps, hyp_len, N, hyp_stride, refs, ref_len, rows_per_ref,
+                                                                      ref_stride, vocab, dist);
+            PGASR_LAUNCH_CHECK();
+            return PGASR_OK;
+        }
+    }
     const int threads = ((rows_per_ref + 31) / 32) * 32;
     const size_t smem = (size_t)(vocab + 1) * W * sizeof(uint32_t);
     if (last_col)
