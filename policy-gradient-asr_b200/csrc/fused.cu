@@ -69,7 +69,8 @@ static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
     return tile + 2 * ring + (size_t)2 * G * per * 16 * spl * sizeof(int) + (size_t)(2 * V + 1 + 512 + 512) * sizeof(int);
 }
 
-static size_t pg_role_smem(int T, int V, int K, int spl, int threads, bool stream, bool togo = false) {
+static size_t pg_cdf_bytes(int threads) { return (size_t)threads * 33 * sizeof(float) + 16; }
+static size_t pg_role_smem(int T, int V, int K, int spl, int threads, bool stream, bool togo = false, bool cdf = false) {
     const int Tp = (T + 15) & ~15, W = spl / 2;
     const int Tp2 = (T / 2 + 16) & ~15;
     size_t pg = (stream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15)) + (size_t)2 * K * Tp + (size_t)K * Tp2 +
@@ -77,6 +78,7 @@ static size_t pg_role_smem(int T, int V, int K, int spl, int threads, bool strea
     pg += (size_t)(threads / 32) * kFusedMaxK * 8 + 3 * kFusedMaxK * 4 + 16 + 16;
     // reward-to-go: log-sum-exp per frame, chunk counters, the last column / reward-to-go of every sample (int16)
     if (togo) pg += (size_t)Tp * 4 + (size_t)(threads / 32) * 64 * 4 + (size_t)K * (Tp + 16) * 2;
+    if (cdf) pg += pg_cdf_bytes(threads);
     return pg;
 }
 
@@ -146,9 +148,16 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
     const bool stream = a.do_pg && pl.stream;
     const bool togo = a.do_pg && a.reward_mode == PGASR_REWARD_ED_TO_GO;
     if (togo && stream) return PGASR_ERR_UNSUPPORTED;      // (reward-to-go needs the logits tile in shared memory)
+    a.cdf_smem = 0;
     if (a.do_pg) {
-        const size_t pg = pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream, togo);
+        size_t pg = pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream, togo);
         if (pg > kFusedSmemLimit) return PGASR_ERR_UNSUPPORTED;
+        // the CDF rows in shared memory when they fit next to everything else (PGASR_NO_CDF_SMEM=1: register path, A/B)
+        static const bool no_cdf = getenv("PGASR_NO_CDF_SMEM") != nullptr;
+        if (!no_cdf && !stream && a.V <= 32 && pg + pg_cdf_bytes(pl.threads) <= kFusedSmemLimit) {
+            a.cdf_smem = 1;
+            pg += pg_cdf_bytes(pl.threads);
+        }
         smem = smem > pg ? smem : pg;
     }
     const int mode = pl.bw ? 3 : !pl.gt ? 0 : !stream ? 1 : 2;   // tiles in shared memory | CTC streams | both stream | block workers

@@ -10,6 +10,8 @@ struct FusedArgs {
     int B, T, V, K, Lmax, blank, reward_mode, baseline_mode;
     float baseline_value, w_pg, w_ctc;
     int do_pg, do_ctc;
+    int cdf_smem;            // PG role: the per-frame CDF rows live in shared memory ([T][33] fp32, V <= 32, tile mode) -- rolled
+                             // loops and a binary search instead of 32 registers and a select tree (fused_impl.cuh P1)
     float* loss; float* dlogits;
     float* rewards; float* logp; int32_t* hyp_len; int32_t* dist; float* nll; uint8_t* samples;   // optional
     int16_t* to_go; int8_t* r_pos;                                                                // optional (reward-to-go)

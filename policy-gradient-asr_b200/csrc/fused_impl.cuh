@@ -363,7 +363,9 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     const int Tc = Tp + 16;
     float* lz_s = reinterpret_cast<float*>(smem_raw + off);      if (togo) off += (size_t)Tp * 4;
     int* warp_acc_i = reinterpret_cast<int*>(smem_raw + off);    if (togo) off += (size_t)kWarps * 64 * 4;   // emitted symbols before each 32-frame chunk
-    int16_t* col_s = reinterpret_cast<int16_t*>(smem_raw + off); // [K][Tc]
+    int16_t* col_s = reinterpret_cast<int16_t*>(smem_raw + off); if (togo) off += (size_t)K * Tc * 2;   // [K][Tc]
+    off = (off + 15) & ~(size_t)15;
+    float* cdf_s = reinterpret_cast<float*>(smem_raw + off);     // [kThreads][33] (a.cdf_smem)
 
     const bool dbg = b == 0 && threadIdx.x == 0;
     PGASR_STAMP(dbg, 30);
@@ -453,11 +455,83 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
                     samples_s[(size_t)k * Tp + t] = (uint8_t)pi;
                     if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi;
                 }
-                term = warp_sum(term);
-                if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)term;   // across passes and warps in fp64: log p ~ -1000
+                // the warp's 32 terms in ONE instruction: 2^-19 fixed point (a term lies in [-92, 0]: the sum of 32 fits an
+                // int32; the rounding, 1e-6 per frame, is far inside the 1e-4 the log-probabilities are checked to)
+                const int ti = __reduce_add_sync(kFull, __float2int_rn(term * 524288.0f));
+                if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)ti * (1.0 / 524288.0);   // across passes and warps in fp64: log p ~ -1000
             }
         };
-        if (V <= 32) sample_frame(std::integral_constant<int, 32>{});
+        if (a.cdf_smem) {
+            // The CDF row of the frame in shared memory (33 floats: odd stride, a thread's walk along its row never
+            // collides with its neighbours'), built and searched by ROLLED loops: the fully unrolled register version
+            // is ~2000 straight-line instructions per thread, and with every warp streaming through them once the phase
+            // was bound by instruction fetch (no_inst was half of its stall samples).  Same arithmetic, same counts.
+            float* cr = cdf_s + (size_t)threadIdx.x * 33;       // (one row per thread, reused by every pass)
+            float mx = -INFINITY, S = 0.0f, logS = 0.0f;
+            if (live) {
+#pragma unroll 2
+                for (int v = 0; v < V; ++v) mx = fmaxf(mx, z[v]);
+                // four classes at a time: the four exp chains are independent, only the running sum is sequential
+                // (a thread's chain of ~25 dependent fp32 operations per class left the issue slots idle: 290 cycles
+                // per class with four warps per scheduler, measured).  Entries V..31 repeat S.
+                float c = 0.0f;
+#pragma unroll 1
+                for (int v = 0; v < 32; v += 4) {
+                    float e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) e[u] = exp_spec(__fsub_rn(z[min(v + u, V - 1)], mx));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        c = v + u < V ? __fadd_rn(c, e[u]) : c;
+                        cr[v + u] = c;
+                    }
+                }
+                S = c;
+                logS = logf(S);
+                if (togo) lz_s[t] = mx + logS;
+            }
+            PGASR_STAMP(dbg && t0 == 0, 60);
+#pragma unroll 1
+            for (int k0 = 0; k0 < K; k0 += 4) {           // four draws (one Philox block) side by side
+                float term[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                int pi[4] = {0, 0, 0, 0};
+                if (live) {
+                    float tau[4];
+                    uint4 rnd = make_uint4(0, 0, 0, 0);
+                    if (!a.uniforms)
+                        rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k0 >> 2), 0x50474153u), key);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float un;
+                        if (a.uniforms) un = k0 + u < K ? __ldg(a.uniforms + ((size_t)b * K + k0 + u) * T + t) : 0.0f;
+                        else un = u32_to_uniform(u == 0 ? rnd.x : u == 1 ? rnd.y : u == 2 ? rnd.z : rnd.w);
+                        tau[u] = __fmul_rn(un, S);
+                    }
+                    int cnt[4] = {0, 0, 0, 0};            // #{v < 32 : cdf[v] <= tau}, the CDF is non-decreasing
+#pragma unroll
+                    for (int h = 16; h > 0; h >>= 1)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) cnt[u] += cr[cnt[u] + h - 1] <= tau[u] ? h : 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        pi[u] = min(cnt[u], V - 1);
+                        term[u] = k0 + u < K ? (z[pi[u]] - mx) - logS : 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u;
+                    if (k < K) {                          // (warp uniform)
+                        if (t < T) {
+                            samples_s[(size_t)k * Tp + t] = (uint8_t)pi[u];
+                            if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi[u];
+                        }
+                        const int ti = __reduce_add_sync(kFull, __float2int_rn(term[u] * 524288.0f));
+                        if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)ti * (1.0 / 524288.0);
+                    }
+                }
+            }
+        } else if (V <= 32) sample_frame(std::integral_constant<int, 32>{});
         else sample_frame(std::integral_constant<int, 64>{});
     }
     __syncthreads();

@@ -47,8 +47,10 @@ constexpr unsigned kFull = 0xffffffffu;
 // Sampler contract (DESIGN.md "sampler spec"): every operation is one fp32 operation rounded to
 // nearest even; __f*_rn intrinsics are never contracted into FMAs by nvcc.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float exp_spec(float x) {
-    if (!(x >= -87.0f)) return 0.0f;
+__device__ __forceinline__ float exp_spec(float x0) {
+    // branch free (an early return made every call its own basic block: neighbouring calls could not interleave):
+    // the polynomial runs on max(x, -87), the spec's "x < -87 -> +0" (and NaN -> +0) is a select at the end
+    const float x = fmaxf(x0, -87.0f);
     float t = __fmul_rn(x, 1.44269504088896341f);
     float n = rintf(t);
     float r = __fsub_rn(x, __fmul_rn(n, 0.693359375f));
@@ -65,7 +67,7 @@ __device__ __forceinline__ float exp_spec(float x) {
     y = __fadd_rn(y, 1.0f);
     int ni = (int)n;
     float scale = __int_as_float((ni + 127) << 23);
-    return __fmul_rn(y, scale);
+    return x0 >= -87.0f ? __fmul_rn(y, scale) : 0.0f;
 }
 
 // Philox4x32-10 (Salmon et al. 2011).  Counter (t, b, k/4, 'PGAS'), key = seed.

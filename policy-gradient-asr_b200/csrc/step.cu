@@ -112,8 +112,21 @@ static size_t step_lane_bytes(int B, int T, int V, int K, int Lmax) {
 }
 }  // namespace pgasr
 
+namespace pgasr {
+constexpr int kMaxLanes = 4;
+// lanes of the workspace = steps of one pgasr_pg_ctc_step_multi call in flight at once (2; PGASR_LANES=1..4 for A/B runs)
+static int step_lanes() {
+    static const int n = [] {
+        const char* e = getenv("PGASR_LANES");
+        const int v = e ? atoi(e) : 2;
+        return v < 1 ? 1 : v > kMaxLanes ? kMaxLanes : v;
+    }();
+    return n;
+}
+}  // namespace pgasr
+
 extern "C" size_t pgasr_pg_ctc_step_workspace_bytes(int B, int T, int V, int K, int Lmax) {
-    return 2 * pgasr::step_lane_bytes(B, T, V, K, Lmax);
+    return (size_t)pgasr::step_lanes() * pgasr::step_lane_bytes(B, T, V, K, Lmax);
 }
 
 extern "C" int pgasr_pg_ctc_step_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
@@ -242,7 +255,7 @@ namespace pgasr {
 // The second stream of pgasr_pg_ctc_step_multi and the events that fork it from / join it to the caller's stream:
 // one set per host thread and device, created on first use (the only objects the library keeps besides the
 // control-block parity; they live as long as the thread).
-struct AuxLane { cudaStream_t stream; cudaEvent_t fork, join; bool ok; };
+struct AuxLane { cudaStream_t stream[kMaxLanes - 1]; cudaEvent_t fork, join[kMaxLanes - 1]; bool ok; };
 static int aux_lane(AuxLane** out) {
     static thread_local AuxLane lanes[64] = {};
     int dev = 0;
@@ -250,9 +263,11 @@ static int aux_lane(AuxLane** out) {
     if (dev < 0 || dev >= 64) return PGASR_ERR_UNSUPPORTED;
     AuxLane& a = lanes[dev];
     if (!a.ok) {
-        PGASR_CUDA_TRY(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
         PGASR_CUDA_TRY(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
-        PGASR_CUDA_TRY(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+        for (int i = 0; i < kMaxLanes - 1; ++i) {
+            PGASR_CUDA_TRY(cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking));
+            PGASR_CUDA_TRY(cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming));
+        }
         a.ok = true;
     }
     *out = &a;
@@ -278,23 +293,24 @@ extern "C" int pgasr_pg_ctc_step_multi(const pgasr_step_io* steps, int n_steps, 
     if (rc) return rc;
     static const bool no_overlap = getenv("PGASR_NO_OVERLAP") != nullptr;
     cudaStream_t s0 = as_stream(stream);
-    void* lane1 = reinterpret_cast<char*>(workspace) + step_lane_bytes(B, T, V, K, Lmax);
+    const size_t lane_bytes = step_lane_bytes(B, T, V, K, Lmax);
+    const int nl = (n_steps >= 2 && !no_overlap) ? (step_lanes() < n_steps ? step_lanes() : n_steps) : 1;
     AuxLane* aux = nullptr;
-    const bool overlap = n_steps >= 2 && !no_overlap;
-    if (overlap) {
+    if (nl > 1) {
         rc = aux_lane(&aux);
         if (rc) return rc;
         PGASR_CUDA_TRY(cudaEventRecord(aux->fork, s0));
-        PGASR_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+        for (int l = 1; l < nl; ++l) PGASR_CUDA_TRY(cudaStreamWaitEvent(aux->stream[l - 1], aux->fork, 0));
     }
     for (int i = 0; i < n_steps; ++i) {
-        const bool second = overlap && (i & 1);
-        rc = step_one(q, steps[i], seed_base + steps[i].seed, second ? lane1 : workspace, second ? aux->stream : s0);
+        const int l = i % nl;
+        rc = step_one(q, steps[i], seed_base + steps[i].seed, reinterpret_cast<char*>(workspace) + (size_t)l * lane_bytes,
+                      l ? aux->stream[l - 1] : s0);
         if (rc) break;
     }
-    if (overlap) {                                         // join, also after an error: the caller's stream stays the one order
-        PGASR_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
-        PGASR_CUDA_TRY(cudaStreamWaitEvent(s0, aux->join, 0));
+    for (int l = 1; l < nl; ++l) {                         // join, also after an error: the caller's stream stays the one order
+        PGASR_CUDA_TRY(cudaEventRecord(aux->join[l - 1], aux->stream[l - 1]));
+        PGASR_CUDA_TRY(cudaStreamWaitEvent(s0, aux->join[l - 1], 0));
     }
     return rc;
 }

@@ -41,6 +41,7 @@ for mode, (wp, wc) in {"both": (1.0, 1.0), "ctc": (0.0, 1.0), "pg": (1.0, 0.0)}.
         print(f"                alpha B0 rows split: pre {d[56]} loop {d[57]} blocks {d[58]} trips/block {d[59]}")
     if wp:
         names = ["tile-load", "sample", "collapse", "myers", "advantages", "grad-tile", "flag-wait", "rmw-out"]
+        print(f" pg sampling split (thread 0): cdf build {d[60]-d[31]}  draws {d[32]-d[60]}")
         print(" pg:  " + "  ".join(f"{n} {d[31+i]-d[30+i]}" for i, n in enumerate(names)) + f"  total {d[38]-d[30]}")
 
 # per-CTA wall times of the last fused launch (globaltimer ns): role start/end spread over the grid
@@ -67,3 +68,22 @@ print(" CTC role duration by utterance (us) / max labels of one class:")
 print("   fastest: " + "  ".join(f"{dur[i]:.1f}/{cmax[i]}" for i in order[:8]))
 print("   slowest: " + "  ".join(f"{dur[i]:.1f}/{cmax[i]}" for i in order[-8:]))
 print(f"   corr(duration, cmax) = {np.corrcoef(dur, cmax)[0, 1]:.2f}")
+
+# the same per-CTA times with consecutive steps overlapping (pgasr_pg_ctc_step_multi, two lanes): how long a CTA lives
+# when the SMs are shared with the neighbouring steps (entries are overwritten by whichever step finishes last)
+batches = []
+for i in range(8):
+    a, b, c, d, _ = make_batch(B, 500, 30, 16, 100, seed=100 + i)
+    batches.append({"logits": torch.from_numpy(a).to(dev), "targets": torch.from_numpy(b).to(dev),
+                    "in_len": torch.from_numpy(c).to(dev), "tgt_len": torch.from_numpy(d).to(dev)})
+q = F.StepQueue(batches, K=16)
+for rep in range(3):
+    q.run(first=0, n=8, seed=rep)
+torch.cuda.synchronize()
+arr = (ctypes.c_ulonglong * (3 * n))()
+assert lib.pgasr_debug_cta_times(arr, n) == 0
+t = np.array(list(arr), dtype=np.float64).reshape(n, 3) / 1e3
+for name, sl in (("CTC role CTAs", slice(0, B)), ("PG role CTAs", slice(B, n))):
+    x = t[sl]
+    dur = x[:, 1] - x[:, 0]
+    print(f" overlapped steps, {name}: role duration median {np.median(dur):6.1f} us  min {dur.min():6.1f}  max {dur.max():6.1f}")
