@@ -4,7 +4,8 @@
  * The upstream project is pure Python: its "plugin interface" for this path is a handful of Python
  * functions and one nn.Module slot.  This header is what those bind to.  Every
  * entry point is extern "C", takes plain device pointers and sizes, allocates nothing, keeps no
- * global state (one exception: the parity of a step workspace, see pgasr_pg_ctc_step), enqueues its work on the
+ * global state (exceptions: the control-block parity of a step workspace lane and the per-thread second stream of
+ * pgasr_pg_ctc_step_multi, see there), enqueues its work on the
  * caller's stream (a cudaStream_t passed as void*; NULL = the
  * legacy default stream) and returns a pgasr_status.  All pointers are device pointers borrowed until
  * the stream work completes, unless a parameter says "host".  There is no CPU fallback: without a
@@ -139,12 +140,12 @@ PGASR_API int pgasr_nll_sum_backward(const int64_t* target, const float* grad_ou
  *   loss[0]  = w_pg * L_pg + w_ctc * mean_b nll[b]
  *   dlogits  = w_pg * g_pg + (w_ctc / B) * g_ctc                     (written once, not accumulated)
  * Optional outputs (NULL to skip): rewards, logp, hyp_len, dist, nll, samples.
- * workspace: pgasr_pg_ctc_step_workspace_bytes(B,T,V,K,Lmax) bytes, 256-byte aligned, armed ONCE with
- * pgasr_pg_ctc_step_workspace_init before its first use (and again after a step that returned an error);
- * one workspace serves one stream at a time.  The step kernel is launched with programmatic stream serialisation:
- * back-to-back steps on one stream overlap the launch of step n+1 with the tail of step n (the CTAs of n+1 wait on
- * the grid dependency before they touch any input or output); for that the workspace holds two control blocks that
- * consecutive calls use alternately -- the library remembers, per workspace pointer, which one is next (host side).
+ * workspace: pgasr_pg_ctc_step_workspace_bytes(B,T,V,K,Lmax) bytes (two lanes, see pgasr_pg_ctc_step_multi), 256-byte
+ * aligned, armed ONCE with pgasr_pg_ctc_step_workspace_init before its first use (and again after a step that returned
+ * an error); one workspace serves one stream at a time.  The step kernel is launched with programmatic stream
+ * serialisation: back-to-back steps on one stream overlap the launch of step n+1 with the tail of step n (the CTAs of
+ * n+1 wait on the grid dependency before they touch any input or output); for that a lane holds two control blocks that
+ * consecutive launches use alternately -- the library remembers, per lane pointer, which one is next (host side).
  * V <= 64 (register-resident fast paths up to 32 classes), K <= 64.  One kernel launch for every shape whose sample
  * buffers fit an SM (2.5 K T <= ~200 KB); targets / in_len / tgt_len and the small outputs may live in pinned host
  * memory mapped into the device (they are read once per CTA / written once).                       */
@@ -162,10 +163,18 @@ PGASR_API int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, con
 
 /* ---- n steps with one call (micro-batches of one optimiser step; a bench loop) ---------------------------
  * steps: HOST array of n_steps records of DEVICE pointers, same meaning as the arguments of pgasr_pg_ctc_step
- * (optional ones may be NULL); step i samples with Philox(seed_base + steps[i].seed).  The steps run back to back on
- * `stream`, all on the one workspace; per step the host does one kernel launch and nothing else.
- * to_go [B,K,T] int16 and r_pos [B,K,T] int8 (optional, reward_mode PGASR_REWARD_ED_TO_GO only): the reward-to-go of
- * every frame and the per-position reward of every collapsed symbol (zero beyond hyp_len).                    */
+ * (optional ones may be NULL); step i samples with Philox(seed_base + steps[i].seed).  Per step the host does one
+ * kernel launch and nothing else.
+ * The steps of one call must be INDEPENDENT: no step's output buffer may be another step's input or output.  They
+ * are enqueued alternately on `stream` and on a second stream the library forks from `stream` (event) and joins back
+ * into it before the call returns, each with its own lane of the workspace, so consecutive steps overlap on the GPU
+ * while, to the caller, everything is ordered on `stream` as usual.  The second stream and its two events are created
+ * on first use, one set per calling host thread and device, and live as long as the thread (together with the
+ * control-block parity above this is all the state the library keeps).  PGASR_NO_OVERLAP=1 in the environment keeps
+ * every step on `stream`.
+ * reward_mode PGASR_REWARD_ED_TO_GO (single-launch kernel with the logits tile in shared memory only; else
+ * PGASR_ERR_UNSUPPORTED): to_go [B,K,T] int16 and r_pos [B,K,T] int8 (optional) receive the reward-to-go of every
+ * frame and the per-position reward of every collapsed symbol (zero beyond hyp_len); rewards = len(ref) - ED.   */
 typedef struct pgasr_step_io {
     const float* logits; const int32_t* targets; const int32_t* in_len; const int32_t* tgt_len;
     const float* uniforms; uint64_t seed;
