@@ -1243,13 +1243,14 @@ __device__ __forceinline__ int lds_s32(unsigned addr) {
 // ADDRESSES of the label's row in one matrix buffer with the frame-slot swizzle folded in:
 // entry = base + row * 128 + (row / LPL) * 4, so that the address of (label, frame slot f) is entry ^ 4 f (base is
 // 128-byte aligned: the xor stays inside the row).  One list per matrix buffer (2 directions x kBwGB buffers).
-// The list is FLAT: bit 31 of an entry says "last label of its class"; a class without labels contributes one entry
-// pointing at the all-zero row 16 SPL - 1 (its state lies beyond S for every transcript this variant takes).  The row
-// worker walks the list in groups of 8, three groups per loop trip and two groups of prefetch, so the list is padded
-// with zero-row entries (no flag) to 3 ceil(groups / 3) + 2 groups.
-// info[0] = loop trips, info[4 + v] (16-byte aligned, 32 entries) = the flagged entry of class v (flag stripped): where
-// the row worker leaves the class's total.  One warp; V <= 32.
-constexpr unsigned kBwEnd = 0x80000000u;
+// The row worker walks the list in groups of 8, three groups per loop trip and two groups of prefetch, replacing every
+// entry's occupancy by the running sum up to it; the list is padded to 3 ceil(groups / 3) + 2 groups with entries
+// pointing at the spare row 16 SPL - 1 (its state lies beyond S for every transcript this variant takes; what lands
+// there is never read back).
+// info[0] = loop trips, info[4 + v] (16-byte aligned, 32 entries) = the LAST entry of the classes 0..v, i.e. where the
+// running sum up to and including class v ends up (kBwNone when no label has a class <= v): a class's total is the
+// difference of two of them.  One warp; V <= 32.
+constexpr unsigned kBwNone = 0xffffffffu;
 constexpr int kBwListWords = 256;     // per copy: the list (at most 23 groups) and, from word 192, info[36]
 constexpr int kBwInfoAt = 192;
 template <int SPL>
@@ -1258,32 +1259,26 @@ __device__ __forceinline__ void bw_build_list(const int* cls_off, const int* cls
     constexpr int LPL = SPL / 2, kRows = 16 * SPL;
     const int lane = threadIdx.x & 31;
     const int cnt = lane < V ? cls_off[lane + 1] - cls_off[lane] : 0;
-    const int pc = lane < V ? max(cnt, 1) : 0;
-    int incl = pc;
+    int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int x = __shfl_up_sync(kFull, incl, o);
         if (lane >= o) incl += x;
     }
-    const int start = incl - pc;
+    const int start = incl - cnt;
     const int total = __shfl_sync(kFull, incl, 31);
     const unsigned ez = base + (unsigned)((kRows - 1) * 128 + ((kRows - 1) / LPL) * 4);
     if (lane < V) {
         const int src = cls_off[lane];
-        unsigned e = ez;
-        for (int i = 0; i < pc; ++i) {
-            e = ez;
-            if (i < cnt) {
-                const int li = cls_pos[src + i];
-                e = base + (unsigned)(li * 128 + (li / LPL) * 4);
-            }
-            elist[start + i] = i == pc - 1 ? (e | kBwEnd) : e;
+        for (int i = 0; i < cnt; ++i) {
+            const int li = cls_pos[src + i];
+            elist[start + i] = base + (unsigned)(li * 128 + (li / LPL) * 4);
         }
-        info[4 + lane] = (int)e;
     }
     const int trips = ((total + 7) / 8 + 2) / 3;
     for (int i = total + lane; i < 8 * (3 * trips + 2); i += 32) elist[i] = ez;
-    if (lane >= V) info[4 + lane] = (int)ez;             // (classes beyond V: the zero row, never stored)
+    __syncwarp();
+    info[4 + lane] = incl > 0 ? (int)elist[incl - 1] : (int)kBwNone;   // (lanes >= V repeat the last class: never used)
     if (lane == 0) info[0] = trips;
     __syncwarp();
 }
@@ -1492,26 +1487,28 @@ __device__ __forceinline__ void ctc_bworker(bool kAlpha, int j, const float* til
         const int tlo = kAlpha ? n_first + q0 : Tb - 1 - n_first - q0 - (nf - 1);
         const unsigned prow = (unsigned)__cvta_generic_to_shared(tile + (size_t)t * RS);
         const float gmul = dead ? 0.0f : gs30;
-        // ---- class totals: a running integer sum over the class-ordered list; where an entry ends its class the
-        // total (difference of two running sums) replaces that entry's occupancy in the matrix (nobody reads it again)
-        int acc = 0, last = 0;
+        // ---- running integer sums over the class-ordered list: every entry's occupancy is replaced by the sum up to
+        // and including it (load, add, store back to the same address: four instructions per label for 32 frames; a
+        // version that stored only at class ends needed a compare, a select and two predicated instructions per entry)
+        int acc = 0;
         unsigned E[3][8];
         int X[3][8];
         auto ld_list = [&](unsigned (&e)[8], unsigned addr) {
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]) : "r"(addr));
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7]) : "r"(addr + 16u));
         };
-        auto ld_occ = [&](int (&x)[8], const unsigned (&e)[8]) {
+        auto ld_occ = [&](int (&x)[8], unsigned (&e)[8]) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(x[u]) : "r"((e[u] & ~kBwEnd) ^ fx));
+            for (int u = 0; u < 8; ++u) {
+                e[u] ^= fx;                               // (this lane's slot of the entry's row)
+                asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(x[u]) : "r"(e[u]));
+            }
         };
         auto sum8 = [&](const int (&x)[8], const unsigned (&e)[8]) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 acc += x[u];
-                const bool end = (int)e[u] < 0;
-                if (end) asm volatile("st.shared.s32 [%0], %1;\n" ::"r"((e[u] & ~kBwEnd) ^ fx), "r"(acc - last));
-                last = end ? acc : last;
+                asm volatile("st.shared.s32 [%0], %1;\n" ::"r"(e[u]), "r"(acc));
             }
         };
         ld_list(E[0], el_s);
@@ -1539,20 +1536,32 @@ __device__ __forceinline__ void ctc_bworker(bool kAlpha, int j, const float* til
         __syncwarp();
         const int row = kAlpha ? lane : nf - 1 - lane;   // this lane's frame within the block's rows, ascending in t
         const unsigned srow = st_s + 4u * (unsigned)(max(row, 0) * V);
+        const unsigned zslot = (elist[8 * (3 * ntrips + 2) - 1]) ^ fx;   // (a padding entry: any valid address)
+        int tot;                                          // sum of all label occupancies: where the last class ends
+        {
+            unsigned ce;
+            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(ce) : "r"(cl_s + 4u * (unsigned)(V - 1)));
+            asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(tot) : "r"(ce == kBwNone ? zslot : ce ^ fx));
+            tot = ce == kBwNone ? 0 : tot;
+        }
+        int prev = 0;                                     // running sum at the end of the previous class
         for (int v0 = 0; v0 < V; v0 += 8) {
             unsigned cl[8];
             ld_list(cl, cl_s + 4u * (unsigned)v0);
             const unsigned pa = prow + 4u * (unsigned)v0;
-            int occ[8];
+            int ps[8];
             float pv[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(occ[u]) : "r"(cl[u] ^ fx));
+            for (int u = 0; u < 8; ++u)
+                asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(ps[u]) : "r"(cl[u] == kBwNone ? zslot : cl[u] ^ fx));
 #pragma unroll
             for (int u = 0; u < 8; ++u)                   // (beyond V: the row's zero slot, in bounds)
                 asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(pv[u]) : "r"(pa + 4u * (unsigned)min(u, V - v0)));
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int oc = v0 + u == blank ? (1 << 30) - acc : occ[u];   // the blank column: sum_s gamma_t(s) = 1
+                const int upto = cl[u] == kBwNone ? 0 : ps[u];
+                const int oc = v0 + u == blank ? (1 << 30) - tot : upto - prev;   // the blank column: sum_s gamma_t(s) = 1
+                prev = upto;
                 const int pfix = __float2int_rn(pv[u] * (float)kCtcFix);
                 const float gval = (float)(pfix - oc) * gmul;
                 if (valid && v0 + u < V)

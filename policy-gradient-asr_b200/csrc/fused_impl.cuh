@@ -650,7 +650,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
             n1 = bidir ? myers_split_point(n) : n;
             const int nsym = fwd ? n1 : n - n1;
             const int nmax = __reduce_max_sync(kFull, nsym);
-            myers_half<W, P>(fwd ? hyp_s + (size_t)kc * Tp : hrev_s + (size_t)kc * Tp2, nsym, fwd ? peq : peq_r, V, p, nmax,
+            myers_half<W, P, false>(fwd ? hyp_s + (size_t)kc * Tp : hrev_s + (size_t)kc * Tp2, nsym, fwd ? peq : peq_r, V, p, nmax,
                              VPh, VNh);
             if (!fwd) myers_store_column<W, P>(VPh, VNh, n - n1, p, fg_s + (size_t)k * (W * 32 + 2));
         }

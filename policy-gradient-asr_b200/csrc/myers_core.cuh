@@ -221,17 +221,26 @@ __device__ __forceinline__ int myers_row_split(const uint8_t* __restrict__ h, in
     return n + d;
 }
 
-// One block of up to 8 hypothesis symbols (packed little endian in sy) on this lane's WL words of a P-lane group: the
-// body of myers_row_split's pipeline as a function, so that two independent streams can be interleaved in one thread.
-// cinw: the carry bits this lane receives (3 per symbol, see myers_row_split); returns the ones it passes on.
-template <int W, int WL, bool kWhole>
-__device__ __forceinline__ uint32_t myers_block8(uint32_t (&VP)[WL], uint32_t (&VN)[WL], uint32_t cinw, uint2 sy,
-                                                 const uint32_t* __restrict__ pq, uint32_t vmax, int nvalid) {
+// One block of up to 8 hypothesis symbols (packed little endian in sy) on this lane's WL words of a P-lane group.
+// Every horizontal dependency of the recurrence runs from low words to high words: the carry of the addition and the
+// top bits of HP and HN that are shifted into the next word.  They travel as three words per block -- bit (n-1-q) of
+// cin.c / .p / .n is what symbol q of an n-symbol block receives (a funnel shift per symbol collects them most
+// significant first: one instruction each, where packing three bits per symbol into one word cost eight).
+struct MyersCarry { uint32_t c, p, n; };
+__device__ __forceinline__ MyersCarry myers_carry_low(int nsym) {      // what the lowest lane of a group sees: (0, 1, 0)
+    MyersCarry k;
+    k.c = 0u; k.p = nsym >= 32 ? 0xffffffffu : (1u << nsym) - 1u; k.n = 0u;
+    return k;
+}
+template <int W, int WL, bool kWhole, bool kClamp>
+__device__ __forceinline__ MyersCarry myers_block8(uint32_t (&VP)[WL], uint32_t (&VN)[WL], MyersCarry cin, uint2 sy,
+                                                   const uint32_t* __restrict__ pq, uint32_t vmax, int nvalid) {
     constexpr int BS = 8;
     uint32_t eq[BS][WL];
 #pragma unroll
     for (int q = 0; q < BS; ++q) {
-        const uint32_t c = min(((q < 4 ? sy.x : sy.y) >> (8 * (q & 3))) & 0xffu, vmax);
+        uint32_t c = __byte_perm(q < 4 ? sy.x : sy.y, 0u, 0x4440u + (q & 3));   // byte q, zero extended
+        if (kClamp || !kWhole) c = min(c, vmax);          // (a partial block's tail bytes are whatever the buffer holds)
         if constexpr (WL == 1) {
             eq[q][0] = pq[c * W];
         } else if constexpr (WL == 2) {
@@ -242,12 +251,15 @@ __device__ __forceinline__ uint32_t myers_block8(uint32_t (&VP)[WL], uint32_t (&
             eq[q][0] = e.x; eq[q][1] = e.y; eq[q][2] = e.z; eq[q][3] = e.w;
         }
     }
-    uint32_t coutw = 0u;
+    MyersCarry out;
+    out.c = out.p = out.n = 0u;
+    const int nv = kWhole ? BS : nvalid;
 #pragma unroll
     for (int q = 0; q < BS; ++q) {
         if (kWhole || q < nvalid) {
+            const int sh = nv - 1 - q;                    // (a compile-time constant for whole blocks)
             uint32_t D0[WL], HP[WL], HN[WL];
-            uint32_t carry = (cinw >> (3 * q)) & 1u;
+            uint32_t carry = (cin.c >> sh) & 1u;
 #pragma unroll
             for (int w = 0; w < WL; ++w) {
                 const uint64_t sum = (uint64_t)(eq[q][w] & VP[w]) + VP[w] + carry;
@@ -256,17 +268,19 @@ __device__ __forceinline__ uint32_t myers_block8(uint32_t (&VP)[WL], uint32_t (&
                 HP[w] = VN[w] | ~(D0[w] | VP[w]);
                 HN[w] = D0[w] & VP[w];
             }
-            coutw |= (carry | ((HP[WL - 1] >> 31) << 1) | ((HN[WL - 1] >> 31) << 2)) << (3 * q);
+            out.c = (out.c << 1) | carry;
+            out.p = __funnelshift_l(HP[WL - 1], out.p, 1);    // (out.p << 1) | (HP >> 31)
+            out.n = __funnelshift_l(HN[WL - 1], out.n, 1);
 #pragma unroll
             for (int w = WL - 1; w >= 0; --w) {
-                const uint32_t hps = (HP[w] << 1) | (w ? HP[w - 1] >> 31 : (cinw >> (3 * q + 1)) & 1u);
-                const uint32_t hns = (HN[w] << 1) | (w ? HN[w - 1] >> 31 : (cinw >> (3 * q + 2)) & 1u);
+                const uint32_t hps = (HP[w] << 1) | (w ? HP[w - 1] >> 31 : (cin.p >> sh) & 1u);
+                const uint32_t hns = (HN[w] << 1) | (w ? HN[w - 1] >> 31 : (cin.n >> sh) & 1u);
                 VP[w] = hns | ~(D0[w] | hps);
                 VN[w] = hps & D0[w];
             }
         }
     }
-    return coutw;
+    return out;
 }
 
 // Meeting in the middle: ED(ref[:m], h[:n]) = min_j ED(ref[:j], h[:n1]) + ED(ref[j:], h[n1:]).  The forward half
@@ -281,7 +295,7 @@ __host__ __device__ __forceinline__ int myers_split_point(int n) { return min(n,
 
 // one half: nsym symbols of h (8-byte aligned, readable to the next multiple of 8) on this lane's WL words; the state
 // is left in VP / VN.  Call with all 32 lanes; nmax = the largest nsym of the warp.
-template <int W, int P>
+template <int W, int P, bool kClamp = true>
 __device__ __forceinline__ void myers_half(const uint8_t* __restrict__ h, int nsym, const uint32_t* __restrict__ peq_any,
                                            int vocab, int p, int nmax, uint32_t (&VP)[W / P], uint32_t (&VN)[W / P]) {
     constexpr int WL = W / P;
@@ -290,19 +304,25 @@ __device__ __forceinline__ void myers_half(const uint8_t* __restrict__ h, int ns
     for (int w = 0; w < WL; ++w) { VP[w] = 0xffffffffu; VN[w] = 0u; }
     const uint32_t vmax = (uint32_t)vocab;
     const uint32_t* pq = peq_any + p * WL;
-    constexpr uint32_t kLow = 0x00492492u;
-    uint32_t cinw = kLow;
+    MyersCarry cin = myers_carry_low(BS);
     const int iters = (nmax + BS - 1) / BS + P - 1;
     for (int it = 0; it < iters; ++it) {
         const int i0 = (it - p) * BS;
-        uint32_t coutw = 0u;
+        MyersCarry out;
+        out.c = out.p = out.n = 0u;
         if (i0 >= 0 && i0 < nsym) {
             const uint2 sy = *reinterpret_cast<const uint2*>(h + i0);
-            if (i0 + BS <= nsym) coutw = myers_block8<W, WL, true>(VP, VN, cinw, sy, pq, vmax, BS);
-            else coutw = myers_block8<W, WL, false>(VP, VN, cinw, sy, pq, vmax, nsym - i0);
+            if (i0 + BS <= nsym) {
+                out = myers_block8<W, WL, true, kClamp>(VP, VN, cin, sy, pq, vmax, BS);
+            } else {
+                if (p == 0) cin = myers_carry_low(nsym - i0);
+                out = myers_block8<W, WL, false, kClamp>(VP, VN, cin, sy, pq, vmax, nsym - i0);
+            }
         }
-        cinw = __shfl_up_sync(kFull, coutw, 1);
-        cinw = p == 0 ? kLow : cinw;
+        cin.c = __shfl_up_sync(kFull, out.c, 1);
+        cin.p = __shfl_up_sync(kFull, out.p, 1);
+        cin.n = __shfl_up_sync(kFull, out.n, 1);
+        if (p == 0) cin = myers_carry_low(BS);
     }
 }
 

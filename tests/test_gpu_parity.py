@@ -938,3 +938,33 @@ def test_step_reward_to_go_through_the_loss_module(cuda):
     loss = crit(x, dev_t(targets, cuda), dev_t(in_len, cuda), dev_t(tgt_len, cuda))
     loss.backward()
     assert torch.isfinite(loss) and torch.isfinite(x.grad).all() and float(x.grad.abs().sum()) > 0
+
+
+@pytest.mark.gpu
+def test_step_queue_overlap_soak_bit_reproducible(cuda):
+    """Consecutive steps of a multi-step call overlap on two streams / two workspace lanes (up to three grids share the
+    GPU): 40 runs of a 6-step window at the headline shape must reproduce the first run bit for bit, and that run must
+    equal the steps taken one at a time."""
+    from pgasr_b200 import functional as F
+    B, T, V, K, L = 64, 500, 30, 16, 100
+    batches = []
+    for s in range(6):
+        lg, tg, il, tl, _ = make_batch(B, T, V, K, L, seed=900 + s, ragged=(s % 3 == 0))
+        batches.append({"logits": dev_t(lg, cuda), "targets": dev_t(tg, cuda), "in_len": dev_t(il, cuda),
+                        "tgt_len": dev_t(tl, cuda)})
+    q = F.StepQueue(batches, K=K, want=("rewards", "nll"))
+    q.run(first=0, n=6, seed=11)
+    torch.cuda.synchronize()
+    first = [{k: o[k].clone() for k in ("loss", "dlogits", "rewards", "nll")} for o in q.outputs]
+    for j, b in enumerate(batches):
+        o = F.pg_ctc_step(b["logits"], b["targets"], b["in_len"], b["tgt_len"], K=K, seed=11 + j, want=("rewards", "nll"))
+        for k in ("dlogits", "rewards", "nll"):
+            assert torch.equal(o[k], first[j][k]), (j, k)
+    for rep in range(40):
+        for o in q.outputs:
+            o["dlogits"].fill_(float("nan"))
+        q.run(first=0, n=6, seed=11)
+        torch.cuda.synchronize()
+        for j, o in enumerate(q.outputs):
+            for k in ("loss", "dlogits", "rewards", "nll"):
+                assert torch.equal(o[k], first[j][k]), (rep, j, k)
