@@ -148,6 +148,11 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
     const bool stream = a.do_pg && pl.stream;
     const bool togo = a.do_pg && a.reward_mode == PGASR_REWARD_ED_TO_GO;
     if (togo && stream) return PGASR_ERR_UNSUPPORTED;      // (reward-to-go needs the logits tile in shared memory)
+    // The 60 KB logits tile of either role arrives as ONE TMA bulk copy (cp.async.bulk + mbarrier) when the 16-byte
+    // alignment rules hold, instead of 3750 16-byte cp.async from 512 threads: measured A/B (same box) softmax-tile phase
+    // 7.58 k -> 7.04 k cycles, PG tile load 2.24 k -> 1.67 k, step 38.3 -> 38.0 us.  PGASR_NO_BULK_TILE=1: cp.async path.
+    static const bool no_bulk_tile = getenv("PGASR_NO_BULK_TILE") != nullptr;
+    a.bulk_tile = !no_bulk_tile && (((size_t)a.T * a.V * 4) & 15) == 0 && ((reinterpret_cast<uintptr_t>(a.logits) & 15) == 0);
     a.cdf_smem = 0;
     if (a.do_pg) {
         size_t pg = pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream, togo);

@@ -10,6 +10,7 @@ struct FusedArgs {
     int B, T, V, K, Lmax, blank, reward_mode, baseline_mode;
     float baseline_value, w_pg, w_ctc;
     int do_pg, do_ctc;
+    int bulk_tile;           // the roles' logits tiles arrive as ONE bulk copy (cp.async.bulk + mbarrier) instead of 16-byte cp.async
     int cdf_smem;            // PG role: the per-frame CDF rows live in shared memory ([T][33] fp32, V <= 32, tile mode) -- rolled
                              // loops and a binary search instead of 32 registers and a select tree (fused_impl.cuh P1)
     float* loss; float* dlogits;

@@ -37,6 +37,14 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 
 constexpr int kFusedMaxK = 64;
 
+// one bulk copy global -> shared memory, completion on an mbarrier (see fused.cu for the measured A/B)
+__device__ __forceinline__ void bulk_load_tile(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+
 // Second ticket (thread 0 of a CTA, once): the CTA that draws the last one reduces the loss at the end of the kernel
 // and re-arms the control block.  It is drawn as EARLY as the protocol allows -- by a CTC CTA right after it released
 // its flag, by a PG CTA right after it acquired that flag and before its read-modify-write of dlogits -- so that the
@@ -101,7 +109,7 @@ __device__ __forceinline__ int cdf_count32(const float (&c)[32], float tau) {
 // kBW: block workers (ctc_core.cuh, "Block workers"): 5 occupancy workers and 2 row workers per direction instead of 7
 // workers that do both; up to 8 states per lane, tile in shared memory, 512 threads.
 template <int SPL, int kThreads, bool kGT, bool kBW = false>
-__device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last) {
+__device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last, unsigned long long* s_mbar) {
     static_assert(!kBW || (!kGT && SPL <= 8 && kThreads == 512 && kBwGA == 4 && kBwGB <= 3), "block workers: tile mode only");
     constexpr int G = (kThreads / 32 - 2) / 2;             // gradient workers per direction
     constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;      // frames of a batch per worker
@@ -188,7 +196,10 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
             for (int c0 = 0; c0 < Tb; c0 += chunk) {
                 const int n = min(chunk, Tb - c0);
                 const float* src = lg + (size_t)c0 * V;
-                if (al16) {
+                const bool bulk = a.bulk_tile && c0 == 0 && n == Tb && ((n * V * 4) & 15) == 0;
+                if (bulk) {
+                    if (threadIdx.x == 0) bulk_load_tile(stage, src, (unsigned)(n * V * 4), s_mbar);
+                } else if (al16) {
                     const int n16 = n * V / 4, rem = n * V - n16 * 4;
                     for (int i = threadIdx.x; i < n16; i += kThreads)
                         cp_async16(reinterpret_cast<char*>(stage) + (size_t)i * 16,
@@ -208,6 +219,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
                         }
                     }
                 }
+                if (bulk) mbar_wait(s_mbar, 0u);
                 cp_async_wait<0>();
                 __syncthreads();
                 if constexpr (kBW) {
@@ -331,7 +343,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
 // kStream (long utterances): no [T][V] tile in shared memory -- a thread reads its frame's logits straight from
 // global memory, and the gradient rows are formed in registers and added to dlogits row by row.
 template <int W, int kThreads, bool kStream>
-__device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last) {
+__device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last, unsigned long long* s_mbar) {
     constexpr int kWarps = kThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = a.T, V = a.V, K = a.K;
@@ -371,7 +383,9 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     PGASR_STAMP(dbg, 30);
     // ---- P0: logits tile -> shared memory ------------------------------------------------------
     const float* lg = a.logits + (size_t)b * T * V;
-    if (!kStream) {
+    if (!kStream && a.bulk_tile) {
+        if (threadIdx.x == 0) bulk_load_tile(ztile, lg, (unsigned)((size_t)T * V * 4), s_mbar);
+    } else if (!kStream) {
         if ((((size_t)T * V * 4) & 15) == 0) {
             const int n16 = T * V / 4;
             for (int i = threadIdx.x; i < n16; i += kThreads)
@@ -391,6 +405,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     }
     for (int i = threadIdx.x; i < kWarps * kFusedMaxK; i += kThreads) warp_acc[i] = 0.0;
     for (int i = threadIdx.x; i < (V + 1) * W; i += kThreads) { peq[i] = 0u; peq_r[i] = 0u; }
+    if (!kStream && a.bulk_tile) mbar_wait(s_mbar, 0u);
     cp_async_wait<0>();
     __syncthreads();
 
@@ -897,6 +912,11 @@ template <int SPL, int kThreads, bool kGT, bool kStream, bool kBW = false>
 __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_ticket, s_last;
+    __shared__ __align__(8) unsigned long long s_mbar;      // completion of the bulk tile load (a.bulk_tile)
+    if (threadIdx.x == 0 && a.bulk_tile) {
+        mbar_init(&s_mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
 #ifdef PGASR_TIMING
     const unsigned long long t_start = gtime();
 #endif
@@ -909,8 +929,8 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const unsigned ticket = s_ticket;
     const unsigned n_ctc = a.do_ctc ? (unsigned)a.B : 0u;
-    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT, kBW>(a, (int)ticket, smem_raw, &s_last);
-    else fused_pg_role<SPL / 2, kThreads, kStream>(a, (int)(ticket - n_ctc), smem_raw, &s_last);
+    if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT, kBW>(a, (int)ticket, smem_raw, &s_last, &s_mbar);
+    else fused_pg_role<SPL / 2, kThreads, kStream>(a, (int)(ticket - n_ctc), smem_raw, &s_last, &s_mbar);
 
 #ifdef PGASR_TIMING
     if (threadIdx.x == 0 && ticket < 2048) { g_cta_ns[ticket][0] = t_start; g_cta_ns[ticket][1] = gtime(); }
