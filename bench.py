@@ -418,7 +418,7 @@ def run_ours(args):
             "clocks": sampler.result(),
             "launch_path": "functional.pg_ctc_step per step (Python)" if args.python_loop else
                            f"pgasr_pg_ctc_step_multi: one C-ABI call per {min(pool, args.steps)} steps; consecutive steps of a "
-                           "call overlap on two streams (independent batches, own workspace lane each)",
+                           "call overlap on three streams (independent batches, own workspace lane each)",
         }
         if cpu_ref:
             line["cpu_baseline_reference"] = cpu_ref

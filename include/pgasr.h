@@ -4,7 +4,7 @@
  * The upstream project is pure Python: its "plugin interface" for this path is a handful of Python
  * functions and one nn.Module slot.  This header is what those bind to.  Every
  * entry point is extern "C", takes plain device pointers and sizes, allocates nothing, keeps no
- * global state (exceptions: the control-block parity of a step workspace lane and the per-thread second stream of
+ * global state (exceptions: the control-block parity of a step workspace lane and the per-thread extra streams of
  * pgasr_pg_ctc_step_multi, see there), enqueues its work on the
  * caller's stream (a cudaStream_t passed as void*; NULL = the
  * legacy default stream) and returns a pgasr_status.  All pointers are device pointers borrowed until
@@ -140,7 +140,7 @@ PGASR_API int pgasr_nll_sum_backward(const int64_t* target, const float* grad_ou
  *   loss[0]  = w_pg * L_pg + w_ctc * mean_b nll[b]
  *   dlogits  = w_pg * g_pg + (w_ctc / B) * g_ctc                     (written once, not accumulated)
  * Optional outputs (NULL to skip): rewards, logp, hyp_len, dist, nll, samples.
- * workspace: pgasr_pg_ctc_step_workspace_bytes(B,T,V,K,Lmax) bytes (two lanes, see pgasr_pg_ctc_step_multi), 256-byte
+ * workspace: pgasr_pg_ctc_step_workspace_bytes(B,T,V,K,Lmax) bytes (three lanes, see pgasr_pg_ctc_step_multi), 256-byte
  * aligned, armed ONCE with pgasr_pg_ctc_step_workspace_init before its first use (and again after a step that returned
  * an error); one workspace serves one stream at a time.  The step kernel is launched with programmatic stream
  * serialisation: back-to-back steps on one stream overlap the launch of step n+1 with the tail of step n (the CTAs of
@@ -166,9 +166,9 @@ PGASR_API int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, con
  * (optional ones may be NULL); step i samples with Philox(seed_base + steps[i].seed).  Per step the host does one
  * kernel launch and nothing else.
  * The steps of one call must be INDEPENDENT: no step's output buffer may be another step's input or output.  They
- * are enqueued alternately on `stream` and on a second stream the library forks from `stream` (event) and joins back
+ * are enqueued in rotation on `stream` and on two more streams the library forks from `stream` (event) and joins back
  * into it before the call returns, each with its own lane of the workspace, so consecutive steps overlap on the GPU
- * while, to the caller, everything is ordered on `stream` as usual.  The second stream and its two events are created
+ * while, to the caller, everything is ordered on `stream` as usual.  The extra streams and their events are created
  * on first use, one set per calling host thread and device, and live as long as the thread (together with the
  * control-block parity above this is all the state the library keeps).  PGASR_NO_OVERLAP=1 in the environment keeps
  * every step on `stream`.
