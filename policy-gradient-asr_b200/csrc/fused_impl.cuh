@@ -380,6 +380,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     float* cdf_s = reinterpret_cast<float*>(smem_raw + off);     // [kThreads][33] (a.cdf_smem)
 
     const bool dbg = b == 0 && threadIdx.x == 0;
+    (void)dbg;
     PGASR_STAMP(dbg, 30);
     // ---- P0: logits tile -> shared memory ------------------------------------------------------
     const float* lg = a.logits + (size_t)b * T * V;
@@ -648,7 +649,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     // ---- P3: edit distance, P lanes per sample ---------------------------------------------------
     // (all K samples in the lanes of as few warps as possible: a Myers step is a chain of dependent integer
     // instructions, and lanes of one warp share them; one sample per warp was measured 3.6x slower.  The words of a
-    // sample are spread over P lanes that run one symbol apart, see myers_row_split)
+    // sample are spread over P lanes that run one block apart, see myers_half)
     if constexpr (W >= 4) {
         // forward halves on the first nw warps, backward halves on the next nw (myers_core.cuh, "Meeting in the middle")
         constexpr int P = 4;                              // lanes per sample

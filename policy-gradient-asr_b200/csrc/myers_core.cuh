@@ -131,95 +131,10 @@ __device__ __forceinline__ int myers_row(const uint8_t* __restrict__ h, int n, c
     return d;
 }
 
-// ED(ref[:m], h[:n]) with the W words of one hypothesis spread over P adjacent lanes (WL = W / P words each), as a
-// block-skewed pipeline: the hypothesis is cut into blocks of 8 symbols and in outer iteration `it` lane p works on
-// block it - p, one block behind lane p - 1.  Every horizontal dependency of the recurrence runs from low words to
-// high words (the carry of the addition and the top bits of HP and HN that are shifted into the next word), so
-// lane p needs from lane p - 1 exactly three carry bits per symbol of the block that lane finished one iteration
-// earlier: 24 bits, one shuffle per block.  (A skew of one SYMBOL was measured slower than one thread per sample,
-// 190 against 115 cycles per symbol: the shuffle and the loads then sit on the dependent chain of every symbol.)
-// Call with all 32 lanes of a warp (the lanes of a group adjacent, p = lane % P); `nmax` = the largest n of the
-// warp; h must be 8-byte aligned and readable up to the next multiple of 8 (symbols beyond n are ignored).
-// Every lane of a group returns the distance.
-template <int W, int P>
-__device__ __forceinline__ int myers_row_split(const uint8_t* __restrict__ h, int n, const uint32_t* __restrict__ peq,
-                                               int vocab, int m, int p, int nmax) {
-    constexpr int WL = W / P;
-    constexpr int BS = 8;
-    static_assert(WL * P == W && (WL == 1 || WL == 2 || WL == 4), "words per lane");
-    uint32_t VP[WL], VN[WL];
-#pragma unroll
-    for (int w = 0; w < WL; ++w) { VP[w] = 0xffffffffu; VN[w] = 0u; }
-    const uint32_t vmax = (uint32_t)vocab;
-    const uint32_t* pq = peq + p * WL;
-    // carry bits of symbol q of a block: bit 3q the carry of the addition, 3q+1 HP shifted in, 3q+2 HN shifted in;
-    // the lowest lane of a group always sees (0, 1, 0)
-    constexpr uint32_t kLow = 0x00492492u;
-    uint32_t cinw = kLow;
-    auto step = [&](const uint32_t (&eq)[WL], int q, uint32_t& coutw) {
-        uint32_t D0[WL], HP[WL], HN[WL];
-        uint32_t carry = (cinw >> (3 * q)) & 1u;
-#pragma unroll
-        for (int w = 0; w < WL; ++w) {
-            const uint64_t sum = (uint64_t)(eq[w] & VP[w]) + VP[w] + carry;
-            carry = (uint32_t)(sum >> 32);
-            D0[w] = (((uint32_t)sum ^ VP[w]) | eq[w]) | VN[w];
-            HP[w] = VN[w] | ~(D0[w] | VP[w]);
-            HN[w] = D0[w] & VP[w];
-        }
-        coutw |= (carry | ((HP[WL - 1] >> 31) << 1) | ((HN[WL - 1] >> 31) << 2)) << (3 * q);
-#pragma unroll
-        for (int w = WL - 1; w >= 0; --w) {
-            const uint32_t hps = (HP[w] << 1) | (w ? HP[w - 1] >> 31 : (cinw >> (3 * q + 1)) & 1u);
-            const uint32_t hns = (HN[w] << 1) | (w ? HN[w - 1] >> 31 : (cinw >> (3 * q + 2)) & 1u);
-            VP[w] = hns | ~(D0[w] | hps);
-            VN[w] = hps & D0[w];
-        }
-    };
-    const int iters = (nmax + BS - 1) / BS + P - 1;
-    for (int it = 0; it < iters; ++it) {
-        const int i0 = (it - p) * BS;
-        uint32_t coutw = 0u;
-        if (i0 >= 0 && i0 < n) {
-            const uint2 sy = *reinterpret_cast<const uint2*>(h + i0);
-            uint32_t eq[BS][WL];
-#pragma unroll
-            for (int q = 0; q < BS; ++q) {
-                const uint32_t c = min(((q < 4 ? sy.x : sy.y) >> (8 * (q & 3))) & 0xffu, vmax);
-                if constexpr (WL == 1) {
-                    eq[q][0] = pq[c * W];
-                } else if constexpr (WL == 2) {
-                    const uint2 e = *reinterpret_cast<const uint2*>(pq + c * W);
-                    eq[q][0] = e.x; eq[q][1] = e.y;
-                } else {
-                    const uint4 e = *reinterpret_cast<const uint4*>(pq + c * W);
-                    eq[q][0] = e.x; eq[q][1] = e.y; eq[q][2] = e.z; eq[q][3] = e.w;
-                }
-            }
-            if (i0 + BS <= n) {
-#pragma unroll
-                for (int q = 0; q < BS; ++q) step(eq[q], q, coutw);
-            } else {
-#pragma unroll
-                for (int q = 0; q < BS; ++q)
-                    if (i0 + q < n) step(eq[q], q, coutw);
-            }
-        }
-        cinw = __shfl_up_sync(kFull, coutw, 1);
-        cinw = p == 0 ? kLow : cinw;
-    }
-    // dp[n, m] = dp[n, 0] + sum_{j<m} (VP_j - VN_j): own words, then across the group
-    int d = 0;
-#pragma unroll
-    for (int w = 0; w < WL; ++w) {
-        const int lo = (p * WL + w) * 32;
-        const uint32_t msk = m >= lo + 32 ? 0xffffffffu : (m > lo ? (1u << (m - lo)) - 1u : 0u);
-        d += __popc(VP[w] & msk) - __popc(VN[w] & msk);
-    }
-#pragma unroll
-    for (int o = 1; o < P; o <<= 1) d += __shfl_xor_sync(kFull, d, o);
-    return n + d;
-}
+// The W words of one hypothesis can be spread over P adjacent lanes (WL = W / P words each) as a block-skewed pipeline:
+// the hypothesis is cut into blocks of 8 symbols and in outer iteration `it` lane p works on block it - p, one block
+// behind lane p - 1 (myers_half below).  (A skew of one SYMBOL was measured slower than one thread per sample, 190
+// against 115 cycles per symbol: the shuffle and the loads then sit on the dependent chain of every symbol.)
 
 // One block of up to 8 hypothesis symbols (packed little endian in sy) on this lane's WL words of a P-lane group.
 // Every horizontal dependency of the recurrence runs from low words to high words: the carry of the addition and the
@@ -288,7 +203,7 @@ __device__ __forceinline__ MyersCarry myers_block8(uint32_t (&VP)[WL], uint32_t 
 // (hrev[i] = h[n-1-i], n - n1 symbols) against the table of the reversed reference; the two halves run in DIFFERENT
 // warps (the phase is bound by the integer pipe of the scheduler partition a warp sits on -- two interleaved chains in
 // one warp took exactly as long as one chain of twice the length, measured -- so the halves must sit on different
-// partitions), each as the block-skewed pipeline of myers_row_split.  The column of a half is its VP / VN vectors
+// partitions), each as the block-skewed pipeline of myers_half.  The column of a half is its VP / VN vectors
 // (vertical differences): the backward warps write theirs out as prefix sums (G), and after a CTA barrier the forward
 // warps form theirs on the fly and take the minimum over the m + 1 meeting points.
 __host__ __device__ __forceinline__ int myers_split_point(int n) { return min(n, ((n + 1) / 2 + 7) & ~7); }
