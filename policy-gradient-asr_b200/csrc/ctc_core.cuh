@@ -1189,12 +1189,15 @@ __device__ __forceinline__ void ctc_grad_worker(int g, const float* tile, const 
 // B-worker one named barrier per block (gam_full); B-worker -> A-workers a release/acquire counter in shared memory
 // per matrix buffer (the B-worker is a block period ahead, so the wait is normally a single load).
 // =====================================================================================================
+#ifndef PGASR_BW_GA
+#define PGASR_BW_GA 4
+#endif
 namespace pgasr {
 
 // Warp w of the CTA runs on scheduler partition w % 4.  The walkers are warps 0 and 1; the occupancy (A) workers -- the
 // fp64 work -- sit on partitions 2 and 3 only (warps 2,3,6,7,10,11,14,15: four per direction), the row (B) workers
 // share the walkers' partitions (integer and shared-memory work), and the two warps left over idle at the barriers.
-constexpr int kBwGA = 4;          // A-workers per direction
+constexpr int kBwGA = PGASR_BW_GA;          // A-workers per direction (4: partitions 2/3 only; 5: the spare warp too)
 constexpr int kBwGB = 2;          // B-workers per direction (= matrix buffers per direction), at most 3
 constexpr int kBwNB = 2 * kBwGA;  // frames per ring batch: two per A-worker
 constexpr int kBwBB = 32 / kBwNB; // ring batches per block

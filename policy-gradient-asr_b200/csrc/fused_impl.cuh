@@ -110,7 +110,7 @@ __device__ __forceinline__ int cdf_count32(const float (&c)[32], float tau) {
 // workers that do both; up to 8 states per lane, tile in shared memory, 512 threads.
 template <int SPL, int kThreads, bool kGT, bool kBW = false>
 __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last, unsigned long long* s_mbar) {
-    static_assert(!kBW || (!kGT && SPL <= 8 && kThreads == 512 && kBwGA == 4 && kBwGB <= 3), "block workers: tile mode only");
+    static_assert(!kBW || (!kGT && SPL <= 8 && kThreads == 512 && (kBwGA == 4 || (kBwGA == 5 && kBwGB == 2)) && kBwGB <= 3), "block workers: tile mode only");
     constexpr int G = (kThreads / 32 - 2) / 2;             // gradient workers per direction
     constexpr int kPer = (kBatchOf<SPL> + G - 1) / G;      // frames of a batch per worker
     constexpr int kMidThreads = 32 * (2 + 2 * G);
@@ -301,7 +301,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
             unsigned long long* done_d = bw_done + dirx * kBwGB;
             const int bar_g = al ? 10 : 13;
             const int bj = (!(w & 1) && w >= 2 && (w >> 1) - 1 < kBwGB) ? (w >> 1) - 1 : -1;
-            const int ga = (w & 1) ? (w >> 1) : -1;
+            const int ga = (w & 1) ? (w >> 1) : (kBwGA == 5 && w == 6) ? 4 : -1;
             const unsigned* list_w = bw_lists + (dirx * kBwGB + max(bj, 0)) * kBwListWords;
             if (warp == 0)
                 ctc_walk_tile<SPL, kBwGA, true, false, kBwNB>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid);
