@@ -67,7 +67,9 @@ __device__ __forceinline__ float exp_spec(float x0) {
     y = __fadd_rn(y, 1.0f);
     int ni = (int)n;
     float scale = __int_as_float((ni + 127) << 23);
-    return x0 >= -87.0f ? __fmul_rn(y, scale) : 0.0f;
+    // (a multiplication by 1 or 0, not a select: the compiler turns "cond ? value : 0" back into a branch around the
+    // whole polynomial; y * scale is finite and >= 0, so the product is exact: the value itself or +0)
+    return __fmul_rn(__fmul_rn(y, scale), x0 >= -87.0f ? 1.0f : 0.0f);
 }
 
 // Philox4x32-10 (Salmon et al. 2011).  Counter (t, b, k/4, 'PGAS'), key = seed.

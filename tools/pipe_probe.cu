@@ -7,7 +7,8 @@ template <int OP, int CH>
 __global__ void probe(double* out, long long* cyc, int iters, double seed) {
     double a[CH];
     float f[CH];
-    for (int c = 0; c < CH; ++c) { a[c] = seed + c * 1e-3 + threadIdx.x * 1e-6; f[c] = (float)a[c]; }
+    unsigned u[CH];
+    for (int c = 0; c < CH; ++c) { a[c] = seed + c * 1e-3 + threadIdx.x * 1e-6; f[c] = (float)a[c]; u[c] = (unsigned)(c * 977 + threadIdx.x); }
     double m = 1.0000001, b = 1e-9;
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
@@ -19,11 +20,13 @@ __global__ void probe(double* out, long long* cyc, int iters, double seed) {
             if (OP == 3) f[c] = fmaf(f[c], 1.0000001f, 1e-9f);
             if (OP == 4) f[c] = exp2f(f[c]) * 0.25f;      // MUFU.EX2 + FMUL
             if (OP == 5) f[c] = __log2f(f[c]) + 3.0f;     // MUFU.LG2 + FADD
+            if (OP == 6) f[c] = __fadd_rn(__fmul_rn(f[c], 1.0000001f), 1e-9f);   // FMUL + FADD, never fused (the sampler's arithmetic)
+            if (OP == 7) { u[c] = (u[c] ^ 0x9E3779B9u) + (u[c] >> 7); }          // LOP3 + SHF + IADD3 (the edit distance's arithmetic)
         }
     }
     long long t1 = clock64();
     double s = 0;
-    for (int c = 0; c < CH; ++c) s += a[c] + f[c];
+    for (int c = 0; c < CH; ++c) s += a[c] + f[c] + (double)u[c];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
@@ -62,5 +65,10 @@ int main() {
     // saturate: 32 warps per SM
     run<0, 8>("dadd", 1024, 148); run<2, 8>("dfma", 1024, 148); run<3, 8>("ffma", 1024, 148);
     run<4, 8>("ex2", 1024, 148); run<5, 8>("lg2", 1024, 148);
+    // what one scheduler partition issues: 1, 4 and 8 warps per partition, 8 independent chains per thread
+    run<3, 8>("ffma", 128, 148); run<3, 8>("ffma", 512, 148);
+    run<6, 8>("fmul+fadd", 128, 148); run<6, 8>("fmul+fadd", 512, 148); run<6, 8>("fmul+fadd", 1024, 148);
+    run<7, 8>("lop+shf+iadd", 128, 148); run<7, 8>("lop+shf+iadd", 512, 148); run<7, 8>("lop+shf+iadd", 1024, 148);
+    run<2, 8>("dfma", 512, 148);
     return 0;
 }
