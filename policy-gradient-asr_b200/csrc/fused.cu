@@ -70,12 +70,12 @@ static size_t ctc_role_smem(int T, int V, int spl, int threads, bool gt) {
 }
 
 static size_t pg_cdf_bytes(int threads) { return (size_t)threads * 33 * sizeof(float) + 16; }
-static size_t pg_role_smem(int T, int V, int K, int spl, int threads, bool stream, bool togo = false, bool cdf = false) {
+// (mirrors the carve-up of fused_pg_role: the tile, one block per utterance of the CTA, reward-to-go arrays, CDF rows)
+static size_t pg_role_smem(int T, int V, int K, int spl, int threads, bool stream, bool togo = false, bool cdf = false, int nutt = 1) {
     const int Tp = (T + 15) & ~15, W = spl / 2;
-    const int Tp2 = (T / 2 + 16) & ~15;
-    size_t pg = (stream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15)) + (size_t)2 * K * Tp + (size_t)K * Tp2 +
-                (size_t)2 * (V + 1) * W * 4 + (size_t)((K + 7) & ~7) * (W * 32 + 2) * 2 + 16;
-    pg += (size_t)(threads / 32) * kFusedMaxK * 8 + 3 * kFusedMaxK * 4 + 16 + 16;
+    const size_t ub = W == 2 ? pg_u_bytes<2, 512>(T, V, K) : W == 4 ? pg_u_bytes<4, 512>(T, V, K) :
+                      W == 8 ? pg_u_bytes<8, 512>(T, V, K) : pg_u_bytes<16, 256>(T, V, K);
+    size_t pg = (stream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15)) + (size_t)nutt * ub + 16;
     // reward-to-go: log-sum-exp per frame, chunk counters, the last column / reward-to-go of every sample (int16)
     if (togo) pg += (size_t)Tp * 4 + (size_t)(threads / 32) * 64 * 4 + (size_t)K * (Tp + 16) * 2;
     if (cdf) pg += pg_cdf_bytes(threads);
@@ -125,7 +125,7 @@ size_t fused_workspace_bytes(int B, int T, int V, int K, int Lmax) {
 }
 
 // a.do_pg must be 0 when the PG role does not fit (fused_capability bit 1)
-int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
+int fused_step(FusedArgs& a, void* workspace, cudaStream_t st, bool throughput) {
     const FusedPlan pl = fused_plan(a.T, a.V, a.K, a.Lmax);
     if (!pl.ctc_ok || (a.do_pg && !pl.pg_ok)) return PGASR_ERR_UNSUPPORTED;
     const FusedWs w = fused_ws(a.B, a.T, a.V, pl.spl, pl.gt);
@@ -154,8 +154,16 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st) {
     static const bool no_bulk_tile = getenv("PGASR_NO_BULK_TILE") != nullptr;
     a.bulk_tile = !no_bulk_tile && (((size_t)a.T * a.V * 4) & 15) == 0 && ((reinterpret_cast<uintptr_t>(a.logits) & 15) == 0);
     a.cdf_smem = 0;
+    a.pg_pair = 0;
     if (a.do_pg) {
-        size_t pg = pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream, togo);
+        // two utterances per PG CTA (their edit distances side by side) when the step is one of several in flight and both
+        // blocks fit: measured 39.3 -> 36.5 us per step overlapped, but 58 -> 63 us for a step on its own (the pair CTA
+        // outlasts the CTC CTA), hence not for single steps.  PGASR_NO_PAIR=1: never (A/B)
+        static const bool no_pair = getenv("PGASR_NO_PAIR") != nullptr;
+        if (throughput && !no_pair && !stream && !togo && a.B >= 2 && a.V <= 32 &&
+            pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream, togo, true, 2) <= kFusedSmemLimit)
+            a.pg_pair = 1;
+        size_t pg = pg_role_smem(a.T, a.V, a.K, pl.spl, pl.threads, stream, togo, false, a.pg_pair ? 2 : 1);
         if (pg > kFusedSmemLimit) return PGASR_ERR_UNSUPPORTED;
         // the CDF rows in shared memory when they fit next to everything else (PGASR_NO_CDF_SMEM=1: register path, A/B)
         static const bool no_cdf = getenv("PGASR_NO_CDF_SMEM") != nullptr;

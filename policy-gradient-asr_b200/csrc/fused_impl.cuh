@@ -342,33 +342,57 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
 // ------------------------------------------------------------------------------------------------ PG role
 // kStream (long utterances): no [T][V] tile in shared memory -- a thread reads its frame's logits straight from
 // global memory, and the gradient rows are formed in registers and added to dlogits row by row.
+// A PG CTA serves `nutt` utterances b0, b0 + 1 (two in the common mode, a.pg_pair): the sampling of the two runs one
+// after the other on the one logits tile buffer, but their edit distances -- the phase that keeps only four warps of
+// the CTA busy -- run side by side, so the pair costs one edit-distance phase instead of two.
+struct PgU {
+    int b, Tb, m;
+    uint8_t *samples_s, *hyp_s, *hrev_s;
+    uint32_t *peq, *peq_r;
+    int16_t* fg_s;
+    double* warp_acc;
+    float* adv_s;
+    int *hlen_s, *dist_s;
+    float* misc_s;
+};
 template <int W, int kThreads, bool kStream>
-__device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw, unsigned* s_last, unsigned long long* s_mbar) {
+__device__ void fused_pg_role(const FusedArgs& a, int b0, int nutt, unsigned char* smem_raw, unsigned* s_last,
+                              unsigned long long* s_mbar) {
     constexpr int kWarps = kThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = a.T, V = a.V, K = a.K;
     const int Tp = (T + 15) & ~15;
-    int Tb = a.in_len ? a.in_len[b] : T;
-    Tb = min(max(Tb, 0), T);
-    int m = a.tgt_len ? a.tgt_len[b] : a.Lmax;
-    m = min(max(m, 0), a.Lmax);
-
-    // shared-memory carve-up
-    float* ztile = reinterpret_cast<float*>(smem_raw);                                // [T][V] (tile mode only)
-    size_t off = kStream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15);
-    uint8_t* samples_s = smem_raw + off;            off += (size_t)K * Tp;            // [K][Tp]
-    uint8_t* hyp_s = smem_raw + off;                off += (size_t)K * Tp;            // [K][Tp]
     const int Tp2 = (T / 2 + 16) & ~15;
-    uint8_t* hrev_s = smem_raw + off;               off += (size_t)K * Tp2;           // [K][Tp2] second halves, reversed
-    uint32_t* peq = reinterpret_cast<uint32_t*>(smem_raw + off); off += (size_t)(V + 1) * W * 4;
-    uint32_t* peq_r = reinterpret_cast<uint32_t*>(smem_raw + off); off += (size_t)(V + 1) * W * 4;   // reversed transcript
-    int16_t* fg_s = reinterpret_cast<int16_t*>(smem_raw + off);  off += (size_t)((K + 7) & ~7) * (W * 32 + 2) * 2;   // (idle groups of the last warp get their own scratch)
-    off = (off + 15) & ~(size_t)15;
-    double* warp_acc = reinterpret_cast<double*>(smem_raw + off); off += (size_t)kWarps * kFusedMaxK * 8;   // log-prob partial sums
-    float* adv_s = reinterpret_cast<float*>(smem_raw + off);     off += kFusedMaxK * 4;
-    int* hlen_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
-    int* dist_s = reinterpret_cast<int*>(smem_raw + off);        off += kFusedMaxK * 4;
-    float* misc_s = reinterpret_cast<float*>(smem_raw + off);    off += 16;          // [0] sum of advantages
+
+    // shared-memory carve-up: the logits tile (shared by the utterances of the CTA), one block per utterance, then the
+    // reward-to-go arrays and the CDF rows
+    float* ztile = reinterpret_cast<float*>(smem_raw);                                // [T][V] (tile mode only)
+    const size_t off0 = kStream ? 0 : (((size_t)T * V * 4 + 15) & ~(size_t)15);
+    const size_t ubytes = pg_u_bytes<W, kThreads>(T, V, K);
+    auto pg_u = [&](int uu) {
+        PgU X;
+        X.b = b0 + uu;
+        int Tb = a.in_len ? a.in_len[X.b] : T;
+        X.Tb = min(max(Tb, 0), T);
+        int m = a.tgt_len ? a.tgt_len[X.b] : a.Lmax;
+        X.m = min(max(m, 0), a.Lmax);
+        unsigned char* p = smem_raw + off0 + (size_t)uu * ubytes;
+        size_t off = 0;
+        X.samples_s = p + off;            off += (size_t)K * Tp;            // [K][Tp]
+        X.hyp_s = p + off;                off += (size_t)K * Tp;            // [K][Tp]
+        X.hrev_s = p + off;               off += (size_t)K * Tp2;           // [K][Tp2] second halves, reversed
+        X.peq = reinterpret_cast<uint32_t*>(p + off);   off += (size_t)(V + 1) * W * 4;
+        X.peq_r = reinterpret_cast<uint32_t*>(p + off); off += (size_t)(V + 1) * W * 4;   // reversed transcript
+        X.fg_s = reinterpret_cast<int16_t*>(p + off);   off += (size_t)((K + 7) & ~7) * (W * 32 + 2) * 2;   // (idle groups of the last warp get their own scratch)
+        off = (off + 15) & ~(size_t)15;
+        X.warp_acc = reinterpret_cast<double*>(p + off); off += (size_t)kWarps * kFusedMaxK * 8;   // log-prob partial sums
+        X.adv_s = reinterpret_cast<float*>(p + off);     off += kFusedMaxK * 4;
+        X.hlen_s = reinterpret_cast<int*>(p + off);      off += kFusedMaxK * 4;
+        X.dist_s = reinterpret_cast<int*>(p + off);      off += kFusedMaxK * 4;
+        X.misc_s = reinterpret_cast<float*>(p + off);    // [0] sum of advantages
+        return X;
+    };
+    size_t off = off0 + (size_t)nutt * ubytes;
     // reward-to-go mode: log-sum-exp of every frame (P1 -> P5) and, per sample, the last column of the edit-distance
     // table c[i] = ED(ref, hyp[:i]) (int16, i = 0..n), later overwritten in place by the reward-to-go of every frame
     const bool togo = a.reward_mode == PGASR_REWARD_ED_TO_GO;
@@ -378,526 +402,623 @@ __device__ void fused_pg_role(const FusedArgs& a, int b, unsigned char* smem_raw
     int16_t* col_s = reinterpret_cast<int16_t*>(smem_raw + off); if (togo) off += (size_t)K * Tc * 2;   // [K][Tc]
     off = (off + 15) & ~(size_t)15;
     float* cdf_s = reinterpret_cast<float*>(smem_raw + off);     // [kThreads][33] (a.cdf_smem)
+    unsigned nload = 0;                                    // bulk tile loads so far (the mbarrier's phase)
+    int ref_rr[2][2];
 
-    const bool dbg = b == 0 && threadIdx.x == 0;
-    (void)dbg;
-    PGASR_STAMP(dbg, 30);
-    // ---- P0: logits tile -> shared memory ------------------------------------------------------
-    const float* lg = a.logits + (size_t)b * T * V;
-    if (!kStream && a.bulk_tile) {
-        if (threadIdx.x == 0) bulk_load_tile(ztile, lg, (unsigned)((size_t)T * V * 4), s_mbar);
-    } else if (!kStream) {
-        if ((((size_t)T * V * 4) & 15) == 0) {
-            const int n16 = T * V / 4;
-            for (int i = threadIdx.x; i < n16; i += kThreads)
-                cp_async16(reinterpret_cast<char*>(ztile) + (size_t)i * 16, reinterpret_cast<const char*>(lg) + (size_t)i * 16);
-        } else {
-            for (int i = threadIdx.x; i < T * V; i += kThreads) cp_async4(ztile + i, lg + i);
+    // ======== sampling, one utterance after the other ========
+    for (int uu = 0; uu < nutt; ++uu) {
+        const PgU X = pg_u(uu);
+        const int b = X.b, Tb = X.Tb, m = X.m;
+        uint8_t* const samples_s = X.samples_s; uint8_t* const hyp_s = X.hyp_s; uint8_t* const hrev_s = X.hrev_s;
+        uint32_t* const peq = X.peq; uint32_t* const peq_r = X.peq_r; int16_t* const fg_s = X.fg_s;
+        double* const warp_acc = X.warp_acc; float* const adv_s = X.adv_s; int* const hlen_s = X.hlen_s;
+        int* const dist_s = X.dist_s; float* const misc_s = X.misc_s;
+        const float* const lg = a.logits + (size_t)b * T * V;
+        const int32_t* const ref = a.targets + (size_t)b * a.Lmax;
+        const bool dbg = b == 0 && threadIdx.x == 0;
+        (void)dbg; (void)samples_s; (void)hyp_s; (void)hrev_s; (void)peq; (void)peq_r; (void)fg_s; (void)warp_acc; (void)adv_s;
+        (void)hlen_s; (void)dist_s; (void)misc_s; (void)lg; (void)ref; (void)Tb; (void)m;
+        int (&ref_r)[2] = ref_rr[uu];
+        PGASR_STAMP(dbg, 30);
+        // ---- P0: logits tile -> shared memory ------------------------------------------------------
+        if (!kStream && a.bulk_tile) {
+            if (threadIdx.x == 0) bulk_load_tile(ztile, lg, (unsigned)((size_t)T * V * 4), s_mbar);
+        } else if (!kStream) {
+            if ((((size_t)T * V * 4) & 15) == 0) {
+                const int n16 = T * V / 4;
+                for (int i = threadIdx.x; i < n16; i += kThreads)
+                    cp_async16(reinterpret_cast<char*>(ztile) + (size_t)i * 16, reinterpret_cast<const char*>(lg) + (size_t)i * 16);
+            } else {
+                for (int i = threadIdx.x; i < T * V; i += kThreads) cp_async4(ztile + i, lg + i);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
-    }
-    // the transcript may live in mapped host memory: fetch it now, it is needed after the sampling phase
-    const int32_t* ref = a.targets + (size_t)b * a.Lmax;
-    int ref_r[2];
+        // the transcript may live in mapped host memory: fetch it now, it is needed after the sampling phase
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int j = threadIdx.x + q * kThreads;
-        ref_r[q] = j < m ? ref[j] : -1;
-    }
-    for (int i = threadIdx.x; i < kWarps * kFusedMaxK; i += kThreads) warp_acc[i] = 0.0;
-    for (int i = threadIdx.x; i < (V + 1) * W; i += kThreads) { peq[i] = 0u; peq_r[i] = 0u; }
-    if (!kStream && a.bulk_tile) mbar_wait(s_mbar, 0u);
-    cp_async_wait<0>();
-    __syncthreads();
+        for (int q = 0; q < 2; ++q) {
+            const int j = threadIdx.x + q * kThreads;
+            ref_r[q] = j < m ? ref[j] : -1;
+        }
+        for (int i = threadIdx.x; i < kWarps * kFusedMaxK; i += kThreads) warp_acc[i] = 0.0;
+        for (int i = threadIdx.x; i < (V + 1) * W; i += kThreads) { peq[i] = 0u; peq_r[i] = 0u; }
+        if (!kStream && a.bulk_tile) mbar_wait(s_mbar, nload++ & 1u);
+        cp_async_wait<0>();
+        __syncthreads();
 
-    PGASR_STAMP(dbg, 31);
-    // ---- P1: softmax CDF + K draws, one thread per frame (DESIGN.md "sampler spec") ------------
-    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-    for (int t0 = 0; t0 < T; t0 += kThreads) {
-        const int t = t0 + threadIdx.x;
-        const bool live = t < Tb;
-        const float* z = (kStream ? lg : ztile) + (size_t)(live ? t : 0) * V;
-        // one code path per alphabet width: the CDF lives in 32 registers (V <= 32, the common case) or in 64
-        auto sample_frame = [&](auto vp_tag) {
-            constexpr int VPW = decltype(vp_tag)::value;
-            float cdf[VPW];
-            float mx = -INFINITY, S = 0.0f, logS = 0.0f;
-            if (live) {
-#pragma unroll
-                for (int v = 0; v < VPW; ++v) cdf[v] = v < V ? z[v] : -INFINITY;
-#pragma unroll
-                for (int v = 0; v < VPW; ++v) mx = fmaxf(mx, cdf[v]);
-                float c = 0.0f;
-#pragma unroll
-                for (int v = 0; v < VPW; ++v) {
-                    if (v < V) c = __fadd_rn(c, exp_spec(__fsub_rn(cdf[v], mx)));
-                    cdf[v] = c;
-                }
-                S = c;
-                logS = logf(S);
-                if (togo) lz_s[t] = mx + logS;
-            }
-            uint4 rnd = make_uint4(0, 0, 0, 0);
-            for (int k = 0; k < K; ++k) {
-                float term = 0.0f;
-                int pi = 0;
+
+        PGASR_STAMP(dbg, 31);
+        // ---- P1: softmax CDF + K draws, one thread per frame (DESIGN.md "sampler spec") ------------
+        const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        for (int t0 = 0; t0 < T; t0 += kThreads) {
+            const int t = t0 + threadIdx.x;
+            const bool live = t < Tb;
+            const float* z = (kStream ? lg : ztile) + (size_t)(live ? t : 0) * V;
+            // one code path per alphabet width: the CDF lives in 32 registers (V <= 32, the common case) or in 64
+            auto sample_frame = [&](auto vp_tag) {
+                constexpr int VPW = decltype(vp_tag)::value;
+                float cdf[VPW];
+                float mx = -INFINITY, S = 0.0f, logS = 0.0f;
                 if (live) {
-                    float u;
-                    if (a.uniforms) {
-                        u = __ldg(a.uniforms + ((size_t)b * K + k) * T + t);
-                    } else {
-                        if ((k & 3) == 0)
-                            rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k >> 2), 0x50474153u), key);
-                        const uint32_t x = (k & 3) == 0 ? rnd.x : (k & 3) == 1 ? rnd.y : (k & 3) == 2 ? rnd.z : rnd.w;
-                        u = u32_to_uniform(x);
-                    }
-                    const float tau = __fmul_rn(u, S);
-                    // (entries V.. of cdf[] repeat S, so the count over all entries differs from the spec's count
-                    // over V entries only when tau == S, where both clamp to V - 1)
-                    int cnt;
-                    if constexpr (VPW == 32) {
-                        cnt = cdf_count32(cdf, tau);
-                    } else {
-                        const bool hi = cdf[31] <= tau;           // the CDF is non-decreasing: pick the half, search it
-                        float half[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) half[i] = hi ? cdf[32 + i] : cdf[i];
-                        cnt = (hi ? 32 : 0) + cdf_count32(half, tau);
+                    for (int v = 0; v < VPW; ++v) cdf[v] = v < V ? z[v] : -INFINITY;
+#pragma unroll
+                    for (int v = 0; v < VPW; ++v) mx = fmaxf(mx, cdf[v]);
+                    float c = 0.0f;
+#pragma unroll
+                    for (int v = 0; v < VPW; ++v) {
+                        if (v < V) c = __fadd_rn(c, exp_spec(__fsub_rn(cdf[v], mx)));
+                        cdf[v] = c;
                     }
-                    pi = min(cnt, V - 1);
-                    term = (z[pi] - mx) - logS;
+                    S = c;
+                    logS = logf(S);
+                    if (togo) lz_s[t] = mx + logS;
                 }
-                if (t < T) {
-                    samples_s[(size_t)k * Tp + t] = (uint8_t)pi;
-                    if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi;
-                }
-                // the warp's 32 terms in ONE instruction: 2^-19 fixed point (a term lies in [-92, 0]: the sum of 32 fits an
-                // int32; the rounding, 1e-6 per frame, is far inside the 1e-4 the log-probabilities are checked to)
-                const int ti = __reduce_add_sync(kFull, __float2int_rn(term * 524288.0f));
-                if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)ti * (1.0 / 524288.0);   // across passes and warps in fp64: log p ~ -1000
-            }
-        };
-        if (a.cdf_smem) {
-            // The CDF row of the frame in shared memory (33 floats: odd stride, a thread's walk along its row never
-            // collides with its neighbours'), built and searched by ROLLED loops: the fully unrolled register version
-            // is ~2000 straight-line instructions per thread, and with every warp streaming through them once the phase
-            // was bound by instruction fetch (no_inst was half of its stall samples).  Same arithmetic, same counts.
-            float* cr = cdf_s + (size_t)threadIdx.x * 33;       // (one row per thread, reused by every pass)
-            float mx = -INFINITY, S = 0.0f, logS = 0.0f;
-            if (live) {
-#pragma unroll 2
-                for (int v = 0; v < V; ++v) mx = fmaxf(mx, z[v]);
-                // four classes at a time: the four exp chains are independent, only the running sum is sequential
-                // (a thread's chain of ~25 dependent fp32 operations per class left the issue slots idle: 290 cycles
-                // per class with four warps per scheduler, measured).  Entries V..31 repeat S.
-                float c = 0.0f;
-#pragma unroll 1
-                for (int v = 0; v < 32; v += 4) {
-                    float e[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) e[u] = exp_spec(__fsub_rn(z[min(v + u, V - 1)], mx));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        c = v + u < V ? __fadd_rn(c, e[u]) : c;
-                        cr[v + u] = c;
-                    }
-                }
-                S = c;
-                logS = logf(S);
-                if (togo) lz_s[t] = mx + logS;
-            }
-            PGASR_STAMP(dbg && t0 == 0, 60);
-#pragma unroll 1
-            for (int k0 = 0; k0 < K; k0 += 4) {           // four draws (one Philox block) side by side
-                float term[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                int pi[4] = {0, 0, 0, 0};
-                if (live) {
-                    float tau[4];
-                    uint4 rnd = make_uint4(0, 0, 0, 0);
-                    if (!a.uniforms)
-                        rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k0 >> 2), 0x50474153u), key);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float un;
-                        if (a.uniforms) un = k0 + u < K ? __ldg(a.uniforms + ((size_t)b * K + k0 + u) * T + t) : 0.0f;
-                        else un = u32_to_uniform(u == 0 ? rnd.x : u == 1 ? rnd.y : u == 2 ? rnd.z : rnd.w);
-                        tau[u] = __fmul_rn(un, S);
-                    }
-                    int cnt[4] = {0, 0, 0, 0};            // #{v < 32 : cdf[v] <= tau}, the CDF is non-decreasing
-#pragma unroll
-                    for (int h = 16; h > 0; h >>= 1)
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) cnt[u] += cr[cnt[u] + h - 1] <= tau[u] ? h : 0;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        pi[u] = min(cnt[u], V - 1);
-                        term[u] = k0 + u < K ? (z[pi[u]] - mx) - logS : 0.0f;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int k = k0 + u;
-                    if (k < K) {                          // (warp uniform)
-                        if (t < T) {
-                            samples_s[(size_t)k * Tp + t] = (uint8_t)pi[u];
-                            if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi[u];
+                uint4 rnd = make_uint4(0, 0, 0, 0);
+                for (int k = 0; k < K; ++k) {
+                    float term = 0.0f;
+                    int pi = 0;
+                    if (live) {
+                        float u;
+                        if (a.uniforms) {
+                            u = __ldg(a.uniforms + ((size_t)b * K + k) * T + t);
+                        } else {
+                            if ((k & 3) == 0)
+                                rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k >> 2), 0x50474153u), key);
+                            const uint32_t x = (k & 3) == 0 ? rnd.x : (k & 3) == 1 ? rnd.y : (k & 3) == 2 ? rnd.z : rnd.w;
+                            u = u32_to_uniform(x);
                         }
-                        const int ti = __reduce_add_sync(kFull, __float2int_rn(term[u] * 524288.0f));
-                        if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)ti * (1.0 / 524288.0);
+                        const float tau = __fmul_rn(u, S);
+                        // (entries V.. of cdf[] repeat S, so the count over all entries differs from the spec's count
+                        // over V entries only when tau == S, where both clamp to V - 1)
+                        int cnt;
+                        if constexpr (VPW == 32) {
+                            cnt = cdf_count32(cdf, tau);
+                        } else {
+                            const bool hi = cdf[31] <= tau;           // the CDF is non-decreasing: pick the half, search it
+                            float half[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) half[i] = hi ? cdf[32 + i] : cdf[i];
+                            cnt = (hi ? 32 : 0) + cdf_count32(half, tau);
+                        }
+                        pi = min(cnt, V - 1);
+                        term = (z[pi] - mx) - logS;
+                    }
+                    if (t < T) {
+                        samples_s[(size_t)k * Tp + t] = (uint8_t)pi;
+                        if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi;
+                    }
+                    // the warp's 32 terms in ONE instruction: 2^-19 fixed point (a term lies in [-92, 0]: the sum of 32 fits an
+                    // int32; the rounding, 1e-6 per frame, is far inside the 1e-4 the log-probabilities are checked to)
+                    const int ti = __reduce_add_sync(kFull, __float2int_rn(term * 524288.0f));
+                    if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)ti * (1.0 / 524288.0);   // across passes and warps in fp64: log p ~ -1000
+                }
+            };
+            if (a.cdf_smem) {
+                // The CDF row of the frame in shared memory (33 floats: odd stride, a thread's walk along its row never
+                // collides with its neighbours'), built and searched by ROLLED loops: the fully unrolled register version
+                // is ~2000 straight-line instructions per thread, and with every warp streaming through them once the phase
+                // was bound by instruction fetch (no_inst was half of its stall samples).  Same arithmetic, same counts.
+                float* cr = cdf_s + (size_t)threadIdx.x * 33;       // (one row per thread, reused by every pass)
+                float mx = -INFINITY, S = 0.0f, logS = 0.0f;
+                if (live) {
+#pragma unroll 2
+                    for (int v = 0; v < V; ++v) mx = fmaxf(mx, z[v]);
+                    // four classes at a time: the four exp chains are independent, only the running sum is sequential
+                    // (a thread's chain of ~25 dependent fp32 operations per class left the issue slots idle: 290 cycles
+                    // per class with four warps per scheduler, measured).  Entries V..31 repeat S.
+                    float c = 0.0f;
+#pragma unroll 1
+                    for (int v = 0; v < 32; v += 4) {
+                        float e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) e[u] = exp_spec(__fsub_rn(z[min(v + u, V - 1)], mx));
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            c = v + u < V ? __fadd_rn(c, e[u]) : c;
+                            cr[v + u] = c;
+                        }
+                    }
+                    S = c;
+                    logS = logf(S);
+                    if (togo) lz_s[t] = mx + logS;
+                }
+                PGASR_STAMP(dbg && t0 == 0, 60);
+#pragma unroll 1
+                for (int k0 = 0; k0 < K; k0 += 4) {           // four draws (one Philox block) side by side
+                    float term[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    int pi[4] = {0, 0, 0, 0};
+                    if (live) {
+                        float tau[4];
+                        uint4 rnd = make_uint4(0, 0, 0, 0);
+                        if (!a.uniforms)
+                            rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k0 >> 2), 0x50474153u), key);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float un;
+                            if (a.uniforms) un = k0 + u < K ? __ldg(a.uniforms + ((size_t)b * K + k0 + u) * T + t) : 0.0f;
+                            else un = u32_to_uniform(u == 0 ? rnd.x : u == 1 ? rnd.y : u == 2 ? rnd.z : rnd.w);
+                            tau[u] = __fmul_rn(un, S);
+                        }
+                        int cnt[4] = {0, 0, 0, 0};            // #{v < 32 : cdf[v] <= tau}, the CDF is non-decreasing
+#pragma unroll
+                        for (int h = 16; h > 0; h >>= 1)
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) cnt[u] += cr[cnt[u] + h - 1] <= tau[u] ? h : 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            pi[u] = min(cnt[u], V - 1);
+                            term[u] = k0 + u < K ? (z[pi[u]] - mx) - logS : 0.0f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + u;
+                        if (k < K) {                          // (warp uniform)
+                            if (t < T) {
+                                samples_s[(size_t)k * Tp + t] = (uint8_t)pi[u];
+                                if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi[u];
+                            }
+                            const int ti = __reduce_add_sync(kFull, __float2int_rn(term[u] * 524288.0f));
+                            if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)ti * (1.0 / 524288.0);
+                        }
                     }
                 }
-            }
-        } else if (V <= 32) sample_frame(std::integral_constant<int, 32>{});
-        else sample_frame(std::integral_constant<int, 64>{});
-    }
-    __syncthreads();
-
-    PGASR_STAMP(dbg, 32);
-    // ---- P2: collapse (one warp per sample) and the match table of the transcript ---------------
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int j = threadIdx.x + q * kThreads;
-        const uint32_t c = (uint32_t)ref_r[q];
-        if (j < m && c < (uint32_t)V) {
-            atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
-            const int jr = m - 1 - j;
-            atomicOr(&peq_r[c * W + (jr >> 5)], 1u << (jr & 31));
-        }
-    }
-    for (int j = threadIdx.x + 2 * kThreads; j < m; j += kThreads) {     // (Lmax > 2 * threads: never with Lmax <= 511)
-        const uint32_t c = (uint32_t)ref[j];
-        if (c < (uint32_t)V) {
-            atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
-            const int jr = m - 1 - j;
-            atomicOr(&peq_r[c * W + (jr >> 5)], 1u << (jr & 31));
-        }
-    }
-    for (int k = warp; k < K; k += kWarps) {
-        const uint8_t* in = samples_s + (size_t)k * Tp;
-        uint8_t* o = hyp_s + (size_t)k * Tp;
-        int base = 0, carry = -1;
-        for (int t0 = 0; t0 < Tb; t0 += 32) {
-            const int t = t0 + lane;
-            const int x = t < Tb ? (int)in[t] : -2;
-            int p = __shfl_up_sync(kFull, x, 1);
-            if (lane == 0) p = carry;
-            const bool keep = t < Tb && x != p && x != a.blank;
-            const unsigned mask = __ballot_sync(kFull, keep);
-            if (keep) o[base + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)x;
-            base += __popc(mask);
-            carry = __shfl_sync(kFull, x, 31);
-        }
-        if (lane == 0) hlen_s[k] = base;
-        __syncwarp();
-        uint8_t* orv = hrev_s + (size_t)k * Tp2;          // the edit distance meets in the middle: second half backwards
-        for (int i = lane; i < base / 2; i += 32) orv[i] = o[base - 1 - i];
-    }
-    __syncthreads();
-
-    PGASR_STAMP(dbg, 33);
-    // ---- P3 (reward-to-go): one thread per sample, the whole last column; then one warp per sample turns it into the
-    // per-position rewards (output) and, in place, into the reward-to-go of every frame ----------------------------
-    if (togo) {
-        if ((int)threadIdx.x < K) {
-            const int k = threadIdx.x;
-            dist_s[k] = myers_row<W, true, int16_t>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, col_s + (size_t)k * Tc);
+            } else if (V <= 32) sample_frame(std::integral_constant<int, 32>{});
+            else sample_frame(std::integral_constant<int, 64>{});
         }
         __syncthreads();
+
+        PGASR_STAMP(dbg, 32);
+    }
+
+    // ======== collapse ========
+    for (int uu = 0; uu < nutt; ++uu) {
+        const PgU X = pg_u(uu);
+        const int b = X.b, Tb = X.Tb, m = X.m;
+        uint8_t* const samples_s = X.samples_s; uint8_t* const hyp_s = X.hyp_s; uint8_t* const hrev_s = X.hrev_s;
+        uint32_t* const peq = X.peq; uint32_t* const peq_r = X.peq_r; int16_t* const fg_s = X.fg_s;
+        double* const warp_acc = X.warp_acc; float* const adv_s = X.adv_s; int* const hlen_s = X.hlen_s;
+        int* const dist_s = X.dist_s; float* const misc_s = X.misc_s;
+        const float* const lg = a.logits + (size_t)b * T * V;
+        const int32_t* const ref = a.targets + (size_t)b * a.Lmax;
+        const bool dbg = b == 0 && threadIdx.x == 0;
+        (void)dbg; (void)samples_s; (void)hyp_s; (void)hrev_s; (void)peq; (void)peq_r; (void)fg_s; (void)warp_acc; (void)adv_s;
+        (void)hlen_s; (void)dist_s; (void)misc_s; (void)lg; (void)ref; (void)Tb; (void)m;
+        const int (&ref_r)[2] = ref_rr[uu];
+        // ---- P2: collapse (one warp per sample) and the match table of the transcript ---------------
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = threadIdx.x + q * kThreads;
+            const uint32_t c = (uint32_t)ref_r[q];
+            if (j < m && c < (uint32_t)V) {
+                atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+                const int jr = m - 1 - j;
+                atomicOr(&peq_r[c * W + (jr >> 5)], 1u << (jr & 31));
+            }
+        }
+        for (int j = threadIdx.x + 2 * kThreads; j < m; j += kThreads) {     // (Lmax > 2 * threads: never with Lmax <= 511)
+            const uint32_t c = (uint32_t)ref[j];
+            if (c < (uint32_t)V) {
+                atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));
+                const int jr = m - 1 - j;
+                atomicOr(&peq_r[c * W + (jr >> 5)], 1u << (jr & 31));
+            }
+        }
         for (int k = warp; k < K; k += kWarps) {
-            int16_t* c = col_s + (size_t)k * Tc;
-            const int n = hlen_s[k];
-            const int cn = c[n];
-            if (a.r_pos) {                                 // r_i = -(c[i+1] - c[i]), zero beyond the hypothesis
-                int8_t* rp = a.r_pos + ((size_t)b * K + k) * T;
-                for (int i = lane; i < T; i += 32) rp[i] = i < n ? (int8_t)(c[i] - c[i + 1]) : (int8_t)0;
-            }
-            __syncwarp();
-            // G_t = c[pos(t)] - c[n], pos(t) = symbols emitted at frames < t; frames from the end towards the start so
-            // that slot t can take G_t (every later read is at pos(t') <= t' < t)
             const uint8_t* in = samples_s + (size_t)k * Tp;
-            const int nch = (T + 31) / 32;
-            // emitted symbols before each chunk: one forward pass of ballots
-            int before = 0;
-            for (int ch = 0; ch < nch; ++ch) {
-                const int t = ch * 32 + lane;
+            uint8_t* o = hyp_s + (size_t)k * Tp;
+            int base = 0, carry = -1;
+            for (int t0 = 0; t0 < Tb; t0 += 32) {
+                const int t = t0 + lane;
                 const int x = t < Tb ? (int)in[t] : -2;
-                const int pv = t > 0 && t - 1 < Tb ? (int)in[t - 1] : -1;
-                const bool keep = t < Tb && x != pv && x != a.blank;
+                int p = __shfl_up_sync(kFull, x, 1);
+                if (lane == 0) p = carry;
+                const bool keep = t < Tb && x != p && x != a.blank;
                 const unsigned mask = __ballot_sync(kFull, keep);
-                if (lane == 0) warp_acc_i[warp * 64 + (ch & 63)] = before;   // (T <= 2048: at most 64 chunks)
-                before += __popc(mask);
+                if (keep) o[base + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)x;
+                base += __popc(mask);
+                carry = __shfl_sync(kFull, x, 31);
             }
+            if (lane == 0) hlen_s[k] = base;
             __syncwarp();
-            for (int ch = nch - 1; ch >= 0; --ch) {
-                const int t = ch * 32 + lane;
-                const int x = t < Tb ? (int)in[t] : -2;
-                const int pv = t > 0 && t - 1 < Tb ? (int)in[t - 1] : -1;
-                const bool keep = t < Tb && x != pv && x != a.blank;
-                const unsigned mask = __ballot_sync(kFull, keep);
-                const int pos = warp_acc_i[warp * 64 + (ch & 63)] + __popc(mask & ((1u << lane) - 1u));
-                const int g = t < Tb ? (int)c[pos] - cn : 0;
-                __syncwarp();
-                if (t < T) {
-                    c[t] = (int16_t)g;
-                    if (a.to_go) a.to_go[((size_t)b * K + k) * T + t] = (int16_t)g;
+            uint8_t* orv = hrev_s + (size_t)k * Tp2;          // the edit distance meets in the middle: second half backwards
+            for (int i = lane; i < base / 2; i += 32) orv[i] = o[base - 1 - i];
+        }
+    }
+    __syncthreads();
+
+    PGASR_STAMP(b0 == 0 && threadIdx.x == 0, 33);
+    // ======== edit distances: the utterances of the CTA side by side ========
+    if (togo) {                                            // (one utterance per CTA in this mode)
+        const int uu = 0;
+        const PgU X = pg_u(uu);
+        const int b = X.b, Tb = X.Tb, m = X.m;
+        uint8_t* const samples_s = X.samples_s; uint8_t* const hyp_s = X.hyp_s; uint8_t* const hrev_s = X.hrev_s;
+        uint32_t* const peq = X.peq; uint32_t* const peq_r = X.peq_r; int16_t* const fg_s = X.fg_s;
+        double* const warp_acc = X.warp_acc; float* const adv_s = X.adv_s; int* const hlen_s = X.hlen_s;
+        int* const dist_s = X.dist_s; float* const misc_s = X.misc_s;
+        const float* const lg = a.logits + (size_t)b * T * V;
+        const int32_t* const ref = a.targets + (size_t)b * a.Lmax;
+        const bool dbg = b == 0 && threadIdx.x == 0;
+        (void)dbg; (void)samples_s; (void)hyp_s; (void)hrev_s; (void)peq; (void)peq_r; (void)fg_s; (void)warp_acc; (void)adv_s;
+        (void)hlen_s; (void)dist_s; (void)misc_s; (void)lg; (void)ref; (void)Tb; (void)m;
+        // ---- P3 (reward-to-go): one thread per sample, the whole last column; then one warp per sample turns it into the
+        // per-position rewards (output) and, in place, into the reward-to-go of every frame ----------------------------
+        {
+            if ((int)threadIdx.x < K) {
+                const int k = threadIdx.x;
+                dist_s[k] = myers_row<W, true, int16_t>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, col_s + (size_t)k * Tc);
+            }
+            __syncthreads();
+            for (int k = warp; k < K; k += kWarps) {
+                int16_t* c = col_s + (size_t)k * Tc;
+                const int n = hlen_s[k];
+                const int cn = c[n];
+                if (a.r_pos) {                                 // r_i = -(c[i+1] - c[i]), zero beyond the hypothesis
+                    int8_t* rp = a.r_pos + ((size_t)b * K + k) * T;
+                    for (int i = lane; i < T; i += 32) rp[i] = i < n ? (int8_t)(c[i] - c[i + 1]) : (int8_t)0;
                 }
                 __syncwarp();
+                // G_t = c[pos(t)] - c[n], pos(t) = symbols emitted at frames < t; frames from the end towards the start so
+                // that slot t can take G_t (every later read is at pos(t') <= t' < t)
+                const uint8_t* in = samples_s + (size_t)k * Tp;
+                const int nch = (T + 31) / 32;
+                // emitted symbols before each chunk: one forward pass of ballots
+                int before = 0;
+                for (int ch = 0; ch < nch; ++ch) {
+                    const int t = ch * 32 + lane;
+                    const int x = t < Tb ? (int)in[t] : -2;
+                    const int pv = t > 0 && t - 1 < Tb ? (int)in[t - 1] : -1;
+                    const bool keep = t < Tb && x != pv && x != a.blank;
+                    const unsigned mask = __ballot_sync(kFull, keep);
+                    if (lane == 0) warp_acc_i[warp * 64 + (ch & 63)] = before;   // (T <= 2048: at most 64 chunks)
+                    before += __popc(mask);
+                }
+                __syncwarp();
+                for (int ch = nch - 1; ch >= 0; --ch) {
+                    const int t = ch * 32 + lane;
+                    const int x = t < Tb ? (int)in[t] : -2;
+                    const int pv = t > 0 && t - 1 < Tb ? (int)in[t - 1] : -1;
+                    const bool keep = t < Tb && x != pv && x != a.blank;
+                    const unsigned mask = __ballot_sync(kFull, keep);
+                    const int pos = warp_acc_i[warp * 64 + (ch & 63)] + __popc(mask & ((1u << lane) - 1u));
+                    const int g = t < Tb ? (int)c[pos] - cn : 0;
+                    __syncwarp();
+                    if (t < T) {
+                        c[t] = (int16_t)g;
+                        if (a.to_go) a.to_go[((size_t)b * K + k) * T + t] = (int16_t)g;
+                    }
+                    __syncwarp();
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
     } else
     // ---- P3: edit distance, P lanes per sample ---------------------------------------------------
     // (all K samples in the lanes of as few warps as possible: a Myers step is a chain of dependent integer
     // instructions, and lanes of one warp share them; one sample per warp was measured 3.6x slower.  The words of a
     // sample are spread over P lanes that run one block apart, see myers_half)
     if constexpr (W >= 4) {
-        // forward halves on the first nw warps, backward halves on the next nw (myers_core.cuh, "Meeting in the middle")
+        // per utterance: forward halves on nw warps, backward halves on the next nw (myers_core.cuh, "Meeting in the
+        // middle"); the utterances of the CTA next to each other when the warps suffice
         constexpr int P = 4;                              // lanes per sample
         const int nw = (K * P + 31) / 32;
         const bool bidir = 2 * nw <= kWarps;              // (K = 64 in the 256-thread variant: forward only, all of h)
-        uint32_t VPh[W / P], VNh[W / P];
-        int k = 0, p = 0, n = 0, n1 = 0;
-        if (warp < (bidir ? 2 : 1) * nw) {                // whole warps: the lanes shuffle with a full mask
-            const bool fwd = warp < nw;
-            const int tid = (int)threadIdx.x - (fwd ? 0 : nw * 32);
-            k = tid / P; p = tid % P;
-            const int kc = min(k, K - 1);
-            n = k < K ? hlen_s[kc] : 0;
-            n1 = bidir ? myers_split_point(n) : n;
-            const int nsym = fwd ? n1 : n - n1;
-            const int nmax = __reduce_max_sync(kFull, nsym);
-            myers_half<W, P, false>(fwd ? hyp_s + (size_t)kc * Tp : hrev_s + (size_t)kc * Tp2, nsym, fwd ? peq : peq_r, V, p, nmax,
-                             VPh, VNh);
-            if (!fwd) myers_store_column<W, P>(VPh, VNh, n - n1, p, fg_s + (size_t)k * (W * 32 + 2));
-        }
-        __syncthreads();
-        if (warp < nw) {
-            int d;
-            if (bidir) {
-                d = myers_meet<W, P>(VPh, VNh, n1, m, p, fg_s + (size_t)k * (W * 32 + 2));
-            } else {                                      // dp[n, m] = n + sum_{j<m} (VP_j - VN_j)
-                d = 0;
-#pragma unroll
-                for (int w = 0; w < W / P; ++w) {
-                    const int lo = (p * (W / P) + w) * 32;
-                    const uint32_t msk = m >= lo + 32 ? 0xffffffffu : (m > lo ? (1u << (m - lo)) - 1u : 0u);
-                    d += __popc(VPh[w] & msk) - __popc(VNh[w] & msk);
-                }
-#pragma unroll
-                for (int o = 1; o < P; o <<= 1) d += __shfl_xor_sync(kFull, d, o);
-                d += n;
+        const int wpu = (bidir ? 2 : 1) * nw;             // warps per utterance
+        const int ucon = nutt * wpu <= kWarps ? nutt : 1; // utterances side by side
+        for (int u0 = 0; u0 < nutt; u0 += ucon) {
+            uint32_t VPh[W / P], VNh[W / P];
+            int k = 0, p = 0, n = 0, n1 = 0;
+            const int uw = warp / wpu;                    // which of the concurrent utterances this warp serves
+            const bool mine = uw < ucon;
+            const int wl = warp - uw * wpu;               // warp within the utterance's group
+            const PgU X = pg_u(u0 + (mine ? uw : 0));
+            if (mine) {                                   // whole warps: the lanes shuffle with a full mask
+                const bool fwd = wl < nw;
+                const int tid = (wl - (fwd ? 0 : nw)) * 32 + lane;
+                k = tid / P; p = tid % P;
+                const int kc = min(k, K - 1);
+                n = k < K ? X.hlen_s[kc] : 0;
+                n1 = bidir ? myers_split_point(n) : n;
+                const int nsym = fwd ? n1 : n - n1;
+                const int nmax = __reduce_max_sync(kFull, nsym);
+                myers_half<W, P, false>(fwd ? X.hyp_s + (size_t)kc * Tp : X.hrev_s + (size_t)kc * Tp2, nsym, fwd ? X.peq : X.peq_r,
+                                        V, p, nmax, VPh, VNh);
+                if (!fwd) myers_store_column<W, P>(VPh, VNh, n - n1, p, X.fg_s + (size_t)k * (W * 32 + 2));
             }
-            if (k < K && p == 0) dist_s[k] = d;
+            __syncthreads();
+            if (mine && wl < nw) {
+                int d;
+                if (bidir) {
+                    d = myers_meet<W, P>(VPh, VNh, n1, X.m, p, X.fg_s + (size_t)k * (W * 32 + 2));
+                } else {                                  // dp[n, m] = n + sum_{j<m} (VP_j - VN_j)
+                    d = 0;
+#pragma unroll
+                    for (int w = 0; w < W / P; ++w) {
+                        const int lo = (p * (W / P) + w) * 32;
+                        const uint32_t msk = X.m >= lo + 32 ? 0xffffffffu : (X.m > lo ? (1u << (X.m - lo)) - 1u : 0u);
+                        d += __popc(VPh[w] & msk) - __popc(VNh[w] & msk);
+                    }
+#pragma unroll
+                    for (int o = 1; o < P; o <<= 1) d += __shfl_xor_sync(kFull, d, o);
+                    d += n;
+                }
+                if (k < K && p == 0) X.dist_s[k] = d;
+            }
         }
     } else {                                              // two words: one thread per sample is as fast (measured)
-        if ((int)threadIdx.x < K) {
-            const int k = threadIdx.x;
-            dist_s[k] = myers_row<W, false>(hyp_s + (size_t)k * Tp, hlen_s[k], peq, V, m, static_cast<int32_t*>(nullptr));
+        if ((int)threadIdx.x < nutt * K) {
+            const PgU X = pg_u((int)threadIdx.x / K);
+            const int k = (int)threadIdx.x % K;
+            X.dist_s[k] = myers_row<W, false>(X.hyp_s + (size_t)k * Tp, X.hlen_s[k], X.peq, V, X.m, static_cast<int32_t*>(nullptr));
         }
     }
     __syncthreads();
 
-    PGASR_STAMP(dbg, 34);
-    // ---- P4: rewards, baseline, advantages, loss term (warp 0) -----------------------------------
-    if (warp == 0) {
-        // rewards are fp32 by contract (bit exact with the oracle); baseline, advantage and the loss term are fp64:
-        // an fp32 rounding of A (1e-7 relative) times log p ~ -1000 would already show in the scalar loss
-        double sumR = 0.0;
-        for (int k = lane; k < K; k += 32) {
-            float R = -(float)dist_s[k];
-            if (a.reward_mode == PGASR_REWARD_NEG_CER) R = __fdiv_rn(R, (float)m);
-            if (togo) R = (float)(m - dist_s[k]);         // G_0 = c[0] - c[n]: what the whole hypothesis earned
-            adv_s[k] = R;
-            sumR += (double)R;
-        }
-        sumR = warp_sum(sumR);
-        double term = 0.0;
-        float sumA = 0.0f;
-        for (int k = lane; k < K; k += 32) {
-            const float R = adv_s[k];
-            double base = 0.0;
-            if (a.baseline_mode == PGASR_BASELINE_MEAN) base = sumR / (double)K;
-            else if (a.baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumR - (double)R) / (double)(K - 1) : 0.0;
-            else if (a.baseline_mode == PGASR_BASELINE_VALUE) base = (double)a.baseline_value;
-            const double Ad = (double)R - base;
-            const float A = (float)Ad;
-            double lp = 0.0;
-            for (int w = 0; w < kWarps; ++w) lp += warp_acc[w * kFusedMaxK + k];
-            term += -Ad * lp;
-            sumA += A;
-            adv_s[k] = A;
-            const size_t o = (size_t)b * K + k;
-            if (a.rewards) a.rewards[o] = R;
-            if (a.logp) a.logp[o] = (float)lp;
-            if (a.hyp_len) a.hyp_len[o] = hlen_s[k];
-            if (a.dist) a.dist[o] = dist_s[k];
-        }
-        term = warp_sum(term);
-        sumA = warp_sum(sumA);
-        if (lane == 0 && !togo) {                         // (reward-to-go: advantages are per frame, the loss term comes from P5)
-            a.loss_terms[b] = (float)term;
-            misc_s[0] = sumA;
+    // ======== rewards, baseline, advantages, loss terms: warp uu for utterance uu ========
+    if (warp < nutt) {
+        const int uu = warp;
+        const PgU X = pg_u(uu);
+        const int b = X.b, Tb = X.Tb, m = X.m;
+        uint8_t* const samples_s = X.samples_s; uint8_t* const hyp_s = X.hyp_s; uint8_t* const hrev_s = X.hrev_s;
+        uint32_t* const peq = X.peq; uint32_t* const peq_r = X.peq_r; int16_t* const fg_s = X.fg_s;
+        double* const warp_acc = X.warp_acc; float* const adv_s = X.adv_s; int* const hlen_s = X.hlen_s;
+        int* const dist_s = X.dist_s; float* const misc_s = X.misc_s;
+        const float* const lg = a.logits + (size_t)b * T * V;
+        const int32_t* const ref = a.targets + (size_t)b * a.Lmax;
+        const bool dbg = b == 0 && threadIdx.x == 0;
+        (void)dbg; (void)samples_s; (void)hyp_s; (void)hrev_s; (void)peq; (void)peq_r; (void)fg_s; (void)warp_acc; (void)adv_s;
+        (void)hlen_s; (void)dist_s; (void)misc_s; (void)lg; (void)ref; (void)Tb; (void)m;
+        PGASR_STAMP(dbg, 34);
+        // ---- P4: rewards, baseline, advantages, loss term (warp 0) -----------------------------------
+        {
+            // rewards are fp32 by contract (bit exact with the oracle); baseline, advantage and the loss term are fp64:
+            // an fp32 rounding of A (1e-7 relative) times log p ~ -1000 would already show in the scalar loss
+            double sumR = 0.0;
+            for (int k = lane; k < K; k += 32) {
+                float R = -(float)dist_s[k];
+                if (a.reward_mode == PGASR_REWARD_NEG_CER) R = __fdiv_rn(R, (float)m);
+                if (togo) R = (float)(m - dist_s[k]);         // G_0 = c[0] - c[n]: what the whole hypothesis earned
+                adv_s[k] = R;
+                sumR += (double)R;
+            }
+            sumR = warp_sum(sumR);
+            double term = 0.0;
+            float sumA = 0.0f;
+            for (int k = lane; k < K; k += 32) {
+                const float R = adv_s[k];
+                double base = 0.0;
+                if (a.baseline_mode == PGASR_BASELINE_MEAN) base = sumR / (double)K;
+                else if (a.baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumR - (double)R) / (double)(K - 1) : 0.0;
+                else if (a.baseline_mode == PGASR_BASELINE_VALUE) base = (double)a.baseline_value;
+                const double Ad = (double)R - base;
+                const float A = (float)Ad;
+                double lp = 0.0;
+                for (int w = 0; w < kWarps; ++w) lp += warp_acc[w * kFusedMaxK + k];
+                term += -Ad * lp;
+                sumA += A;
+                adv_s[k] = A;
+                const size_t o = (size_t)b * K + k;
+                if (a.rewards) a.rewards[o] = R;
+                if (a.logp) a.logp[o] = (float)lp;
+                if (a.hyp_len) a.hyp_len[o] = hlen_s[k];
+                if (a.dist) a.dist[o] = dist_s[k];
+            }
+            term = warp_sum(term);
+            sumA = warp_sum(sumA);
+            if (lane == 0 && !togo) {                         // (reward-to-go: advantages are per frame, the loss term comes from P5)
+                a.loss_terms[b] = (float)term;
+                misc_s[0] = sumA;
+            }
         }
     }
     __syncthreads();
 
-    PGASR_STAMP(dbg, 35);
-    // ---- P5: REINFORCE gradient tile, in place of the logits tile ---------------------------------
-    const float coef = a.w_pg / ((float)a.B * (float)K);
-    const bool dense = a.baseline_mode != PGASR_BASELINE_MEAN;   // sum_k A_k == 0 under the per-utterance mean
-    const float dense_c = coef * misc_s[0];
-    float* dlog_u = a.dlogits + (size_t)b * T * V;
-    if constexpr (kStream) {
-        // one thread per frame: the K sample ids into registers, then for every class the advantage mass that fell
-        // on it; the row is added to (or, without a CTC term, stored as) dlogits directly
+    // ======== gradient tiles and their way into dlogits, the utterance sampled last first (its logits are still in
+    // the tile buffer; an earlier one's are reloaded when the dense term needs them) ========
+    for (int uu = nutt - 1; uu >= 0; --uu) {
+        const PgU X = pg_u(uu);
+        const int b = X.b, Tb = X.Tb, m = X.m;
+        uint8_t* const samples_s = X.samples_s; uint8_t* const hyp_s = X.hyp_s; uint8_t* const hrev_s = X.hrev_s;
+        uint32_t* const peq = X.peq; uint32_t* const peq_r = X.peq_r; int16_t* const fg_s = X.fg_s;
+        double* const warp_acc = X.warp_acc; float* const adv_s = X.adv_s; int* const hlen_s = X.hlen_s;
+        int* const dist_s = X.dist_s; float* const misc_s = X.misc_s;
+        const float* const lg = a.logits + (size_t)b * T * V;
+        const int32_t* const ref = a.targets + (size_t)b * a.Lmax;
+        const bool dbg = b == 0 && threadIdx.x == 0;
+        (void)dbg; (void)samples_s; (void)hyp_s; (void)hrev_s; (void)peq; (void)peq_r; (void)fg_s; (void)warp_acc; (void)adv_s;
+        (void)hlen_s; (void)dist_s; (void)misc_s; (void)lg; (void)ref; (void)Tb; (void)m;
+        PGASR_STAMP(dbg, 35);
+        if (!kStream && uu != nutt - 1) {
+            if (a.baseline_mode != PGASR_BASELINE_MEAN) { // (the tile holds the previous utterance's gradient)
+                if (a.bulk_tile) {
+                    if (threadIdx.x == 0) bulk_load_tile(ztile, lg, (unsigned)((size_t)T * V * 4), s_mbar);
+                    mbar_wait(s_mbar, nload++ & 1u);
+                } else {
+                    for (int i = threadIdx.x; i < T * V; i += kThreads) ztile[i] = __ldg(lg + i);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- P5: REINFORCE gradient tile, in place of the logits tile ---------------------------------
+        const float coef = a.w_pg / ((float)a.B * (float)K);
+        const bool dense = a.baseline_mode != PGASR_BASELINE_MEAN;   // sum_k A_k == 0 under the per-utterance mean
+        const float dense_c = coef * misc_s[0];
+        float* dlog_u = a.dlogits + (size_t)b * T * V;
+        const bool final_u = uu == 0;                          // the last utterance this CTA finishes: it draws the done ticket
+        if constexpr (kStream) {
+            // one thread per frame: the K sample ids into registers, then for every class the advantage mass that fell
+            // on it; the row is added to (or, without a CTC term, stored as) dlogits directly
+            if (threadIdx.x == 0) {
+                if (a.do_ctc) {
+                    const unsigned* flag = a.ctrl + 4 + b;
+                    while (ld_acquire(flag) == 0u) __nanosleep(40);
+                }
+                if (final_u) draw_done_ticket(a, s_last);
+            }
+            __syncthreads();
+            PGASR_STAMP(dbg, 37);
+            for (int t = threadIdx.x; t < T; t += kThreads) {
+                float* out = dlog_u + (size_t)t * V;
+                if (t >= Tb) {
+                    if (!a.do_ctc)
+                        for (int v = 0; v < V; ++v) out[v] = 0.0f;
+                    continue;
+                }
+                float mx = 0.0f, sc = 0.0f;
+                const float* zr = lg + (size_t)t * V;
+                if (dense) {
+                    mx = -INFINITY;
+                    float ssum = 0.0f;
+                    for (int v = 0; v < V; ++v) mx = fmaxf(mx, zr[v]);
+                    for (int v = 0; v < V; ++v) ssum += __expf(zr[v] - mx);
+                    sc = dense_c / ssum;
+                }
+                for (int v = 0; v < V; ++v) {
+                    float g = dense ? __expf(zr[v] - mx) * sc : 0.0f;
+                    for (int k = 0; k < K; ++k)              // same order of subtractions as the tile mode: k ascending
+                        if (samples_s[(size_t)k * Tp + t] == v) g -= coef * adv_s[k];
+                    out[v] = a.do_ctc ? __ldcg(out + v) + g : g;
+                }
+            }
+            PGASR_STAMP(dbg, 38);
+        } else {
+        if (togo) {
+            // per-frame advantages A_kt = G_kt - b_kt (baseline over the K samples of the frame), the loss term
+            // -sum_kt A_kt log p_t(pi_kt) and the gradient row (1/BK) (p_tv sum_k A_kt - sum_k A_kt [pi_kt = v])
+            double lt = 0.0;
+            for (int t = threadIdx.x; t < T; t += kThreads) {
+                float* row = ztile + (size_t)t * V;
+                if (t < Tb) {
+                    const float lz = lz_s[t];
+                    int sumGi = 0;
+                    for (int k = 0; k < K; ++k) sumGi += (int)col_s[(size_t)k * Tc + t];
+                    const float sumG = (float)sumGi;
+                    auto adv_of = [&](int k) {
+                        const float G = (float)col_s[(size_t)k * Tc + t];
+                        float base = 0.0f;
+                        if (a.baseline_mode == PGASR_BASELINE_MEAN) base = sumG / (float)K;
+                        else if (a.baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumG - G) / (float)(K - 1) : 0.0f;
+                        else if (a.baseline_mode == PGASR_BASELINE_VALUE) base = a.baseline_value;
+                        return G - base;
+                    };
+                    float sumA = 0.0f;
+                    for (int k = 0; k < K; ++k) {
+                        const float A = adv_of(k);
+                        lt += -(double)A * (double)(row[samples_s[(size_t)k * Tp + t]] - lz);
+                        sumA += A;
+                    }
+                    if (dense) {
+                        const float sc = coef * sumA;
+                        for (int v = 0; v < V; ++v) row[v] = __expf(row[v] - lz) * sc;
+                    } else {
+                        for (int v = 0; v < V; ++v) row[v] = 0.0f;
+                    }
+                    for (int k = 0; k < K; ++k) row[samples_s[(size_t)k * Tp + t]] -= coef * adv_of(k);
+                } else {
+                    for (int v = 0; v < V; ++v) row[v] = 0.0f;
+                }
+            }
+            lt = warp_sum(lt);
+            __syncthreads();                                   // (warp_acc: the log-prob partial sums are consumed)
+            if (lane == 0) warp_acc[warp] = lt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < kWarps; ++w) tot += warp_acc[w];
+                a.loss_terms[b] = (float)tot;
+            }
+        } else
+        for (int t = threadIdx.x; t < T; t += kThreads) {
+            float* row = ztile + (size_t)t * V;
+            if (t < Tb) {
+                if (dense) {
+                    float mx = -INFINITY, s = 0.0f;
+                    for (int v = 0; v < V; ++v) mx = fmaxf(mx, row[v]);
+                    for (int v = 0; v < V; ++v) s += __expf(row[v] - mx);
+                    const float sc = dense_c / s;
+                    for (int v = 0; v < V; ++v) row[v] = __expf(row[v] - mx) * sc;
+                } else {
+                    for (int v = 0; v < V; ++v) row[v] = 0.0f;
+                }
+                for (int k = 0; k < K; ++k) row[samples_s[(size_t)k * Tp + t]] -= coef * adv_s[k];
+            } else {
+                for (int v = 0; v < V; ++v) row[v] = 0.0f;
+            }
+        }
+        __syncthreads();
+
+        PGASR_STAMP(dbg, 36);
+        // ---- P6: add the tile onto the CTC rows (or store it when there is no CTC term) ---------------
         if (threadIdx.x == 0) {
             if (a.do_ctc) {
                 const unsigned* flag = a.ctrl + 4 + b;
                 while (ld_acquire(flag) == 0u) __nanosleep(40);
             }
-            draw_done_ticket(a, s_last);
+            if (final_u) draw_done_ticket(a, s_last);
         }
         __syncthreads();
         PGASR_STAMP(dbg, 37);
-        for (int t = threadIdx.x; t < T; t += kThreads) {
-            float* out = dlog_u + (size_t)t * V;
-            if (t >= Tb) {
-                if (!a.do_ctc)
-                    for (int v = 0; v < V; ++v) out[v] = 0.0f;
-                continue;
-            }
-            float mx = 0.0f, sc = 0.0f;
-            const float* zr = lg + (size_t)t * V;
-            if (dense) {
-                mx = -INFINITY;
-                float ssum = 0.0f;
-                for (int v = 0; v < V; ++v) mx = fmaxf(mx, zr[v]);
-                for (int v = 0; v < V; ++v) ssum += __expf(zr[v] - mx);
-                sc = dense_c / ssum;
-            }
-            for (int v = 0; v < V; ++v) {
-                float g = dense ? __expf(zr[v] - mx) * sc : 0.0f;
-                for (int k = 0; k < K; ++k)              // same order of subtractions as the tile mode: k ascending
-                    if (samples_s[(size_t)k * Tp + t] == v) g -= coef * adv_s[k];
-                out[v] = a.do_ctc ? __ldcg(out + v) + g : g;
-            }
-        }
-        PGASR_STAMP(dbg, 38);
-    } else {
-    if (togo) {
-        // per-frame advantages A_kt = G_kt - b_kt (baseline over the K samples of the frame), the loss term
-        // -sum_kt A_kt log p_t(pi_kt) and the gradient row (1/BK) (p_tv sum_k A_kt - sum_k A_kt [pi_kt = v])
-        double lt = 0.0;
-        for (int t = threadIdx.x; t < T; t += kThreads) {
-            float* row = ztile + (size_t)t * V;
-            if (t < Tb) {
-                const float lz = lz_s[t];
-                int sumGi = 0;
-                for (int k = 0; k < K; ++k) sumGi += (int)col_s[(size_t)k * Tc + t];
-                const float sumG = (float)sumGi;
-                auto adv_of = [&](int k) {
-                    const float G = (float)col_s[(size_t)k * Tc + t];
-                    float base = 0.0f;
-                    if (a.baseline_mode == PGASR_BASELINE_MEAN) base = sumG / (float)K;
-                    else if (a.baseline_mode == PGASR_BASELINE_LOO) base = K > 1 ? (sumG - G) / (float)(K - 1) : 0.0f;
-                    else if (a.baseline_mode == PGASR_BASELINE_VALUE) base = a.baseline_value;
-                    return G - base;
-                };
-                float sumA = 0.0f;
-                for (int k = 0; k < K; ++k) {
-                    const float A = adv_of(k);
-                    lt += -(double)A * (double)(row[samples_s[(size_t)k * Tp + t]] - lz);
-                    sumA += A;
-                }
-                if (dense) {
-                    const float sc = coef * sumA;
-                    for (int v = 0; v < V; ++v) row[v] = __expf(row[v] - lz) * sc;
-                } else {
-                    for (int v = 0; v < V; ++v) row[v] = 0.0f;
-                }
-                for (int k = 0; k < K; ++k) row[samples_s[(size_t)k * Tp + t]] -= coef * adv_of(k);
-            } else {
-                for (int v = 0; v < V; ++v) row[v] = 0.0f;
-            }
-        }
-        lt = warp_sum(lt);
-        __syncthreads();                                   // (warp_acc: the log-prob partial sums are consumed)
-        if (lane == 0) warp_acc[warp] = lt;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double tot = 0.0;
-            for (int w = 0; w < kWarps; ++w) tot += warp_acc[w];
-            a.loss_terms[b] = (float)tot;
-        }
-    } else
-    for (int t = threadIdx.x; t < T; t += kThreads) {
-        float* row = ztile + (size_t)t * V;
-        if (t < Tb) {
-            if (dense) {
-                float mx = -INFINITY, s = 0.0f;
-                for (int v = 0; v < V; ++v) mx = fmaxf(mx, row[v]);
-                for (int v = 0; v < V; ++v) s += __expf(row[v] - mx);
-                const float sc = dense_c / s;
-                for (int v = 0; v < V; ++v) row[v] = __expf(row[v] - mx) * sc;
-            } else {
-                for (int v = 0; v < V; ++v) row[v] = 0.0f;
-            }
-            for (int k = 0; k < K; ++k) row[samples_s[(size_t)k * Tp + t]] -= coef * adv_s[k];
-        } else {
-            for (int v = 0; v < V; ++v) row[v] = 0.0f;
-        }
-    }
-    __syncthreads();
-
-    PGASR_STAMP(dbg, 36);
-    // ---- P6: add the tile onto the CTC rows (or store it when there is no CTC term) ---------------
-    if (threadIdx.x == 0) {
-        if (a.do_ctc) {
-            const unsigned* flag = a.ctrl + 4 + b;
-            while (ld_acquire(flag) == 0u) __nanosleep(40);
-        }
-        draw_done_ticket(a, s_last);
-    }
-    __syncthreads();
-    PGASR_STAMP(dbg, 37);
-    if ((((size_t)T * V * 4) & 15) == 0) {
-        float4* d4 = reinterpret_cast<float4*>(dlog_u);
-        const float4* t4 = reinterpret_cast<const float4*>(ztile);
-        const int n4 = T * V / 4;
-        // In the CTA that drew the last ticket the last warp reduces the loss (three dependent L2 round trips) while
-        // the other warps share the pass among themselves, instead of after it.
-        const bool last = *s_last != 0u;
-        const int nt = last ? kThreads - 32 : kThreads;
-        if (last && warp == kWarps - 1) {
-            loss_reduce_and_rearm(a);
-        } else if (a.do_ctc) {
-            // eight L2 reads in flight per thread (one at a time, every pass waited out the full L2 latency)
-            for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * nt) {
-                float4 c[8];
+        if ((((size_t)T * V * 4) & 15) == 0) {
+            float4* d4 = reinterpret_cast<float4*>(dlog_u);
+            const float4* t4 = reinterpret_cast<const float4*>(ztile);
+            const int n4 = T * V / 4;
+            // In the CTA that drew the last ticket the last warp reduces the loss (three dependent L2 round trips) while
+            // the other warps share the pass among themselves, instead of after it.
+            const bool last = final_u && *s_last != 0u;
+            const int nt = last ? kThreads - 32 : kThreads;
+            if (last && warp == kWarps - 1) {
+                loss_reduce_and_rearm(a);
+            } else if (a.do_ctc) {
+                // eight L2 reads in flight per thread (one at a time, every pass waited out the full L2 latency)
+                for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * nt) {
+                    float4 c[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = i0 + u * nt;
-                    c[u] = i < n4 ? __ldcg(d4 + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                }
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * nt;
+                        c[u] = i < n4 ? __ldcg(d4 + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = i0 + u * nt;
-                    if (i < n4) {
-                        const float4 g = t4[i];
-                        d4[i] = make_float4(g.x + c[u].x, g.y + c[u].y, g.z + c[u].z, g.w + c[u].w);
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * nt;
+                        if (i < n4) {
+                            const float4 g = t4[i];
+                            d4[i] = make_float4(g.x + c[u].x, g.y + c[u].y, g.z + c[u].z, g.w + c[u].w);
+                        }
                     }
                 }
+            } else {
+                for (int i = threadIdx.x; i < n4; i += nt) d4[i] = t4[i];
             }
         } else {
-            for (int i = threadIdx.x; i < n4; i += nt) d4[i] = t4[i];
+            if (final_u && *s_last != 0u && warp == kWarps - 1) loss_reduce_and_rearm(a);    // (then it joins the pass)
+            for (int i = threadIdx.x; i < T * V; i += kThreads)
+                dlog_u[i] = a.do_ctc ? __ldcg(dlog_u + i) + ztile[i] : ztile[i];
         }
-    } else {
-        if (*s_last != 0u && warp == kWarps - 1) loss_reduce_and_rearm(a);    // (then it joins the pass)
-        for (int i = threadIdx.x; i < T * V; i += kThreads)
-            dlog_u[i] = a.do_ctc ? __ldcg(dlog_u + i) + ztile[i] : ztile[i];
+        PGASR_STAMP(dbg, 38);
+        }   // tile mode
+        __syncthreads();                                   // (the next utterance rewrites the tile)
     }
-    PGASR_STAMP(dbg, 38);
-    }   // tile mode
 }
 
 #ifdef PGASR_TIMING
@@ -931,7 +1052,12 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     const unsigned ticket = s_ticket;
     const unsigned n_ctc = a.do_ctc ? (unsigned)a.B : 0u;
     if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT, kBW>(a, (int)ticket, smem_raw, &s_last, &s_mbar);
-    else fused_pg_role<SPL / 2, kThreads, kStream>(a, (int)(ticket - n_ctc), smem_raw, &s_last, &s_mbar);
+    else {
+        // a PG CTA serves one utterance, or two (a.pg_pair: utterances 2j and 2j + 1)
+        const int j = (int)(ticket - n_ctc);
+        const int b0 = a.pg_pair ? 2 * j : j;
+        fused_pg_role<SPL / 2, kThreads, kStream>(a, b0, a.pg_pair ? min(2, a.B - b0) : 1, smem_raw, &s_last, &s_mbar);
+    }
 
 #ifdef PGASR_TIMING
     if (threadIdx.x == 0 && ticket < 2048) { g_cta_ns[ticket][0] = t_start; g_cta_ns[ticket][1] = gtime(); }
@@ -957,7 +1083,7 @@ static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) smem_set[dev] = smem;
     }
-    const int grid = (a.do_ctc ? a.B : 0) + (a.do_pg ? a.B : 0);
+    const int grid = (a.do_ctc ? a.B : 0) + (a.do_pg ? (a.pg_pair ? (a.B + 1) / 2 : a.B) : 0);
     static const bool no_pdl = getenv("PGASR_NO_PDL") != nullptr;     // (A/B measurements)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

@@ -165,7 +165,8 @@ static int step_check(const StepParams& q, const void* workspace, size_t workspa
 }
 
 // one step: one launch of the single-launch kernel when the shape fits, else the chain of stand-alone kernels
-static int step_one(const StepParams& q, const pgasr_step_io& io, uint64_t seed, void* workspace, cudaStream_t st) {
+static int step_one(const StepParams& q, const pgasr_step_io& io, uint64_t seed, void* workspace, cudaStream_t st,
+                    bool throughput = false) {
     if (!io.logits || !io.targets || !io.loss || !io.dlogits) return PGASR_ERR_INVALID_ARG;
     void* stream = reinterpret_cast<void*>(st);
     const int B = q.B, T = q.T, V = q.V, K = q.K, Lmax = q.Lmax;
@@ -180,7 +181,7 @@ static int step_one(const StepParams& q, const pgasr_step_io& io, uint64_t seed,
     a.dist = io.dist; a.nll = io.nll; a.samples = io.samples; a.to_go = io.to_go; a.r_pos = io.r_pos;
     if ((do_pg || do_ctc) && (cap & 1) && (!do_pg || (cap & 2))) {
         // one launch: heterogeneous CTAs (CTC role / PG role per utterance), see fused.cu
-        return fused_step(a, workspace, st);
+        return fused_step(a, workspace, st, throughput);
     }
     if (do_pg && q.reward_mode == PGASR_REWARD_ED_TO_GO) return PGASR_ERR_UNSUPPORTED;   // (single-launch kernel only)
     // long utterances: the PG role's tiles do not fit one SM -- the PG part runs as the chain of stand-alone
@@ -306,7 +307,7 @@ extern "C" int pgasr_pg_ctc_step_multi(const pgasr_step_io* steps, int n_steps, 
     for (int i = 0; i < n_steps; ++i) {
         const int l = i % nl;
         rc = step_one(q, steps[i], seed_base + steps[i].seed, reinterpret_cast<char*>(workspace) + (size_t)l * lane_bytes,
-                      l ? aux->stream[l - 1] : s0);
+                      l ? aux->stream[l - 1] : s0, nl > 1);
         if (rc) break;
     }
     for (int l = 1; l < nl; ++l) {                         // join, also after an error: the caller's stream stays the one order
