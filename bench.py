@@ -232,7 +232,8 @@ class Dist:
             raise RuntimeError("bench.py (impl ours) needs a CUDA device; there is no CPU fallback")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
-        if self.world > 1:
+        self.solo = bool(os.environ.get("PGASR_BENCH_NO_DIST"))      # diagnosis only: ranks run unsynchronised, rank 0 reports itself
+        if self.world > 1 and not self.solo:
             dist.init_process_group("nccl", device_id=self.dev)
         from pgasr_b200 import _native
         if not os.path.exists(_native.LIB_PATH):             # the library normally travels with the snapshot; else build it here
@@ -244,19 +245,19 @@ class Dist:
         assert _native.lib().pgasr_device_check() == 0, "not an sm_100 device"
 
     def barrier(self):
-        if self.world > 1:
+        if self.world > 1 and not self.solo:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
     def max_over_ranks(self, x):
-        if self.world > 1:
+        if self.world > 1 and not self.solo:
             t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             return float(t[0])
         return x
 
     def close(self):
-        if self.world > 1:
+        if self.world > 1 and not self.solo:
             self.dist.destroy_process_group()
 
 
