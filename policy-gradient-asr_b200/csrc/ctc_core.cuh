@@ -710,7 +710,14 @@ __device__ __forceinline__ void ctc_walk_tile(const float* tile, const int32_t* 
                                               GradRing<SPL, NB> ring, Barrier mid_barrier, float* pring = nullptr,
                                               int RSR = 0, int T = 0) {
     constexpr int kGroup = 32 * (1 + G);                  // this warp + its workers
-    constexpr int kWU = NB % 7 == 0 ? 7 : NB % 5 == 0 ? 5 : NB;   // frames per unrolled group
+    // frames per unrolled group of the second half: TWO.  Unrolling the whole batch (8 frames, ~3 KB of code) measured
+    // 3 % slower per step than groups of 4 or 2 (36.3 / 35.3 / 35.2 us): six code streams share the SM's instruction
+    // caches and the walkers showed instruction-fetch stalls (18 % of their second-half samples).
+#ifdef PGASR_WALK_UNROLL
+    constexpr int kWU = NB % PGASR_WALK_UNROLL == 0 ? PGASR_WALK_UNROLL : NB;
+#else
+    constexpr int kWU = NB % 2 == 0 ? 2 : NB % 7 == 0 ? 7 : NB;
+#endif
     const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;
     const int S = 2 * L + 1;
