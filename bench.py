@@ -54,13 +54,20 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=0, help="utterances per CPU step (0: same as --batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--w-pg", type=float, default=None, help="diagnosis: override the PG weight (0 drops the PG role)")
+    ap.add_argument("--w-ctc", type=float, default=None, help="diagnosis: override the CTC weight (0 drops the CTC role)")
     ap.add_argument("--python-loop", action="store_true", help="one functional.pg_ctc_step call per step (round-1 loop)")
     args = ap.parse_args()
     sh = SHAPES.get(args.config, SHAPES[1])
     for k in ("batch", "T", "V", "K", "L"):
         if not getattr(args, k):
             setattr(args, k, sh[k])
+    w_pg, w_ctc = args.w_pg, args.w_ctc
     args.w_pg, args.w_ctc = sh["w_pg"], sh["w_ctc"]
+    if w_pg is not None:
+        args.w_pg = w_pg
+    if w_ctc is not None:
+        args.w_ctc = w_ctc
     return args
 
 

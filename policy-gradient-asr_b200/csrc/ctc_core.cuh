@@ -1401,6 +1401,7 @@ __device__ __forceinline__ void ctc_aworker(bool kAlpha, int g, int Tb, int L, c
                 for (int jj = 0; jj < SPL / 4; ++jj) chk &= __double2hiint(av[r][jj].x) & __double2hiint(av[r][jj].y);
             named_bar_arrive(ring.bar_empty + buf + (chk == -1 ? 16 : 0), kGroup);   // (values are finite and >= 0: never -1)
         }
+#ifndef EXP_A_IDLE
         int wi[2][LPL];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -1426,6 +1427,9 @@ __device__ __forceinline__ void ctc_aworker(bool kAlpha, int g, int Tb, int L, c
             for (int j = 0; j < LPL; ++j) gp[j * 32] = wi[r][j];
 #endif
         }
+#else
+        asm volatile("" :: "d"(o[0][0].x), "d"(o[1][0].y), "r"(eo[0] + eo[1]), "d"(invZ0), "r"(E0), "r"(zlast ? 1 : 0), "l"(grow), "r"(gbuf) : "memory");
+#endif
         if (nb + 1 < nbatch) fetch();
         const bool last_of_block = bi == kBB - 1 || nb == nbatch - 1;
         if (last_of_block) {
@@ -1500,6 +1504,11 @@ __device__ __forceinline__ void ctc_bworker(bool kAlpha, int j, const float* til
         // ---- running integer sums over the class-ordered list: every entry's occupancy is replaced by the sum up to
         // and including it (load, add, store back to the same address: four instructions per label for 32 frames; a
         // version that stored only at class ends needed a compare, a select and two predicated instructions per entry)
+#ifdef EXP_B_IDLE
+        (void)prow; (void)gmul; (void)valid; (void)fx; (void)el_s; (void)cl_s; (void)ntrips;
+        if (it > 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        __syncwarp();
+#else
         int acc = 0;
         unsigned E[3][8];
         int X[3][8];
@@ -1578,6 +1587,7 @@ __device__ __forceinline__ void ctc_bworker(bool kAlpha, int j, const float* til
                     asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(srow + 4u * (unsigned)(v0 + u)), "f"(gval) : "memory");
             }
         }
+#endif
         // (the executing threads' shared-memory writes -> visible to the bulk-copy engine)
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();

@@ -37,6 +37,18 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 
 constexpr int kFusedMaxK = 64;
 
+#ifdef PGASR_TIMING
+static __device__ unsigned long long g_cta_ns[2048][3];          // per ticket: start, role end, exit (globaltimer ns)
+// per role (0 CTC, 1 PG), summed over every CTA since the last reset: CTAs, ns at the grid-dependency wait, ns from
+// there to the exit, ns a PG CTA spent waiting for CTC flags -- what a CTA costs in SM time when steps overlap
+static __device__ unsigned long long g_role_ns[2][4];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
+#endif
+
 // one bulk copy global -> shared memory, completion on an mbarrier (see fused.cu for the measured A/B)
 __device__ __forceinline__ void bulk_load_tile(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -100,6 +112,18 @@ __device__ __forceinline__ int cdf_count32(const float (&c)[32], float tau) {
     return (b4 ? 16 : 0) + (b3 ? 8 : 0) + (b2 ? 4 : 0) + (b1 ? 2 : 0) + (b0 ? 1 : 0);
 }
 
+// One level of the binary search over a CDF row in shared memory, four draws side by side: off[u] is the row's
+// shared-memory address plus four times the count so far (plain asm: free to be scheduled, ordered by the address).
+template <int H>
+__device__ __forceinline__ void cdf_search_step(unsigned (&off)[4], const float (&tau)[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        float cv;
+        asm("ld.shared.f32 %0, [%1+%2];\n" : "=f"(cv) : "r"(off[u]), "n"(4 * (H - 1)));
+        off[u] += cv <= tau[u] ? 4u * H : 0u;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ CTC role
 // warp 0: alpha recurrence, warp 1: beta recurrence; every other warp is a gradient worker, even warps on the
 // alpha side, odd warps on the beta side (G = (warps - 2) / 2 per direction).
@@ -116,6 +140,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     constexpr int kMidThreads = 32 * (2 + 2 * G);
     const int warp = threadIdx.x >> 5;
     const int T = a.T, V = a.V;
+    PGASR_STAMP(b == 0 && threadIdx.x == 0, 6);
     // floats per tile row.  Block workers read and write the tile with a lane per FRAME, so consecutive rows must
     // fall into different banks: an odd stride with at least one zero slot after the V classes
     const int RS = kBW ? ((V + 1) | 1) : ctc_row_stride_f32(V);
@@ -168,6 +193,13 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     float* bw_stage = reinterpret_cast<float*>(bw_done + 2 * kBwGB);    // [2][kBwGB][32 frames][32]
     // The transcript and the lengths may live in mapped HOST memory (pgasr_host_*: a PCIe round trip per dependent
     // access), so everything is fetched here in one go and the transcript is used from shared memory afterwards.
+    // the whole logits tile as one bulk load, issued before anything is known about the utterance's length (rows beyond it
+    // are loaded and never used): the load then flies while the lengths and the transcript arrive
+    const size_t stage_bytes = 2 * grad_ring_bytes<SPL, kNB>() + gam_bytes;
+    const int stage_chunk = (int)(stage_bytes / ((size_t)V * 4)) & ~3;
+    const bool early_bulk = a.bulk_tile && stage_chunk >= T;
+    if (early_bulk && threadIdx.x == 0)
+        bulk_load_tile(stage_base, a.logits + (size_t)b * T * V, (unsigned)((size_t)T * V * 4), s_mbar);
     for (int i = threadIdx.x; i < a.Lmax; i += kThreads) lab_s[i] = a.targets[(size_t)b * a.Lmax + i];
     int Tb = a.in_len ? a.in_len[b] : T;
     Tb = min(max(Tb, 0), T);
@@ -178,6 +210,7 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     PGASR_STAMP(b == 0 && threadIdx.x == 0, 0);
     for (int i = Tb * V + threadIdx.x; i < T * V; i += kThreads) dlog_u[i] = 0.0f;
     if (Tb == 0) {
+        if (early_bulk) mbar_wait(s_mbar, 0u);             // (nothing may still be landing in shared memory when the CTA ends)
         if (threadIdx.x == 0) *nll_u = L == 0 ? 0.0f : INFINITY;
     } else {
         ring_a.dbg = ring_b.dbg = (b == 0);
@@ -190,15 +223,13 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         const float* lg = a.logits + (size_t)b * T * V;
         {
             float* stage = reinterpret_cast<float*>(stage_base);
-            const size_t stage_bytes = 2 * grad_ring_bytes<SPL, kNB>() + gam_bytes;
-            const int chunk = (int)(stage_bytes / ((size_t)V * 4)) & ~3;
+            const int chunk = stage_chunk;
             const bool al16 = (((size_t)T * V * 4) & 15) == 0;
             for (int c0 = 0; c0 < Tb; c0 += chunk) {
                 const int n = min(chunk, Tb - c0);
                 const float* src = lg + (size_t)c0 * V;
-                const bool bulk = a.bulk_tile && c0 == 0 && n == Tb && ((n * V * 4) & 15) == 0;
+                const bool bulk = early_bulk;              // (then the one chunk is the whole utterance)
                 if (bulk) {
-                    if (threadIdx.x == 0) bulk_load_tile(stage, src, (unsigned)(n * V * 4), s_mbar);
                 } else if (al16) {
                     const int n16 = n * V / 4, rem = n * V - n16 * 4;
                     for (int i = threadIdx.x; i < n16; i += kThreads)
@@ -294,18 +325,36 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
         if constexpr (kBW) {
             // even warps serve alpha, odd warps beta; w = warp / 2 is the warp's number within its direction: 0 the
             // walker, odd w the A-workers (scheduler partitions 2 / 3), even w the B-workers (the walker's partition)
+#if defined(PGASR_ROLE_MAP) && PGASR_ROLE_MAP == 1
+            // (A/B) both walkers on partition 0, the four B-workers on partition 1, A-workers on 2 / 3
+            const int pp = warp & 3, ii = warp >> 2;
+            const bool al = pp == 0 ? ii == 0 : pp == 1 ? ii < 2 : pp == 2;
+            const bool walker = pp == 0 && ii < 2;
+            const int bj = pp == 1 ? (ii & 1) : -1;
+            const int ga = pp >= 2 ? ii : -1;
+#elif defined(PGASR_ROLE_MAP) && PGASR_ROLE_MAP == 2
+            // (A/B) walkers on partitions 0 / 1 as usual, but each walker shares its partition with the OTHER direction's B-workers
+            const int w0 = warp >> 1;
+            const bool isb = !(w0 & 1) && w0 >= 2 && (w0 >> 1) - 1 < kBwGB;
+            const bool al = isb ? (warp & 1) : !(warp & 1);
+            const bool walker = warp < 2;
+            const int bj = isb ? (w0 >> 1) - 1 : -1;
+            const int ga = (w0 & 1) ? (w0 >> 1) : -1;
+#else
             const bool al = !(warp & 1);
             const int w = warp >> 1;
+            const bool walker = warp < 2;
+            const int bj = (!(w & 1) && w >= 2 && (w >> 1) - 1 < kBwGB) ? (w >> 1) - 1 : -1;
+            const int ga = (w & 1) ? (w >> 1) : (kBwGA == 5 && w == 6) ? 4 : -1;
+#endif
             const int dirx = al ? 0 : 1;
             int* gam_d = bw_gam + dirx * (kBwGB * 16 * SPL * 32);
             unsigned long long* done_d = bw_done + dirx * kBwGB;
             const int bar_g = al ? 10 : 13;
-            const int bj = (!(w & 1) && w >= 2 && (w >> 1) - 1 < kBwGB) ? (w >> 1) - 1 : -1;
-            const int ga = (w & 1) ? (w >> 1) : (kBwGA == 5 && w == 6) ? 4 : -1;
             const unsigned* list_w = bw_lists + (dirx * kBwGB + max(bj, 0)) * kBwListWords;
-            if (warp == 0)
+            if (walker && al)
                 ctc_walk_tile<SPL, kBwGA, true, false, kBwNB>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_a, mid);
-            else if (warp == 1)
+            else if (walker)
                 ctc_walk_tile<SPL, kBwGA, false, false, kBwNB>(tile, lab_u, Tb, L, V, RS, a.blank, nll_u, lat_u, exp_u, ring_b, mid);
             else if (bj >= 0)
                 ctc_bworker<SPL>(al, bj, tile, RS, Tb, V, a.blank, gs, dlog_u, al ? ring_a.norm : ring_b.norm, done_d, bar_g,
@@ -331,11 +380,25 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
     }
     __threadfence();                                       // rows and nll visible device-wide before the flag
     __syncthreads();
+#ifdef PGASR_TIMING
+    // (a clock64 right behind the barrier would execute before the barrier releases, BAR.SYNC.DEFER_BLOCKING: take it
+    // behind a shared-memory load)
+    if (b == 0 && threadIdx.x == 0) { const unsigned x = *reinterpret_cast<volatile unsigned*>(s_last); asm volatile("" ::"r"(x) : "memory"); }
+#endif
     PGASR_STAMP(b == 0 && threadIdx.x == 0, 3);
+    // Thread 0's chain here is what every other warp of the CTA -- and the SM -- waits for (measured: 5.8 k cycles with a
+    // release store, a second fence, the ticket and the nll copy one after the other).  One fence orders the CTA's rows, nll
+    // and loss term before BOTH the flag and the ticket: the fence inside st.release, with the ticket behind it in program
+    // order.  Flag store and ticket may then become visible in either order, which is fine: the last ticket of the grid
+    // (whose CTA re-arms the flags) is drawn after this utterance's PG CTA drew its own, and that CTA has read the flag by
+    // then.  Without a PG role nobody reads the flag: it is not set at all.  The caller's nll copy rides on another warp.
+    if (threadIdx.x == 32 && a.nll) a.nll[b] = *nll_u;     // (possibly host memory; the loss reads nll_ws)
     if (threadIdx.x == 0) {
-        st_release(a.ctrl + 4 + b, 1u);
-        draw_done_ticket(a, s_last);
-        if (a.nll) a.nll[b] = *nll_u;                      // the caller's copy (possibly host memory); the loss reads nll_ws
+        if (a.do_pg) st_release(a.ctrl + 4 + b, 1u);
+        else __threadfence();
+        PGASR_STAMP(b == 0, 9);
+        *s_last = atomicAdd(a.ctrl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+        PGASR_STAMP(b == 0, 7);
     }
 }
 
@@ -513,7 +576,7 @@ __device__ void fused_pg_role(const FusedArgs& a, int b0, int nutt, unsigned cha
                     if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)ti * (1.0 / 524288.0);   // across passes and warps in fp64: log p ~ -1000
                 }
             };
-            if (a.cdf_smem) {
+            if (!kStream && a.cdf_smem) {
                 // The CDF row of the frame in shared memory (33 floats: odd stride, a thread's walk along its row never
                 // collides with its neighbours'), built and searched by ROLLED loops: the fully unrolled register version
                 // is ~2000 straight-line instructions per thread, and with every warp streaming through them once the phase
@@ -543,50 +606,90 @@ __device__ void fused_pg_role(const FusedArgs& a, int b0, int nutt, unsigned cha
                     if (togo) lz_s[t] = mx + logS;
                 }
                 PGASR_STAMP(dbg && t0 == 0, 60);
+                // four draws (one Philox block) side by side.  The loop is instantiated per source of the uniforms and per
+                // "K is a multiple of four", so that its body is ONE basic block: with the run-time tests inside it the
+                // compiler recomputed the frame's row address for every draw (11 instructions per z[pi]) and kept a
+                // branch per draw (~90 instructions per draw, now ~70).  The search walks a BYTE offset (the count is the
+                // offset / 4); the 32 log-prob terms of a warp and draw are summed by one redux in 2^-19 fixed point (a
+                // term lies in [-92, 0]: the sum fits an int32) and kept by lane k of the warp until the end of the pass.
+                // Shared-memory addresses are taken once, as opaque 32-bit values: the role is compiled against the CTA's
+                // 128-register cap and the compiler otherwise REMATERIALISES them per draw (window base, padded row stride,
+                // even the thread index) rather than hold them.  Frames beyond T (last pass) store to the unused 33rd entry
+                // of the thread's CDF row with stride 0, so the stores need no branch.
+                unsigned cr32 = (unsigned)__cvta_generic_to_shared(cr);
+                unsigned z32 = (unsigned)__cvta_generic_to_shared(z);
+                unsigned s32 = t < T ? (unsigned)__cvta_generic_to_shared(samples_s + t) : cr32 + 128u;
+                unsigned sstr = t < T ? (unsigned)Tp : 0u;
+                asm volatile("mov.u32 %0, %0;\n mov.u32 %1, %1;\n mov.u32 %2, %2;\n mov.u32 %3, %3;\n"
+                             : "+r"(cr32), "+r"(z32), "+r"(s32), "+r"(sstr) : : "memory");   // (after the row's stores above)
+                auto draw_loop = [&](auto ph_tag, auto full_tag) {
+                    constexpr bool kPh = decltype(ph_tag)::value, kFullK = decltype(full_tag)::value;
+                    int acc = 0;                              // lane k & 31: sum of draw k's terms over the warp's frames
+                    auto flush = [&](int base) {              // across passes and warps in fp64: log p ~ -1000
+                        if (base + lane < K) warp_acc[warp * kFusedMaxK + base + lane] += (double)acc * (1.0 / 524288.0);
+                        acc = 0;
+                    };
+                    unsigned sk = s32;                        // running address of samples_s[k0][t]
 #pragma unroll 1
-                for (int k0 = 0; k0 < K; k0 += 4) {           // four draws (one Philox block) side by side
-                    float term[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    int pi[4] = {0, 0, 0, 0};
-                    if (live) {
-                        float tau[4];
-                        uint4 rnd = make_uint4(0, 0, 0, 0);
-                        if (!a.uniforms)
-                            rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k0 >> 2), 0x50474153u), key);
+                    for (int k0 = 0; k0 < K; k0 += 4) {
+                        if (k0 == 32) flush(0);               // (K > 32: the lanes take the second 32 draws)
+                        float term[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                        int pi[4] = {0, 0, 0, 0};
+                        if (live) {
+                            float tau[4];
+                            if constexpr (kPh) {
+                                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)b, (uint32_t)(k0 >> 2), 0x50474153u), key);
+                                tau[0] = __fmul_rn(u32_to_uniform(rnd.x), S);
+                                tau[1] = __fmul_rn(u32_to_uniform(rnd.y), S);
+                                tau[2] = __fmul_rn(u32_to_uniform(rnd.z), S);
+                                tau[3] = __fmul_rn(u32_to_uniform(rnd.w), S);
+                            } else {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float un;
-                            if (a.uniforms) un = k0 + u < K ? __ldg(a.uniforms + ((size_t)b * K + k0 + u) * T + t) : 0.0f;
-                            else un = u32_to_uniform(u == 0 ? rnd.x : u == 1 ? rnd.y : u == 2 ? rnd.z : rnd.w);
-                            tau[u] = __fmul_rn(un, S);
-                        }
-                        int cnt[4] = {0, 0, 0, 0};            // #{v < 32 : cdf[v] <= tau}, the CDF is non-decreasing
-#pragma unroll
-                        for (int h = 16; h > 0; h >>= 1)
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) cnt[u] += cr[cnt[u] + h - 1] <= tau[u] ? h : 0;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            pi[u] = min(cnt[u], V - 1);
-                            term[u] = k0 + u < K ? (z[pi[u]] - mx) - logS : 0.0f;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int k = k0 + u;
-                        if (k < K) {                          // (warp uniform)
-                            if (t < T) {
-                                samples_s[(size_t)k * Tp + t] = (uint8_t)pi[u];
-                                if (a.samples) a.samples[((size_t)b * K + k) * T + t] = (uint8_t)pi[u];
+                                for (int u = 0; u < 4; ++u) {
+                                    const float un = (kFullK || k0 + u < K) ? __ldg(a.uniforms + ((size_t)b * K + k0 + u) * T + t) : 0.0f;
+                                    tau[u] = __fmul_rn(un, S);
+                                }
                             }
-                            const int ti = __reduce_add_sync(kFull, __float2int_rn(term[u] * 524288.0f));
-                            if (lane == 0) warp_acc[warp * kFusedMaxK + k] += (double)ti * (1.0 / 524288.0);
+                            unsigned off[4] = {cr32, cr32, cr32, cr32};   // row address + 4 #{v < 32 : cdf[v] <= tau} (non-decreasing CDF)
+                            cdf_search_step<16>(off, tau); cdf_search_step<8>(off, tau); cdf_search_step<4>(off, tau);
+                            cdf_search_step<2>(off, tau);  cdf_search_step<1>(off, tau);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                pi[u] = min((int)((off[u] - cr32) >> 2), V - 1);
+                                float zv;
+                                asm("ld.shared.f32 %0, [%1];\n" : "=f"(zv) : "r"(z32 + 4u * (unsigned)pi[u]));
+                                term[u] = (kFullK || k0 + u < K) ? (zv - mx) - logS : 0.0f;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int k = k0 + u;
+                            if (kFullK || k < K) {                // (warp uniform)
+                                asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(sk), "r"(pi[u]));
+                                sk += sstr;
+                                const int ti = __reduce_add_sync(kFull, __float2int_rn(term[u] * 524288.0f));
+                                acc += lane == (k & 31) ? ti : 0;
+                            }
                         }
                     }
+                    flush(K > 32 ? 32 : 0);
+                };
+                using std::true_type; using std::false_type;
+                if (a.uniforms) {
+                    if ((K & 3) == 0) draw_loop(false_type{}, true_type{}); else draw_loop(false_type{}, false_type{});
+                } else {
+                    if ((K & 3) == 0) draw_loop(true_type{}, true_type{}); else draw_loop(true_type{}, false_type{});
                 }
             } else if (V <= 32) sample_frame(std::integral_constant<int, 32>{});
             else sample_frame(std::integral_constant<int, 64>{});
         }
         __syncthreads();
+        if (!kStream && a.cdf_smem && a.samples) {         // (that path keeps the draw loop free of global stores)
+            for (int i = threadIdx.x; i < K * T; i += kThreads) {
+                const int k = i / T, tt = i - k * T;
+                a.samples[((size_t)b * K + k) * T + tt] = samples_s[(size_t)k * Tp + tt];
+            }
+        }
 
         PGASR_STAMP(dbg, 32);
     }
@@ -973,7 +1076,13 @@ __device__ void fused_pg_role(const FusedArgs& a, int b0, int nutt, unsigned cha
         if (threadIdx.x == 0) {
             if (a.do_ctc) {
                 const unsigned* flag = a.ctrl + 4 + b;
+#ifdef PGASR_TIMING
+                const unsigned long long f0 = gtime();
+#endif
                 while (ld_acquire(flag) == 0u) __nanosleep(40);
+#ifdef PGASR_TIMING
+                atomicAdd(&g_role_ns[1][3], gtime() - f0);
+#endif
             }
             if (final_u) draw_done_ticket(a, s_last);
         }
@@ -1021,19 +1130,15 @@ __device__ void fused_pg_role(const FusedArgs& a, int b0, int nutt, unsigned cha
     }
 }
 
-#ifdef PGASR_TIMING
-static __device__ unsigned long long g_cta_ns[2048][3];          // per ticket: start, role end, exit (globaltimer ns)
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-    return t;
-}
-#endif
 
 template <int SPL, int kThreads, bool kGT, bool kStream, bool kBW = false>
 __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_ticket, s_last;
+#ifdef PGASR_TIMING
+    __shared__ long long s_clk[2];                          // clock64 at CTA start and after the grid-dependency wait
+    if (threadIdx.x == 0) s_clk[0] = clock64();
+#endif
     __shared__ __align__(8) unsigned long long s_mbar;      // completion of the bulk tile load (a.bulk_tile)
     if (threadIdx.x == 0 && a.bulk_tile) {
         mbar_init(&s_mbar, 1);
@@ -1049,6 +1154,11 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     // has completed and flushed.  The next launch may start as soon as every CTA of this grid got here.
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+#ifdef PGASR_TIMING
+    const unsigned long long t_go = gtime();
+    if (threadIdx.x == 0) s_clk[1] = clock64();
+    if (threadIdx.x == 0 && s_ticket == 0) { g_dbg[4] = s_clk[0]; g_dbg[5] = s_clk[1]; }
+#endif
     const unsigned ticket = s_ticket;
     const unsigned n_ctc = a.do_ctc ? (unsigned)a.B : 0u;
     if (ticket < n_ctc) fused_ctc_role<SPL, kThreads, kGT, kBW>(a, (int)ticket, smem_raw, &s_last, &s_mbar);
@@ -1068,7 +1178,14 @@ __global__ void __launch_bounds__(kThreads, 1) pg_ctc_fused_kernel(const FusedAr
     __syncthreads();
     if (s_last && threadIdx.x < 32 && (ticket < n_ctc || kStream)) loss_reduce_and_rearm(a);
 #ifdef PGASR_TIMING
+    if (threadIdx.x == 0 && ticket == 0) g_dbg[8] = clock64();
     if (threadIdx.x == 0 && ticket < 2048) g_cta_ns[ticket][2] = gtime();
+    if (threadIdx.x == 0) {
+        const int role = ticket < n_ctc ? 0 : 1;
+        atomicAdd(&g_role_ns[role][0], 1ull);
+        atomicAdd(&g_role_ns[role][1], t_go - t_start);
+        atomicAdd(&g_role_ns[role][2], gtime() - t_go);
+    }
 #endif
 }
 

@@ -13,6 +13,15 @@ extern "C" __attribute__((visibility("default"))) int pgasr_debug_cta_times(unsi
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(host, pgasr::g_cta_ns, sizeof(unsigned long long) * 3 * n) == cudaSuccess ? 0 : -5;
 }
+extern "C" __attribute__((visibility("default"))) int pgasr_debug_role_times(unsigned long long* host8, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(host8, pgasr::g_role_ns, sizeof(unsigned long long) * 8) != cudaSuccess) return -5;
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(pgasr::g_role_ns, z, sizeof(z));
+    }
+    return 0;
+}
 extern "C" __attribute__((visibility("default"))) int pgasr_debug_read(long long* host64, int reset) {
     cudaDeviceSynchronize();
     if (cudaMemcpyFromSymbol(host64, pgasr::g_dbg, sizeof(long long) * 64) != cudaSuccess) return -5;

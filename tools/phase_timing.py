@@ -31,6 +31,8 @@ for mode, (wp, wc) in {"both": (1.0, 1.0), "ctc": (0.0, 1.0), "pg": (1.0, 0.0)}.
     print(f"== {mode} (cycles)")
     if wc:
         print(f" ctc: zero-rows {d[1]-d[0]}  softmax-tile {d[2]-d[1]}  lattice+grad {d[3]-d[2]}  total {d[3]-d[0]}")
+        print(f" ctc CTA outside the role's stamps: start->grid-dependency wait passed {d[5]-d[4]}  ->role entry {d[6]-d[5]}  ->transcript and lengths in {d[0]-d[6]}"
+              f"  | flag {d[9]-d[3]}  done ticket {d[7]-d[9]}  ->exit {d[8]-d[7]}  | CTA total {d[8]-d[4]}")
         print(f" walker start after the tile barrier: alpha +{d[10]-d[2]}  beta +{d[14]-d[2]}   mid barrier passed at: alpha +{d[12]-d[2]}  beta +{d[16]-d[2]}")
         print(f" alpha walker: first-half {d[11]-d[10]}  mid-wait {d[12]-d[11]}  second-half {d[13]-d[12]}")
         print(f" beta  walker: first-half {d[15]-d[14]}  mid-wait {d[16]-d[15]}  second-half {d[17]-d[16]}")
@@ -87,3 +89,32 @@ for name, sl in (("CTC role CTAs", slice(0, B)), ("PG role CTAs", slice(B, n))):
     x = t[sl]
     dur = x[:, 1] - x[:, 0]
     print(f" overlapped steps, {name}: role duration median {np.median(dur):6.1f} us  min {dur.min():6.1f}  max {dur.max():6.1f}")
+
+# SM time per CTA in the steady state of overlapped steps (timing build: per-role sums over every CTA of a long run)
+if hasattr(lib, "pgasr_debug_role_times"):
+    r8 = (ctypes.c_ulonglong * 8)()
+    NS = 32                                                # steps per call: fill and drain are ~3 % of a call
+    q = F.StepQueue([batches[i % 8] for i in range(NS)], K=16)
+    for rep in range(6):
+        q.run(first=0, n=NS, seed=10 + rep)
+    lib.pgasr_debug_role_times(r8, 1)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    nrep = 12
+    for rep in range(nrep):
+        q.run(first=0, n=NS, seed=20 + rep)
+    ev1.record()
+    torch.cuda.synchronize()
+    lib.pgasr_debug_role_times(r8, 0)
+    r = list(r8)
+    us_step = ev0.elapsed_time(ev1) * 1e3 / (NS * nrep)
+    print(f" steady state, {NS * nrep} overlapped steps: {us_step:.2f} us per step")
+    tot = 0.0
+    for i, name in enumerate(("CTC", "PG")):
+        n_, w_, a_, f_ = r[4 * i:4 * i + 4]
+        if n_:
+            print(f"   {name} CTAs: {n_ / (NS * nrep):.0f} per step, at the grid-dependency wait {w_ / n_ / 1e3:6.2f} us, "
+                  f"active {a_ / n_ / 1e3:6.2f} us" + (f" (of which waiting for CTC flags {f_ / n_ / 1e3:6.2f} us)" if i else ""))
+            tot += (w_ + a_) / (NS * nrep) / 1e3
+    print(f"   SM time per step {tot:.0f} us = {tot / 148:.2f} us x 148 SMs")
