@@ -730,17 +730,30 @@ __device__ void fused_pg_role(const FusedArgs& a, int b0, int nutt, unsigned cha
         for (int k = warp; k < K; k += kWarps) {
             const uint8_t* in = samples_s + (size_t)k * Tp;
             uint8_t* o = hyp_s + (size_t)k * Tp;
-            int base = 0, carry = -1;
-            for (int t0 = 0; t0 < Tb; t0 += 32) {
-                const int t = t0 + lane;
-                const int x = t < Tb ? (int)in[t] : -2;
-                int p = __shfl_up_sync(kFull, x, 1);
-                if (lane == 0) p = carry;
-                const bool keep = t < Tb && x != p && x != a.blank;
-                const unsigned mask = __ballot_sync(kFull, keep);
-                if (keep) o[base + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)x;
-                base += __popc(mask);
-                carry = __shfl_sync(kFull, x, 31);
+            // four 32-frame chunks at a time; a frame's predecessor comes from shared memory, not from a shuffle with a carry
+            // into the next chunk, so the chunks are independent up to the running output position (a chunk was a chain of
+            // load -> shuffle -> vote -> popc -> store, ~100 cycles, sixteen of them in a row)
+            int base = 0;
+            const unsigned lt = (1u << lane) - 1u;
+            for (int t0 = 0; t0 < Tb; t0 += 128) {
+                int x[4];
+                bool keep[4];
+                unsigned mask[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u + lane;
+                    const bool in_u = t < Tb;
+                    x[u] = in_u ? (int)in[t] : -2;
+                    const int pv = (in_u && t > 0) ? (int)in[t - 1] : -1;
+                    keep[u] = in_u && x[u] != pv && x[u] != a.blank;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) mask[u] = __ballot_sync(kFull, keep[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (keep[u]) o[base + __popc(mask[u] & lt)] = (uint8_t)x[u];
+                    base += __popc(mask[u]);
+                }
             }
             if (lane == 0) hlen_s[k] = base;
             __syncwarp();
