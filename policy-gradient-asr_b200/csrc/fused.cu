@@ -155,6 +155,12 @@ int fused_step(FusedArgs& a, void* workspace, cudaStream_t st, bool throughput) 
     a.bulk_tile = !no_bulk_tile && (((size_t)a.T * a.V * 4) & 15) == 0 && ((reinterpret_cast<uintptr_t>(a.logits) & 15) == 0);
     a.cdf_smem = 0;
     a.pg_pair = 0;
+    // Steps of a multi-step call run on three streams: a dependent launch then only brings the next step's CTAs onto SMs
+    // early, where they sit at the grid-dependency wait (2.4 us per CTA, measured) while another lane's CTAs could run.
+    // Measured on one box, 3 lanes: 34.75 / 34.54 us per step with it, 34.23 / 34.27 without (20-step region 36.26 / 35.97
+    // against 35.78 / 35.66).  Single steps keep it (back-to-back launches on one stream).  PGASR_PDL_THROUGHPUT=1: keep (A/B)
+    static const bool pdl_tp = getenv("PGASR_PDL_THROUGHPUT") != nullptr;
+    a.no_pdl = throughput && !pdl_tp;
     if (a.do_pg) {
         // two utterances per PG CTA (their edit distances side by side) when the step is one of several in flight and both
         // blocks fit: measured 39.3 -> 36.5 us per step overlapped, but 58 -> 63 us for a step on its own (the pair CTA

@@ -11,6 +11,7 @@ struct FusedArgs {
     float baseline_value, w_pg, w_ctc;
     int do_pg, do_ctc;
     int pg_pair;             // a PG CTA serves two utterances (their edit distances side by side); grid = B + ceil(B / 2)
+    int no_pdl;              // host side only: launch without programmatic stream serialisation (steps of a multi-step call)
     int bulk_tile;           // the roles' logits tiles arrive as ONE bulk copy (cp.async.bulk + mbarrier) instead of 16-byte cp.async
     int cdf_smem;            // PG role: the per-frame CDF rows live in shared memory ([T][33] fp32, V <= 32, tile mode) -- rolled
                              // loops and a binary search instead of 32 registers and a select tree (fused_impl.cuh P1)

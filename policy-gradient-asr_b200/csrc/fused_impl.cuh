@@ -340,6 +340,14 @@ __device__ void fused_ctc_role(const FusedArgs& a, int b, unsigned char* smem_ra
             const bool walker = warp < 2;
             const int bj = isb ? (w0 >> 1) - 1 : -1;
             const int ga = (w0 & 1) ? (w0 >> 1) : -1;
+#elif defined(PGASR_ROLE_MAP) && PGASR_ROLE_MAP == 3
+            // (A/B) per direction: partition 0 / 1 = walker, B-worker 0, A-worker 0, spare; partition 2 / 3 = A-workers 1..3
+            // and B-worker 1 (evens out the instruction load of the partitions: 99 / 87 per frame instead of 110 / 75)
+            const bool al = !(warp & 1);
+            const int w = warp >> 1;                   // 0..7 within the direction: partitions 0,2,0,2,0,2,0,2 (alpha)
+            const bool walker = w == 0;
+            const int bj = w == 2 ? 0 : w == 7 ? 1 : -1;
+            const int ga = w == 4 ? 0 : w == 1 ? 1 : w == 3 ? 2 : w == 5 ? 3 : -1;
 #else
             const bool al = !(warp & 1);
             const int w = warp >> 1;
@@ -730,30 +738,17 @@ __device__ void fused_pg_role(const FusedArgs& a, int b0, int nutt, unsigned cha
         for (int k = warp; k < K; k += kWarps) {
             const uint8_t* in = samples_s + (size_t)k * Tp;
             uint8_t* o = hyp_s + (size_t)k * Tp;
-            // four 32-frame chunks at a time; a frame's predecessor comes from shared memory, not from a shuffle with a carry
-            // into the next chunk, so the chunks are independent up to the running output position (a chunk was a chain of
-            // load -> shuffle -> vote -> popc -> store, ~100 cycles, sixteen of them in a row)
-            int base = 0;
-            const unsigned lt = (1u << lane) - 1u;
-            for (int t0 = 0; t0 < Tb; t0 += 128) {
-                int x[4];
-                bool keep[4];
-                unsigned mask[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int t = t0 + 32 * u + lane;
-                    const bool in_u = t < Tb;
-                    x[u] = in_u ? (int)in[t] : -2;
-                    const int pv = (in_u && t > 0) ? (int)in[t - 1] : -1;
-                    keep[u] = in_u && x[u] != pv && x[u] != a.blank;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) mask[u] = __ballot_sync(kFull, keep[u]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (keep[u]) o[base + __popc(mask[u] & lt)] = (uint8_t)x[u];
-                    base += __popc(mask[u]);
-                }
+            int base = 0, carry = -1;
+            for (int t0 = 0; t0 < Tb; t0 += 32) {
+                const int t = t0 + lane;
+                const int x = t < Tb ? (int)in[t] : -2;
+                int p = __shfl_up_sync(kFull, x, 1);
+                if (lane == 0) p = carry;
+                const bool keep = t < Tb && x != p && x != a.blank;
+                const unsigned mask = __ballot_sync(kFull, keep);
+                if (keep) o[base + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)x;
+                base += __popc(mask);
+                carry = __shfl_sync(kFull, x, 31);
             }
             if (lane == 0) hlen_s[k] = base;
             __syncwarp();
@@ -1224,7 +1219,7 @@ static int launch_fused(FusedArgs& a, size_t smem, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
+    cfg.numAttrs = (no_pdl || a.no_pdl) ? 0 : 1;
     PGASR_CUDA_TRY(cudaLaunchKernelEx(&cfg, pg_ctc_fused_kernel<SPL, kThreads, kGT, kStream, kBW>, a));
     ++g_launches;
     return PGASR_OK;
