@@ -171,7 +171,8 @@ PGASR_API int pgasr_pg_ctc_step(const float* logits, const int32_t* targets, con
  * while, to the caller, everything is ordered on `stream` as usual.  The extra streams and their events are created
  * on first use, one set per calling host thread and device, and live as long as the thread (together with the
  * control-block parity above this is all the state the library keeps).  PGASR_NO_OVERLAP=1 in the environment keeps
- * every step on `stream`.
+ * every step on `stream`.  The steps of a multi-step call are launched in plain stream order (no programmatic
+ * serialisation: with three lanes in flight it only parked the next step's CTAs on SMs another lane could use).
  * reward_mode PGASR_REWARD_ED_TO_GO (single-launch kernel with the logits tile in shared memory only; else
  * PGASR_ERR_UNSUPPORTED): to_go [B,K,T] int16 and r_pos [B,K,T] int8 (optional) receive the reward-to-go of every
  * frame and the per-position reward of every collapsed symbol (zero beyond hyp_len); rewards = len(ref) - ED.   */
