@@ -77,6 +77,22 @@ def algorithmic_bytes_per_utt(args):
     return 8 * T * V + 4 * L + 8 * K + 12 if args.w_pg else 8 * T * V + 4 * L + 4
 
 
+def algorithmic_ops(args, utt_per_s):
+    """algorithmic op counts per utterance next to the byte roofline (the path is bound by serial depth
+    and ALU work, not by bytes).  Hypothesis length: ~0.93 T for random logits, ~L for peaky ones (SURVEY's figures)."""
+    T, V, K, L = args.T, args.V, args.K, args.L
+    S = 2 * L + 1
+    lh = int(round(0.93 * T)) if args.regime == "random" else L
+    per = {}
+    if args.w_pg:
+        per.update({"sampler_exp": T * V, "sampler_cdf_compares_linear_scan": K * T * V, "sampler_draws": K * T,
+                    "levenshtein_cells": K * lh * L, "levenshtein_dependent_diagonals": lh + L - 1})
+    if args.w_ctc:
+        per.update({"ctc_state_updates_alpha_plus_beta": 2 * T * S, "ctc_dependent_frames": T})
+    rates = {k + "_per_s": v * utt_per_s for k, v in per.items() if "dependent" not in k}
+    return {"per_utterance": per, "achieved": rates, "hyp_len_assumed": lh if args.w_pg else None}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -430,6 +446,10 @@ def run_ours(args):
         }
         if cpu_ref:
             line["cpu_baseline_reference"] = cpu_ref
+        try:
+            line["algorithmic_ops"] = algorithmic_ops(args, value)
+        except Exception:                                   # (reporting only: never in the way of the line)
+            pass
         emit(line)
     D.close()
     return 0
