@@ -180,3 +180,22 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_algorithmic_ops_match_the_survey_figures():
+    """at T=500, V=30, K=16, L=100 the path is 15 k exponentials, 201 k lattice state updates over 500
+    dependent frames and K*L_h*L edit-distance cells per utterance; bench.py reports them times the measured rate."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = types.SimpleNamespace(T=500, V=30, K=16, L=100, regime="random", w_pg=1.0, w_ctc=1.0)
+    ops = bench.algorithmic_ops(a, 2.0)
+    per = ops["per_utterance"]
+    assert per["sampler_exp"] == 15000 and per["ctc_state_updates_alpha_plus_beta"] == 2 * 500 * 201
+    assert per["levenshtein_cells"] == 16 * ops["hyp_len_assumed"] * 100 and per["ctc_dependent_frames"] == 500
+    assert ops["achieved"]["sampler_exp_per_s"] == 30000.0 and "ctc_dependent_frames_per_s" not in ops["achieved"]
+    a.regime, a.w_pg = "peaky", 0.0
+    ops = bench.algorithmic_ops(a, 1.0)
+    assert "levenshtein_cells" not in ops["per_utterance"] and ops["hyp_len_assumed"] is None
